@@ -1,0 +1,106 @@
+/* qinco_b200 — C ABI of the B200-native QINCo / QINCo2 encode-decode path (libqinco_b200.so).
+ *
+ * The reference (facebookresearch/Qinco @ 5a324954) has no FFI: its boundary is a duck-typed PyTorch module.
+ * Each entry point below names the reference call it stands in for; the Python shim in qinco_b200/model.py and
+ * qinco_b200/codec.py rebuilds the reference's signatures on top of these (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - plain C types only; device buffers are raw CUDA device pointers, the stream is a cudaStream_t passed as void*
+ *   - every call returns 0 (QB_OK) or a negative qb_status; qb_last_error() returns a thread-local message
+ *   - the caller owns every buffer including the workspace; qb_encode / qb_decode are asynchronous on `stream`,
+ *     allocate nothing and never synchronise; the *_host variants stage through pinned memory and return when done
+ *   - a model handle is bound to one CUDA device and is not thread-safe
+ *   - codes are uint8 [n, M] row-major (vector-major).  The reference's layouts ([M, n] int64 for qinco.model,
+ *     [n, M] int64 for qinco_v1/codec_qinco.py) are produced at the Python edge.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with QB_ERR_CUDA
+ */
+#ifndef QINCO_B200_H_
+#define QINCO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qb_model qb_model;
+
+typedef enum {
+    QB_OK = 0,
+    QB_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+    QB_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+    QB_ERR_WORKSPACE = -3,   /* workspace too small */
+    QB_ERR_KERNEL = -4,      /* device-side protocol time-out or out-of-range code (err word in message) */
+    QB_ERR_NOMEM = -5
+} qb_status;
+
+/* Model weights, HOST pointers, fp32, row-major, PyTorch [out, in] convention — exactly the tensors of the
+ * reference state dict (qinco/model/qinco_base.py:229-260, 432-433):
+ *   steps.{m}.codebook.weight [K,D]; steps.{m}.substep.codebook.weight [K,D] (m>=1, A>0);
+ *   steps.{m}.concat.mlp.{weight [De,De+D], bias [De]}; steps.{m}.residual_blocks.{l}.{up_proj [Dh,De], down_proj [De,Dh]};
+ *   steps.{m}.in_proj [De,D] / out_proj [D,De] (only when De != D); data_mean [D]; data_std [].
+ * Arrays are indexed by step m (entry 0 of the MLP arrays is ignored; step 0 is a plain codebook,
+ * qinco_base.py:218,263) and up_w / down_w by m*L + l. */
+typedef struct {
+    int32_t D, De, Dh, L, M, K;
+    int32_t A;               /* pre-selected candidates per beam, 0 = all K (cfg.A) */
+    int32_t B;               /* beam width (cfg.B) */
+    int32_t qinco1_mode;     /* 1: no outer skip connection (cfg.qinco1_mode, qinco_base.py:276-278) */
+    int32_t device;          /* CUDA device ordinal */
+    const float* const* codebook;          /* [M] */
+    const float* const* substep_codebook;  /* [M] or NULL when A == 0 */
+    const float* const* concat_w;          /* [M] */
+    const float* const* concat_b;          /* [M] */
+    const float* const* up_w;              /* [M*L] */
+    const float* const* down_w;            /* [M*L] */
+    const float* const* in_proj;           /* [M] or NULL when De == D */
+    const float* const* out_proj;          /* [M] or NULL when De == D */
+    const float* data_mean;                /* [D] or NULL (zeros) */
+    float data_std;                        /* > 0 */
+    /* kernel planner overrides, 0 = automatic */
+    int32_t opt_hc, opt_n_hbuf, opt_slot_bytes, opt_max_stage, opt_max_slab_k;
+} qb_model_desc;
+
+int qb_version(void);
+const char* qb_last_error(void);
+
+/* Replaces constructing QINCo(cfg) + load_state_dict (+ QINCoInferenceWrapper.build, qinco_inference.py:290-330):
+ * packs the weights for the kernels (fp16 MMA operand slabs, fp32 tables) and uploads them. */
+int qb_model_create(const qb_model_desc* desc, qb_model** out);
+int qb_model_destroy(qb_model* m);
+
+/* Bytes of device workspace qb_encode / qb_decode want for n vectors (they process in internal chunks, so the value
+ * saturates; a smaller workspace still works as long as one 128-vector chunk fits). */
+size_t qb_encode_workspace_bytes(const qb_model* m, int64_t n);
+size_t qb_decode_workspace_bytes(const qb_model* m, int64_t n);
+
+/* Replaces QINCo.encode / QINCoInferenceWrapper.encode (qinco_base.py:454-485, qinco_inference.py:340-350) and, with
+ * normalize != 0, forward(x, step="encode") (qinco_base.py:532-534): x_dev [n, D] fp32 row-major ->
+ * codes_dev [n, M] uint8 and, if xhat_dev != NULL, the reconstruction [n, D] fp32 in NORMALISED space. */
+int qb_encode(qb_model* m, const float* x_dev, int64_t n, int normalize, uint8_t* codes_dev, float* xhat_dev,
+              void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Replaces QINCo.decode / QINCoInferenceWrapper.decode (qinco_base.py:447-452, qinco_inference.py:332-338) and, with
+ * denormalize != 0, forward(codes, step="decode") (qinco_base.py:536-537): codes_dev [n, M] uint8 -> out_dev [n, D]. */
+int qb_decode(qb_model* m, const uint8_t* codes_dev, int64_t n, int denormalize, float* out_dev, void* workspace_dev,
+              size_t workspace_bytes, void* stream);
+
+/* Host-buffer variants = the batch loops of qinco_v1/codec_qinco.py:25-46 and :54-72 (H2D, encode/decode, D2H per
+ * chunk, through pinned staging owned by the model).  xhat_host may be NULL. */
+int qb_encode_host(qb_model* m, const float* x_host, int64_t n, int normalize, uint8_t* codes_host, float* xhat_host);
+int qb_decode_host(qb_model* m, const uint8_t* codes_host, int64_t n, int denormalize, float* out_host);
+
+/* Introspection */
+int64_t qb_launch_count(const qb_model* m);      /* kernels launched by this model so far */
+int qb_model_info(const qb_model* m, int step, int32_t* out, int n_out); /* plan of step>=1: see qb_api.cu */
+
+/* Test hook: out[i] = xhat[i] + f_m(C_m[codes[i]], xhat[i]) for n independent rows of step `step` (>= 1), i.e. one
+ * QINCoStep.decode (qinco_base.py:282-290) through the production kernels.  Device pointers. */
+int qb_debug_step(qb_model* m, int step, const float* xhat_dev, const uint8_t* codes_dev, int64_t n, float* out_dev,
+                  void* workspace_dev, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QINCO_B200_H_ */

@@ -1,0 +1,91 @@
+// Device-side parameter blocks and launcher prototypes (qb_mlp.cu, qb_kernels.cu), used by qb_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "qb_plan.h"
+
+namespace qb {
+
+enum { QB_MODE_SCORE = 0, QB_MODE_APPLY = 1 };
+
+// One launch of the tcgen05 MLP kernel over `n_rows` candidate rows of step m.
+//   score: row -> beam b = row / C, slot a = row % C, code = A ? idx[b*A + a] : a;
+//          dist[row] = || r[b] - f_m(C_m[code], xhat_b) ||^2                       (qinco_base.py:329-345)
+//   apply: row -> vector v = row / F_out, b = v*F_in + parent[row], code = sel_code[row*code_stride + code_off];
+//          xhat_out[row] = (xhat_in[b] + f_m(C_m[code], xhat_in[b])) * out_scale + out_shift   (qinco_base.py:363-369,
+//          decode :282-290, :447-452)
+struct MlpParams {
+    QbStepPlan plan;
+    const QbOp* ops;          // device copy of the plan's op list
+    const uint8_t* w_blob;    // packed fp16 slabs of this step
+    const float* t_blk;       // [De/8][K][8]  T_m
+    const float* cb_blk;      // [D/8][K][8]   C_m (outer skip), unused in qinco1_mode
+    int32_t mode;
+    int32_t C, A;             // score
+    int32_t F_in, F_out;      // apply
+    int64_t n_rows;
+    const uint8_t* idx;       // score, A > 0: [n_beams, A]
+    const uint8_t* sel_parent;  // apply: [n_rows] or NULL (parent 0)
+    const uint8_t* sel_code;    // apply
+    int64_t code_stride;
+    int32_t code_off;
+    const float* u;           // [n_beams, De]
+    const float* r;           // score: [n_beams, D]
+    const float* xhat_in;     // apply: [n_beams, D]
+    float* dist;              // score: [n_rows]
+    float* xhat_out;          // apply: [n_rows, D]
+    float out_scale;          // apply
+    const float* out_shift;   // apply: [D] or NULL
+    uint32_t* err_flag;       // device word set non-zero when a barrier wait timed out
+};
+
+cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream);
+cudaError_t mlp_set_smem_attr(int smem_bytes);
+
+// Beam preparation for step m (CUDA cores, fp32), one row per (vector, beam) pair b:
+//   r[b] = xn[v] - xhat[b];  u[b] = Wx . xhat[b];  idx[b] = A smallest of ||r[b] - S_m[k]||^2   (qinco_base.py:114-121)
+// With step0 != 0 it is the first quantisation step instead (qinco_base.py:263, qinco_inference.py:239-246):
+//   xhat[v][j] = C_0[code_j], hist[v][j][0] = code_j for the n_sel nearest codewords of xn[v].
+struct PrepParams {
+    int32_t D, De, K, A;      // A: number of candidates to keep (step0: F_1)
+    int32_t F;                // beams per vector (row b -> v = b / F)
+    int32_t step0;
+    int32_t M;                // hist row length
+    int64_t n_beams;
+    const float* x;           // [n, D] raw input
+    const float* mean;        // [D] or NULL
+    float inv_std;
+    const float* xhat;        // [n_beams, D] (unused for step0)
+    const float* wx_t;        // [D][De]      (NULL: skip u)
+    const float* sub_cb;      // [K][D] pre-selection codebook (step0: C_0); NULL: skip selection
+    float* r;                 // [n_beams, D] or NULL
+    float* u;                 // [n_beams, De]
+    uint8_t* idx;             // [n_beams, A]
+    float* xhat_out;          // step0: [n, A, D]
+    uint8_t* hist_out;        // step0: [n, A, M]
+};
+cudaError_t launch_prep(const PrepParams& p, cudaStream_t stream);
+
+// Beam selection (qinco_base.py:346-372): per vector the F_out smallest of R = F_in*C distances, ascending;
+// writes parent beam, code and the extended code history.
+struct SelectParams {
+    int32_t F_in, F_out, C, A, M, m;   // m = index of this step (history length before it)
+    int64_t n;
+    const float* dist;        // [n, F_in*C]
+    const uint8_t* idx;       // [n*F_in, A] or NULL
+    const uint8_t* hist_in;   // [n, F_in, M]
+    uint8_t* hist_out;        // [n, F_out, M]
+    uint8_t* sel_parent;      // [n, F_out]
+    uint8_t* sel_code;        // [n, F_out]
+};
+cudaError_t launch_select(const SelectParams& p, cudaStream_t stream);
+
+// xhat[v] = C_0[codes[v*M]]  (decode start, qinco_base.py:447-452 with step 0 = plain codebook lookup)
+cudaError_t launch_decode_init(const float* cb0, const uint8_t* codes, int64_t n, int M, int D, int K, float* xhat,
+                               uint32_t* err_flag, cudaStream_t stream);
+// out[i] = in[i]*scale + shift[i % D]
+cudaError_t launch_affine(const float* in, float* out, int64_t n, int D, float scale, const float* shift,
+                          cudaStream_t stream);
+
+}  // namespace qb

@@ -1,0 +1,33 @@
+// Host-side declarations shared by the planner (qb_plan.cpp), the C-ABI (qb_api.cu) and the plan tests.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "qb_plan.h"
+
+namespace qb {
+
+struct PlanOptions {
+    int hc = 0;           // H chunk width (0 = auto)
+    int n_hbuf = 0;       // Hacc / A_H buffers (0 = auto)
+    int slot_bytes = 0;   // weight ring slot size (0 = 16 KiB)
+    int max_stage = 0;    // cap on ring depth (0 = 8)
+    int max_slab_k = 0;   // cap on slab K (0 = 128)
+    int smem_budget = 0;  // bytes of dynamic shared memory the kernel may use (0 = 220 KiB)
+};
+
+uint16_t f32_to_f16(float f);
+float f16_to_f32(uint16_t h);
+
+int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const PlanOptions& opt, QbStepPlan* plan,
+                   std::vector<QbOp>* ops, std::string* err);
+
+int pack_step_weights(const QbStepPlan& plan, const std::vector<QbOp>& ops, const float* const* up,
+                      const float* const* down, const float* out_proj, uint16_t* blob, std::string* err);
+
+void build_tables(int D, int De, int K, const float* codebook, const float* in_proj, const float* concat_w,
+                  const float* concat_b, float* t_blk, float* cb_blk, float* wx_t);
+
+}  // namespace qb

@@ -1,0 +1,225 @@
+// CUDA-core (fp32) kernels around the tcgen05 MLP: beam preparation / first step, beam selection, decode start.
+// These are <2 % of a step's arithmetic; they stay in exact fp32 so candidate pre-selection and the final ranking
+// see the same numbers as the reference's fp32 path.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "qb_dev.h"
+
+namespace qb {
+
+namespace {
+
+constexpr int kPrepThreads = 256;
+constexpr int kPrepRows = 16;   // (vector, beam) rows per block
+
+// lexicographic (value, index) minimum across the warp
+__device__ __forceinline__ void warp_argmin(float& v, int& i) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, off);
+        if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}
+
+// Reference: QincoSubstep.get_distances_for_codes / select_code_candidates (qinco_base.py:114-121), the hoisted
+// half of QConcat (:60-64: Wcat[:, De:] . xhat), and for step 0 QINCoInferenceEncoder.forward's first lines
+// (qinco_inference.py:239-246).
+__global__ void __launch_bounds__(kPrepThreads) qb_prep_kernel(const PrepParams p) {
+    extern __shared__ __align__(16) float sm[];
+    const int D = p.D, De = p.De, K = p.K;
+    float* xs = sm;                          // [kPrepRows][D]  xhat rows
+    float* rs = xs + kPrepRows * D;          // [kPrepRows][D]  residual rows
+    float* dpre = rs + kPrepRows * D;        // [kPrepRows][K]
+    const int tid = threadIdx.x;
+    const int64_t b0 = (int64_t)blockIdx.x * kPrepRows;
+    const int nrow = (int)min((int64_t)kPrepRows, p.n_beams - b0);
+
+    for (int t = tid; t < kPrepRows * D; t += kPrepThreads) {
+        const int i = t / D, d = t - i * D;
+        float xh = 0.f, r = 0.f;
+        if (i < nrow) {
+            const int64_t b = b0 + i;
+            const int64_t v = b / p.F;
+            float xn = p.x[v * D + d];
+            if (p.mean) xn -= p.mean[d];
+            xn *= p.inv_std;
+            if (!p.step0) xh = p.xhat[b * D + d];
+            r = xn - xh;
+            if (p.r) p.r[b * D + d] = r;
+        }
+        xs[t] = xh;
+        rs[t] = r;
+    }
+    __syncthreads();
+
+    if (p.wx_t) {   // u[b][e] = sum_d Wx[e][d] * xhat[b][d]
+        for (int e = tid; e < De; e += kPrepThreads) {
+            float acc[kPrepRows];
+#pragma unroll
+            for (int i = 0; i < kPrepRows; i++) acc[i] = 0.f;
+            for (int d = 0; d < D; d += 4) {
+                const float w0 = __ldg(p.wx_t + (size_t)(d + 0) * De + e), w1 = __ldg(p.wx_t + (size_t)(d + 1) * De + e);
+                const float w2 = __ldg(p.wx_t + (size_t)(d + 2) * De + e), w3 = __ldg(p.wx_t + (size_t)(d + 3) * De + e);
+#pragma unroll
+                for (int i = 0; i < kPrepRows; i++) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xs + i * D + d);
+                    acc[i] = fmaf(w0, xv.x, acc[i]); acc[i] = fmaf(w1, xv.y, acc[i]);
+                    acc[i] = fmaf(w2, xv.z, acc[i]); acc[i] = fmaf(w3, xv.w, acc[i]);
+                }
+            }
+            for (int i = 0; i < nrow; i++) p.u[(b0 + i) * De + e] = acc[i];
+        }
+    }
+
+    if (p.sub_cb) {   // dpre[i][k] = ||r_i - S[k]||^2 with S stored transposed [D][K]
+        for (int k = tid; k < K; k += kPrepThreads) {
+            float acc[kPrepRows];
+#pragma unroll
+            for (int i = 0; i < kPrepRows; i++) acc[i] = 0.f;
+            for (int d = 0; d < D; d += 4) {
+                const float s0 = __ldg(p.sub_cb + (size_t)(d + 0) * K + k), s1 = __ldg(p.sub_cb + (size_t)(d + 1) * K + k);
+                const float s2 = __ldg(p.sub_cb + (size_t)(d + 2) * K + k), s3 = __ldg(p.sub_cb + (size_t)(d + 3) * K + k);
+#pragma unroll
+                for (int i = 0; i < kPrepRows; i++) {
+                    const float4 rv = *reinterpret_cast<const float4*>(rs + i * D + d);
+                    const float e0 = rv.x - s0, e1 = rv.y - s1, e2 = rv.z - s2, e3 = rv.w - s3;
+                    acc[i] = fmaf(e0, e0, acc[i]); acc[i] = fmaf(e1, e1, acc[i]);
+                    acc[i] = fmaf(e2, e2, acc[i]); acc[i] = fmaf(e3, e3, acc[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kPrepRows; i++) dpre[i * K + k] = acc[i];
+        }
+        __syncthreads();
+        // the A smallest per row, ascending, ties to the lower index (torch.topk(largest=False) order)
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int i = warp; i < nrow; i += kPrepThreads / 32) {
+            const int64_t b = b0 + i;
+            float vals[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int k = lane + 32 * j;
+                vals[j] = k < K ? dpre[i * K + k] : FLT_MAX;
+            }
+            for (int a = 0; a < p.A; a++) {
+                float bv = FLT_MAX;
+                int bi = 0x7fffffff;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int k = lane + 32 * j;
+                    if (k < K && (vals[j] < bv || (vals[j] == bv && k < bi))) { bv = vals[j]; bi = k; }
+                }
+                warp_argmin(bv, bi);
+                if (bi >= K) bi = 0;   // all-NaN row: stay in range
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (lane + 32 * j == bi) vals[j] = FLT_MAX;
+                if (!p.step0) {
+                    if (lane == 0) p.idx[b * p.A + a] = (uint8_t)bi;
+                } else {
+                    // first step: beam a of vector b starts at codeword bi of C_0 (row-major copy in xhat = p.xhat)
+                    if (lane == 0) p.hist_out[(b * p.A + a) * p.M] = (uint8_t)bi;
+                    for (int d = lane; d < D; d += 32)
+                        p.xhat_out[(b * p.A + a) * D + d] = __ldg(p.xhat + (size_t)bi * D + d);
+                }
+            }
+        }
+    }
+}
+
+// Reference: dists.topk(F_out, largest=False) + the three gathers of QINCoStep.encode (qinco_base.py:346-372).
+__global__ void __launch_bounds__(256) qb_select_kernel(const SelectParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (v >= p.n) return;
+    const int R = p.F_in * p.C;
+    const float* dist = p.dist + v * R;
+    float last_v = -FLT_MAX;
+    int last_i = -1;
+    for (int j = 0; j < p.F_out; j++) {
+        float bv = FLT_MAX;
+        int bi = 0x7fffffff;
+        for (int i = lane; i < R; i += 32) {
+            const float d = dist[i];
+            const bool after = (d > last_v) || (d == last_v && i > last_i);
+            if (after && (d < bv || (d == bv && i < bi))) { bv = d; bi = i; }
+        }
+        warp_argmin(bv, bi);
+        if (bi >= R) bi = (last_i + 1 < R) ? last_i + 1 : 0;   // NaN / exhausted: stay in range
+        last_v = bv;
+        last_i = bi;
+        const int parent = bi / p.C, a = bi - parent * p.C;
+        const int code = p.idx ? (int)p.idx[(v * p.F_in + parent) * p.A + a] : a;
+        const int64_t o = v * p.F_out + j;
+        if (lane == 0) {
+            p.sel_parent[o] = (uint8_t)parent;
+            p.sel_code[o] = (uint8_t)code;
+            p.hist_out[o * p.M + p.m] = (uint8_t)code;
+        }
+        for (int t = lane; t < p.m; t += 32) p.hist_out[o * p.M + t] = p.hist_in[(v * p.F_in + parent) * p.M + t];
+    }
+}
+
+__global__ void qb_decode_init_kernel(const float* __restrict__ cb0, const uint8_t* __restrict__ codes, int64_t n, int M,
+                                      int D, int K, float* __restrict__ xhat, uint32_t* err_flag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t v = t / (D / 4);
+    const int d = (int)(t - v * (D / 4)) * 4;
+    if (v >= n) return;
+    int c = codes[v * M];
+    if (c >= K) { if (err_flag) atomicExch(err_flag, 0x10u); c = K - 1; }
+    *reinterpret_cast<float4*>(xhat + v * D + d) = __ldg(reinterpret_cast<const float4*>(cb0 + (size_t)c * D + d));
+}
+
+__global__ void qb_affine_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total, int D, float scale,
+                                 const float* __restrict__ shift) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    out[t] = fmaf(in[t], scale, shift ? shift[t % D] : 0.f);
+}
+
+}  // namespace
+
+cudaError_t launch_prep(const PrepParams& p, cudaStream_t stream) {
+    if (p.n_beams <= 0) return cudaSuccess;
+    if (p.K > 256 || p.D % 4) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)(2 * kPrepRows * p.D + kPrepRows * p.K) * sizeof(float);
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(qb_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = smem;
+    }
+    const int64_t grid = (p.n_beams + kPrepRows - 1) / kPrepRows;
+    qb_prep_kernel<<<(unsigned)grid, kPrepThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_select(const SelectParams& p, cudaStream_t stream) {
+    if (p.n <= 0) return cudaSuccess;
+    const int wpb = 8;
+    const int64_t grid = (p.n + wpb - 1) / wpb;
+    qb_select_kernel<<<(unsigned)grid, wpb * 32, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_init(const float* cb0, const uint8_t* codes, int64_t n, int M, int D, int K, float* xhat,
+                               uint32_t* err_flag, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const int64_t total = n * (D / 4);
+    qb_decode_init_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(cb0, codes, n, M, D, K, xhat, err_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_affine(const float* in, float* out, int64_t n, int D, float scale, const float* shift,
+                          cudaStream_t stream) {
+    const int64_t total = n * D;
+    if (total <= 0) return cudaSuccess;
+    qb_affine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out, total, D, scale, shift);
+    return cudaGetLastError();
+}
+
+}  // namespace qb
