@@ -91,6 +91,10 @@ int qb_decode(qb_model* m, const uint8_t* codes_dev, int64_t n, int denormalize,
 int qb_encode_host(qb_model* m, const float* x_host, int64_t n, int normalize, uint8_t* codes_host, float* xhat_host);
 int qb_decode_host(qb_model* m, const uint8_t* codes_host, int64_t n, int denormalize, float* out_host);
 
+/* Reads the device-side error word (set by a kernel before it traps, or by an out-of-range code); 0 when clean.
+ * Cheap (one host read of mapped memory); call it after synchronising the stream. */
+int qb_check(qb_model* m);
+
 /* Introspection */
 int64_t qb_launch_count(const qb_model* m);      /* kernels launched by this model so far */
 int qb_model_info(const qb_model* m, int step, int32_t* out, int n_out); /* plan of step>=1: see qb_api.cu */
@@ -99,6 +103,16 @@ int qb_model_info(const qb_model* m, int step, int32_t* out, int n_out); /* plan
  * QINCoStep.decode (qinco_base.py:282-290) through the production kernels.  Device pointers. */
 int qb_debug_step(qb_model* m, int step, const float* xhat_dev, const uint8_t* codes_dev, int64_t n, float* out_dev,
                   void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Host-only test hooks (no CUDA call): export the tcgen05 op list of one step (32-byte QbOp records, csrc/qb_plan.h),
+ * pack weights into the slab blob and build the hoisted tables, so the CPU test-suite can replay the kernel's dataflow
+ * in numpy.  opts5 = {hc, n_hbuf, slot_bytes, max_stage, max_slab_k} or NULL. */
+int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const int32_t* opts5, int32_t* plan_out,
+                   int n_plan_out, void* ops_out, int max_ops);
+int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int32_t* opts5, const float* const* up,
+                 const float* const* down, const float* out_proj, uint16_t* blob, int64_t blob_halfs);
+int qb_plan_tables(int D, int De, int K, const float* codebook, const float* in_proj, const float* concat_w,
+                   const float* concat_b, float* t_blk, float* cb_blk, float* wx_t);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,74 @@
+"""Build libqinco_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so must travel with the repo snapshot).
+
+    python -m qinco_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The library links cudart statically and has no torch / Python dependency: its
+interface is the C ABI in include/qinco_b200.h.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libqinco_b200.so")
+SOURCES = ["qb_api.cu", "qb_mlp.cu", "qb_kernels.cu", "qb_plan.cpp"]
+HEADERS = ["qb_dev.h", "qb_host.h", "qb_plan.h", os.path.join(ROOT, "include", "qinco_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
+              "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (needed to build libqinco_b200.so)")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
+    deps.append(os.path.abspath(__file__))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile if sources are newer than the library; returns the library path."""
+    if not force and not _stale():
+        return LIB
+    nvcc = _nvcc()
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    objs = []
+    build_dir = os.path.join(PKG, "build")
+    os.makedirs(build_dir, exist_ok=True)
+    log = []
+    for s in SOURCES:
+        o = os.path.join(build_dir, os.path.splitext(s)[0] + ".o")
+        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, s), "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log.append(r.stderr)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"nvcc failed on {s}")
+        objs.append(o)
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB + ".tmp", *objs, "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    os.replace(LIB + ".tmp", LIB)
+    with open(os.path.join(build_dir, "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        sys.stderr.write("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

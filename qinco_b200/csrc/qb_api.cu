@@ -1,0 +1,630 @@
+// C ABI of libqinco_b200.so (include/qinco_b200.h): model packing/upload and the per-chunk launch sequences of the
+// encode / decode loops.
+//
+// Encode of one chunk of vectors (reference qinco/model/qinco_base.py:454-485 loop, :292-374 one beam step):
+//   step 0      prep(step0)            F_1 nearest codewords of C_0 -> beam x-hat + code history
+//   step m>=1   prep                   r = x - xhat_b, u_b = Wx.xhat_b, top-A pre-selection            (CUDA cores, fp32)
+//               mlp(score)             dist[row] = ||r_b - f_m(C_m[code], xhat_b)||^2                  (tcgen05)
+//               select                 F_out smallest per vector, parent beam, code history
+//               mlp(apply)             xhat'_j = xhat_parent + f_m(C_m[code_j], xhat_parent)           (tcgen05)
+// Decode (reference :447-452, :282-290): decode_init, then per step prep(u only) + mlp(apply).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/qinco_b200.h"
+#include "qb_dev.h"
+#include "qb_host.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return QB_ERR_CUDA;
+}
+#define QB_CUDA(call)                                        \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct StepDev {
+    QbStepPlan plan;
+    QbOp* ops = nullptr;
+    uint8_t* w_blob = nullptr;
+    float* t_blk = nullptr;
+    float* cb_blk = nullptr;
+    float* wx_t = nullptr;
+    float* sub_cb_t = nullptr;   // [D][K] pre-selection codebook, transposed (A > 0)
+};
+
+struct HostSlot {
+    float* x_pin = nullptr;
+    uint8_t* codes_pin = nullptr;
+    float* out_pin = nullptr;     // xhat (encode) or decoded vectors (decode)
+    float* x_dev = nullptr;
+    uint8_t* codes_dev = nullptr;
+    float* out_dev = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
+    int64_t pending_i0 = -1, pending_n = 0;
+};
+
+}  // namespace
+
+struct qb_model {
+    int D = 0, De = 0, Dh = 0, L = 0, M = 0, K = 0, A = 0, B = 0, q1 = 0, device = 0, n_sm = 0;
+    float data_std = 1.f;
+    bool has_mean = false;
+    float* cb0 = nullptr;      // [K][D]
+    float* cb0_t = nullptr;    // [D][K]
+    float* mean = nullptr;     // [D]
+    std::vector<StepDev> steps;   // index m, entry 0 unused
+    uint32_t* err_host = nullptr;   // mapped pinned word written by the kernels before they trap
+    uint32_t* err_dev = nullptr;
+    int64_t launches = 0;
+    std::vector<void*> dev_allocs;
+    // host-variant staging
+    int64_t host_chunk = 0;
+    HostSlot slot[2];
+    void* host_ws = nullptr;
+    size_t host_ws_bytes = 0;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+};
+
+namespace {
+
+template <typename T>
+int dev_upload(qb_model* m, const T* host, size_t count, T** out) {
+    void* p = nullptr;
+    QB_CUDA(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16)));
+    m->dev_allocs.push_back(p);
+    if (count) QB_CUDA(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<T*>(p);
+    return QB_OK;
+}
+
+int check_desc(const qb_model_desc* d) {
+    if (!d) return fail(QB_ERR_INVALID, "desc is NULL");
+    if (d->M < 1 || d->M > 64) return fail(QB_ERR_INVALID, "M must be in [1,64]");
+    if (d->K < 1 || d->K > 256) return fail(QB_ERR_INVALID, "K must be in [1,256] (codes are uint8)");
+    if (d->D < 16 || d->D % 16) return fail(QB_ERR_INVALID, "D must be a positive multiple of 16");
+    if (d->A < 0 || d->A > d->K) return fail(QB_ERR_INVALID, "A must be in [0,K]");
+    if (d->B < 1 || d->B > d->K || d->B > 255) return fail(QB_ERR_INVALID, "B must be in [1,min(K,255)]");
+    if (d->L < 0) return fail(QB_ERR_INVALID, "L must be >= 0");
+    if (!(d->data_std > 0.f)) return fail(QB_ERR_INVALID, "data_std must be > 0 (qinco_base.py:526)");
+    if (!d->codebook) return fail(QB_ERR_INVALID, "codebook pointers missing");
+    for (int m = 0; m < d->M; m++)
+        if (!d->codebook[m]) return fail(QB_ERR_INVALID, "codebook[m] is NULL");
+    if (d->M > 1) {
+        if (!d->concat_w || !d->concat_b) return fail(QB_ERR_INVALID, "concat weights missing");
+        if (d->L > 0 && (!d->up_w || !d->down_w)) return fail(QB_ERR_INVALID, "residual block weights missing");
+        if (d->A > 0 && !d->substep_codebook) return fail(QB_ERR_INVALID, "A > 0 needs substep codebooks");
+        if (d->De != d->D && (!d->in_proj || !d->out_proj)) return fail(QB_ERR_INVALID, "de != D needs in_proj/out_proj");
+        for (int m = 1; m < d->M; m++) {
+            if (!d->concat_w[m] || !d->concat_b[m]) return fail(QB_ERR_INVALID, "concat weights of a step are NULL");
+            if (d->A > 0 && !d->substep_codebook[m]) return fail(QB_ERR_INVALID, "substep codebook of a step is NULL");
+            if (d->De != d->D && (!d->in_proj[m] || !d->out_proj[m])) return fail(QB_ERR_INVALID, "projection of a step is NULL");
+            for (int l = 0; l < d->L; l++)
+                if (!d->up_w[m * d->L + l] || !d->down_w[m * d->L + l]) return fail(QB_ERR_INVALID, "block weights of a step are NULL");
+        }
+    }
+    return QB_OK;
+}
+
+// ---- per-chunk workspace ----------------------------------------------------------------------------------------
+struct Workspace {
+    float* xhat[2];
+    uint8_t* hist[2];
+    float* r;
+    float* u;
+    uint8_t* idx;
+    float* dist;
+    uint8_t* selp;
+    uint8_t* selc;
+};
+
+size_t encode_bytes_per_vector(const qb_model* m) {
+    const size_t B = m->B, C = m->A > 0 ? m->A : m->K;
+    return 2 * B * m->D * 4 + 2 * B * m->M + B * m->D * 4 + B * m->De * 4 + B * std::max(m->A, 1) + B * C * 4 + 2 * B;
+}
+constexpr size_t kWsSlack = 16 * 256;   // alignment padding of the carve-up
+
+int64_t default_chunk(const qb_model* m) {
+    const int64_t rows_per_vec = (int64_t)m->B * (m->A > 0 ? m->A : m->K);
+    int64_t c = (int64_t)(4 << 20) / rows_per_vec;
+    c = std::max<int64_t>(c, 1024);
+    return c / 128 * 128;
+}
+
+void carve(const qb_model* m, void* ws, int64_t nc, Workspace* w) {
+    uint8_t* p = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(ws), 256));
+    auto take = [&](size_t bytes) {
+        uint8_t* q = p;
+        p += align_up(bytes, 256);
+        return q;
+    };
+    const size_t B = m->B, C = m->A > 0 ? m->A : m->K, n = (size_t)nc;
+    w->xhat[0] = (float*)take(n * B * m->D * 4);
+    w->xhat[1] = (float*)take(n * B * m->D * 4);
+    w->hist[0] = take(n * B * m->M);
+    w->hist[1] = take(n * B * m->M);
+    w->r = (float*)take(n * B * m->D * 4);
+    w->u = (float*)take(n * B * m->De * 4);
+    w->idx = take(n * B * std::max(m->A, 1));
+    w->dist = (float*)take(n * B * C * 4);
+    w->selp = take(n * B);
+    w->selc = take(n * B);
+}
+
+qb::MlpParams base_mlp(const qb_model* m, int step) {
+    const StepDev& s = m->steps[step];
+    qb::MlpParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.plan = s.plan;
+    p.ops = s.ops;
+    p.w_blob = s.w_blob;
+    p.t_blk = s.t_blk;
+    p.cb_blk = s.cb_blk;
+    p.out_scale = 1.f;
+    p.err_flag = m->err_dev;
+    return p;
+}
+
+int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, uint8_t* codes, float* xhat_out, void* ws,
+                 cudaStream_t st) {
+    Workspace w;
+    carve(m, ws, n, &w);
+    const int D = m->D, M = m->M, K = m->K, A = m->A, B = m->B;
+    const int C = A > 0 ? A : K;
+    const float* mean = (normalize && m->has_mean) ? m->mean : nullptr;
+    const float inv_std_div = normalize ? m->data_std : 1.f;
+    int cur = 0;
+    // ---- step 0 (qinco_base.py:218,263; qinco_inference.py:239-246)
+    const int F1 = (M == 1) ? 1 : B;
+    {
+        qb::PrepParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.D = D; p.De = m->De; p.K = K; p.A = F1; p.F = 1; p.step0 = 1; p.M = M;
+        p.n_beams = n; p.x = x; p.mean = mean; p.inv_std = inv_std_div;
+        p.xhat = m->cb0; p.sub_cb = m->cb0_t;
+        p.xhat_out = (M == 1 && xhat_out) ? xhat_out : w.xhat[cur];
+        p.hist_out = (M == 1) ? codes : w.hist[cur];
+        QB_CUDA(qb::launch_prep(p, st));
+        m->launches++;
+    }
+    int F_in = F1;
+    for (int step = 1; step < M; step++) {
+        const StepDev& s = m->steps[step];
+        const int F_out = (step < M - 1) ? B : 1;
+        const bool last = step == M - 1;
+        {
+            qb::PrepParams p;
+            std::memset(&p, 0, sizeof(p));
+            p.D = D; p.De = m->De; p.K = K; p.A = A; p.F = F_in; p.step0 = 0; p.M = M;
+            p.n_beams = n * F_in; p.x = x; p.mean = mean; p.inv_std = inv_std_div;
+            p.xhat = w.xhat[cur]; p.wx_t = s.wx_t; p.sub_cb = A > 0 ? s.sub_cb_t : nullptr;
+            p.r = w.r; p.u = w.u; p.idx = w.idx;
+            QB_CUDA(qb::launch_prep(p, st));
+            m->launches++;
+        }
+        {
+            qb::MlpParams p = base_mlp(m, step);
+            p.mode = qb::QB_MODE_SCORE;
+            p.C = C; p.A = A;
+            p.n_rows = n * F_in * C;
+            p.idx = w.idx; p.u = w.u; p.r = w.r; p.dist = w.dist;
+            QB_CUDA(qb::launch_mlp(p, m->n_sm, st));
+            m->launches++;
+        }
+        {
+            qb::SelectParams p;
+            std::memset(&p, 0, sizeof(p));
+            p.F_in = F_in; p.F_out = F_out; p.C = C; p.A = A; p.M = M; p.m = step; p.n = n;
+            p.dist = w.dist; p.idx = A > 0 ? w.idx : nullptr;
+            p.hist_in = w.hist[cur]; p.hist_out = last ? codes : w.hist[cur ^ 1];
+            p.sel_parent = w.selp; p.sel_code = w.selc;
+            QB_CUDA(qb::launch_select(p, st));
+            m->launches++;
+        }
+        if (!last || xhat_out) {
+            qb::MlpParams p = base_mlp(m, step);
+            p.mode = qb::QB_MODE_APPLY;
+            p.F_in = F_in; p.F_out = F_out;
+            p.n_rows = n * F_out;
+            p.sel_parent = w.selp; p.sel_code = w.selc; p.code_stride = 1; p.code_off = 0;
+            p.u = w.u; p.xhat_in = w.xhat[cur];
+            p.xhat_out = last ? xhat_out : w.xhat[cur ^ 1];
+            QB_CUDA(qb::launch_mlp(p, m->n_sm, st));
+            m->launches++;
+        }
+        cur ^= 1;
+        F_in = F_out;
+    }
+    return QB_OK;
+}
+
+size_t decode_bytes_per_vector(const qb_model* m) { return (size_t)2 * m->D * 4 + (size_t)m->De * 4; }
+
+int decode_chunk(qb_model* m, const uint8_t* codes, int64_t n, int denormalize, float* out, void* ws, cudaStream_t st) {
+    uint8_t* p0 = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(ws), 256));
+    float* xh[2];
+    xh[0] = (float*)p0;
+    xh[1] = (float*)(p0 + align_up((size_t)n * m->D * 4, 256));
+    float* u = (float*)(p0 + 2 * align_up((size_t)n * m->D * 4, 256));
+    const int D = m->D, M = m->M;
+    const float scale = denormalize ? m->data_std : 1.f;
+    const float* shift = (denormalize && m->has_mean) ? m->mean : nullptr;
+    const bool affine = denormalize && (scale != 1.f || shift);
+    int cur = 0;
+    QB_CUDA(qb::launch_decode_init(m->cb0, codes, n, M, D, m->K, (M == 1 && !affine) ? out : xh[cur], m->err_dev, st));
+    m->launches++;
+    if (M == 1 && affine) {
+        QB_CUDA(qb::launch_affine(xh[cur], out, n, D, scale, shift, st));
+        m->launches++;
+    }
+    for (int step = 1; step < M; step++) {
+        const StepDev& s = m->steps[step];
+        const bool last = step == M - 1;
+        {
+            qb::PrepParams p;
+            std::memset(&p, 0, sizeof(p));
+            p.D = D; p.De = m->De; p.K = m->K; p.A = 0; p.F = 1; p.step0 = 0; p.M = M;
+            p.n_beams = n; p.x = xh[cur]; p.inv_std = 1.f;
+            p.xhat = xh[cur]; p.wx_t = s.wx_t; p.u = u;
+            QB_CUDA(qb::launch_prep(p, st));
+            m->launches++;
+        }
+        {
+            qb::MlpParams p = base_mlp(m, step);
+            p.mode = qb::QB_MODE_APPLY;
+            p.F_in = 1; p.F_out = 1; p.n_rows = n;
+            p.sel_code = codes; p.code_stride = M; p.code_off = step;
+            p.u = u; p.xhat_in = xh[cur];
+            p.xhat_out = last ? out : xh[cur ^ 1];
+            if (last) { p.out_scale = scale; p.out_shift = shift; }
+            QB_CUDA(qb::launch_mlp(p, m->n_sm, st));
+            m->launches++;
+        }
+        cur ^= 1;
+    }
+    return QB_OK;
+}
+
+int check_device_flag(qb_model* m) {
+    const uint32_t e = *reinterpret_cast<volatile uint32_t*>(m->err_host);
+    if (e) {
+        char buf[160];
+        snprintf(buf, sizeof(buf),
+                 "device-side failure, err word 0x%x (0x10: code out of range; 0x1xx/0x2xx/0x3xx/0x4xx: barrier wait "
+                 "time-out in producer/MMA/ring/epilogue)", e);
+        return fail(QB_ERR_KERNEL, buf);
+    }
+    return QB_OK;
+}
+
+int ensure_host_staging(qb_model* m, bool decode) {
+    (void)decode;
+    if (m->host_chunk) return QB_OK;
+    const int64_t nc = default_chunk(m);
+    QB_CUDA(cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking));
+    QB_CUDA(cudaStreamCreateWithFlags(&m->s_comp, cudaStreamNonBlocking));
+    QB_CUDA(cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking));
+    for (auto& s : m->slot) {
+        QB_CUDA(cudaHostAlloc((void**)&s.x_pin, (size_t)nc * m->D * 4, cudaHostAllocDefault));
+        QB_CUDA(cudaHostAlloc((void**)&s.out_pin, (size_t)nc * m->D * 4, cudaHostAllocDefault));
+        QB_CUDA(cudaHostAlloc((void**)&s.codes_pin, (size_t)nc * m->M, cudaHostAllocDefault));
+        QB_CUDA(cudaMalloc((void**)&s.x_dev, (size_t)nc * m->D * 4));
+        QB_CUDA(cudaMalloc((void**)&s.out_dev, (size_t)nc * m->D * 4));
+        QB_CUDA(cudaMalloc((void**)&s.codes_dev, (size_t)nc * m->M));
+        QB_CUDA(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        QB_CUDA(cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
+        QB_CUDA(cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
+    }
+    m->host_ws_bytes = std::max(qb_encode_workspace_bytes(m, nc), qb_decode_workspace_bytes(m, nc));
+    QB_CUDA(cudaMalloc(&m->host_ws, m->host_ws_bytes));
+    m->host_chunk = nc;
+    return QB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qb_version(void) { return 100; }
+const char* qb_last_error(void) { return g_err.c_str(); }
+
+int qb_model_create(const qb_model_desc* d, qb_model** out) {
+    if (!out) return fail(QB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = check_desc(d);
+    if (rc) return rc;
+    int ndev = 0;
+    QB_CUDA(cudaGetDeviceCount(&ndev));
+    if (d->device < 0 || d->device >= ndev) return fail(QB_ERR_INVALID, "device ordinal out of range");
+    QB_CUDA(cudaSetDevice(d->device));
+    cudaDeviceProp prop;
+    QB_CUDA(cudaGetDeviceProperties(&prop, d->device));
+    if (prop.major != 10)
+        return fail(QB_ERR_CUDA, std::string("this library is built for sm_100a only; device is ") + prop.name);
+
+    qb_model* m = new (std::nothrow) qb_model();
+    if (!m) return fail(QB_ERR_NOMEM, "out of host memory");
+    m->D = d->D; m->De = d->De > 0 ? d->De : d->D; m->Dh = d->Dh; m->L = d->L; m->M = d->M; m->K = d->K;
+    m->A = d->A; m->B = d->B; m->q1 = d->qinco1_mode; m->device = d->device; m->n_sm = prop.multiProcessorCount;
+    m->data_std = d->data_std;
+    auto bail = [&](int code) {
+        qb_model_destroy(m);
+        return code;
+    };
+    const int D = m->D, De = m->De, K = m->K;
+
+    QB_CUDA(cudaHostAlloc((void**)&m->err_host, 64, cudaHostAllocMapped));
+    *m->err_host = 0;
+    QB_CUDA(cudaHostGetDevicePointer((void**)&m->err_dev, m->err_host, 0));
+
+    // step 0: plain codebook, row-major and transposed
+    {
+        std::vector<float> t((size_t)D * K);
+        for (int k = 0; k < K; k++)
+            for (int dd = 0; dd < D; dd++) t[(size_t)dd * K + k] = d->codebook[0][(size_t)k * D + dd];
+        if ((rc = dev_upload(m, d->codebook[0], (size_t)K * D, &m->cb0))) return bail(rc);
+        if ((rc = dev_upload(m, t.data(), t.size(), &m->cb0_t))) return bail(rc);
+    }
+    if (d->data_mean) {
+        bool nz = false;
+        for (int i = 0; i < D; i++) nz |= d->data_mean[i] != 0.f;
+        m->has_mean = nz;
+        if ((rc = dev_upload(m, d->data_mean, (size_t)D, &m->mean))) return bail(rc);
+    }
+    m->steps.resize(m->M);
+    qb::PlanOptions opt;
+    opt.hc = d->opt_hc; opt.n_hbuf = d->opt_n_hbuf; opt.slot_bytes = d->opt_slot_bytes;
+    opt.max_stage = d->opt_max_stage; opt.max_slab_k = d->opt_max_slab_k;
+    int max_smem = 0;
+    for (int s = 1; s < m->M; s++) {
+        StepDev& sd = m->steps[s];
+        std::vector<QbOp> ops;
+        std::string err;
+        if (qb::make_step_plan(D, De, m->Dh, m->L, K, m->q1, opt, &sd.plan, &ops, &err)) return bail(fail(QB_ERR_INVALID, err));
+        std::vector<uint16_t> blob((size_t)(sd.plan.w_blob_bytes + 1) / 2, 0);
+        if (qb::pack_step_weights(sd.plan, ops, d->up_w ? d->up_w + (size_t)s * m->L : nullptr,
+                                  d->down_w ? d->down_w + (size_t)s * m->L : nullptr,
+                                  De != D ? d->out_proj[s] : nullptr, blob.data(), &err))
+            return bail(fail(QB_ERR_INVALID, err));
+        std::vector<float> t_blk((size_t)De * K), cb_blk((size_t)D * K), wx_t((size_t)D * De);
+        qb::build_tables(D, De, K, d->codebook[s], De != D ? d->in_proj[s] : nullptr, d->concat_w[s], d->concat_b[s],
+                         t_blk.data(), cb_blk.data(), wx_t.data());
+        if ((rc = dev_upload(m, ops.data(), std::max<size_t>(ops.size(), 1), &sd.ops))) return bail(rc);
+        if ((rc = dev_upload(m, (const uint8_t*)blob.data(), blob.size() * 2, &sd.w_blob))) return bail(rc);
+        if ((rc = dev_upload(m, t_blk.data(), t_blk.size(), &sd.t_blk))) return bail(rc);
+        if ((rc = dev_upload(m, cb_blk.data(), cb_blk.size(), &sd.cb_blk))) return bail(rc);
+        if ((rc = dev_upload(m, wx_t.data(), wx_t.size(), &sd.wx_t))) return bail(rc);
+        if (m->A > 0) {
+            std::vector<float> t((size_t)D * K);
+            for (int k = 0; k < K; k++)
+                for (int dd = 0; dd < D; dd++) t[(size_t)dd * K + k] = d->substep_codebook[s][(size_t)k * D + dd];
+            if ((rc = dev_upload(m, t.data(), t.size(), &sd.sub_cb_t))) return bail(rc);
+        }
+        max_smem = std::max(max_smem, sd.plan.smem_total);
+    }
+    if (max_smem > 0) {
+        cudaError_t e = qb::mlp_set_smem_attr(max_smem);
+        if (e != cudaSuccess) return bail(fail_cuda(e, "cudaFuncSetAttribute(max dynamic smem)"));
+    }
+    QB_CUDA(cudaDeviceSynchronize());
+    *out = m;
+    return QB_OK;
+}
+
+int qb_model_destroy(qb_model* m) {
+    if (!m) return QB_OK;
+    cudaSetDevice(m->device);
+    for (void* p : m->dev_allocs) cudaFree(p);
+    for (auto& s : m->slot) {
+        if (s.x_pin) cudaFreeHost(s.x_pin);
+        if (s.out_pin) cudaFreeHost(s.out_pin);
+        if (s.codes_pin) cudaFreeHost(s.codes_pin);
+        if (s.x_dev) cudaFree(s.x_dev);
+        if (s.out_dev) cudaFree(s.out_dev);
+        if (s.codes_dev) cudaFree(s.codes_dev);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_comp) cudaEventDestroy(s.ev_comp);
+        if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+    }
+    if (m->host_ws) cudaFree(m->host_ws);
+    if (m->s_h2d) cudaStreamDestroy(m->s_h2d);
+    if (m->s_comp) cudaStreamDestroy(m->s_comp);
+    if (m->s_d2h) cudaStreamDestroy(m->s_d2h);
+    if (m->err_host) cudaFreeHost(m->err_host);
+    delete m;
+    return QB_OK;
+}
+
+size_t qb_encode_workspace_bytes(const qb_model* m, int64_t n) {
+    if (!m || n <= 0) return kWsSlack;
+    const int64_t nc = std::min<int64_t>(n, default_chunk(m));
+    return (size_t)nc * encode_bytes_per_vector(m) + kWsSlack;
+}
+size_t qb_decode_workspace_bytes(const qb_model* m, int64_t n) {
+    if (!m || n <= 0) return kWsSlack;
+    const int64_t nc = std::min<int64_t>(n, default_chunk(m) * 16);
+    return (size_t)nc * decode_bytes_per_vector(m) + kWsSlack;
+}
+
+int qb_encode(qb_model* m, const float* x_dev, int64_t n, int normalize, uint8_t* codes_dev, float* xhat_dev,
+              void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!m) return fail(QB_ERR_INVALID, "model is NULL");
+    if (n < 0) return fail(QB_ERR_INVALID, "n < 0");
+    if (n == 0) return QB_OK;
+    if (!x_dev || !codes_dev || !workspace_dev) return fail(QB_ERR_INVALID, "NULL buffer");
+    if (workspace_bytes <= kWsSlack) return fail(QB_ERR_WORKSPACE, "workspace too small");
+    int64_t nc = (int64_t)((workspace_bytes - kWsSlack) / encode_bytes_per_vector(m));
+    nc = std::min<int64_t>(nc, default_chunk(m));
+    if (nc < 1) return fail(QB_ERR_WORKSPACE, "workspace too small for one vector; see qb_encode_workspace_bytes");
+    if (nc >= 128) nc = nc / 128 * 128;
+    QB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    for (int64_t i0 = 0; i0 < n; i0 += nc) {
+        const int64_t c = std::min(nc, n - i0);
+        int rc = encode_chunk(m, x_dev + i0 * m->D, c, normalize, codes_dev + i0 * m->M,
+                              xhat_dev ? xhat_dev + i0 * m->D : nullptr, workspace_dev, st);
+        if (rc) return rc;
+    }
+    return QB_OK;
+}
+
+int qb_decode(qb_model* m, const uint8_t* codes_dev, int64_t n, int denormalize, float* out_dev, void* workspace_dev,
+              size_t workspace_bytes, void* stream) {
+    if (!m) return fail(QB_ERR_INVALID, "model is NULL");
+    if (n < 0) return fail(QB_ERR_INVALID, "n < 0");
+    if (n == 0) return QB_OK;
+    if (!codes_dev || !out_dev || !workspace_dev) return fail(QB_ERR_INVALID, "NULL buffer");
+    if (workspace_bytes <= kWsSlack) return fail(QB_ERR_WORKSPACE, "workspace too small");
+    int64_t nc = (int64_t)((workspace_bytes - kWsSlack) / decode_bytes_per_vector(m));
+    nc = std::min<int64_t>(nc, default_chunk(m) * 16);
+    if (nc < 1) return fail(QB_ERR_WORKSPACE, "workspace too small for one vector; see qb_decode_workspace_bytes");
+    if (nc >= 128) nc = nc / 128 * 128;
+    QB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    for (int64_t i0 = 0; i0 < n; i0 += nc) {
+        const int64_t c = std::min(nc, n - i0);
+        int rc = decode_chunk(m, codes_dev + i0 * m->M, c, denormalize, out_dev + i0 * m->D, workspace_dev, st);
+        if (rc) return rc;
+    }
+    return QB_OK;
+}
+
+int qb_check(qb_model* m) {
+    if (!m) return fail(QB_ERR_INVALID, "model is NULL");
+    return check_device_flag(m);
+}
+
+// Pipelined host loops: chunk i is copied in on one stream while chunk i-1 computes and chunk i-2 copies out.
+static int host_loop(qb_model* m, bool enc, const float* x_host, const uint8_t* codes_in, int64_t n, int flag,
+                     uint8_t* codes_out, float* out_host) {
+    QB_CUDA(cudaSetDevice(m->device));
+    int rc = ensure_host_staging(m, !enc);
+    if (rc) return rc;
+    const int64_t nc = m->host_chunk;
+    const int D = m->D, M = m->M;
+    auto finalize = [&](HostSlot& s) -> int {
+        if (s.pending_i0 < 0) return QB_OK;
+        QB_CUDA(cudaEventSynchronize(s.ev_d2h));
+        if (enc) {
+            std::memcpy(codes_out + s.pending_i0 * M, s.codes_pin, (size_t)s.pending_n * M);
+            if (out_host) std::memcpy(out_host + s.pending_i0 * D, s.out_pin, (size_t)s.pending_n * D * 4);
+        } else {
+            std::memcpy(out_host + s.pending_i0 * D, s.out_pin, (size_t)s.pending_n * D * 4);
+        }
+        s.pending_i0 = -1;
+        return QB_OK;
+    };
+    int64_t ci = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += nc, ci++) {
+        HostSlot& s = m->slot[ci & 1];
+        const int64_t c = std::min(nc, n - i0);
+        if ((rc = finalize(s))) return rc;
+        if (enc) {
+            std::memcpy(s.x_pin, x_host + i0 * D, (size_t)c * D * 4);
+            QB_CUDA(cudaMemcpyAsync(s.x_dev, s.x_pin, (size_t)c * D * 4, cudaMemcpyHostToDevice, m->s_h2d));
+        } else {
+            std::memcpy(s.codes_pin, codes_in + i0 * M, (size_t)c * M);
+            QB_CUDA(cudaMemcpyAsync(s.codes_dev, s.codes_pin, (size_t)c * M, cudaMemcpyHostToDevice, m->s_h2d));
+        }
+        QB_CUDA(cudaEventRecord(s.ev_h2d, m->s_h2d));
+        QB_CUDA(cudaStreamWaitEvent(m->s_comp, s.ev_h2d, 0));
+        if (enc)
+            rc = qb_encode(m, s.x_dev, c, flag, s.codes_dev, out_host ? s.out_dev : nullptr, m->host_ws, m->host_ws_bytes,
+                           m->s_comp);
+        else
+            rc = qb_decode(m, s.codes_dev, c, flag, s.out_dev, m->host_ws, m->host_ws_bytes, m->s_comp);
+        if (rc) return rc;
+        QB_CUDA(cudaEventRecord(s.ev_comp, m->s_comp));
+        QB_CUDA(cudaStreamWaitEvent(m->s_d2h, s.ev_comp, 0));
+        if (enc) {
+            QB_CUDA(cudaMemcpyAsync(s.codes_pin, s.codes_dev, (size_t)c * M, cudaMemcpyDeviceToHost, m->s_d2h));
+            if (out_host)
+                QB_CUDA(cudaMemcpyAsync(s.out_pin, s.out_dev, (size_t)c * D * 4, cudaMemcpyDeviceToHost, m->s_d2h));
+        } else {
+            QB_CUDA(cudaMemcpyAsync(s.out_pin, s.out_dev, (size_t)c * D * 4, cudaMemcpyDeviceToHost, m->s_d2h));
+        }
+        QB_CUDA(cudaEventRecord(s.ev_d2h, m->s_d2h));
+        s.pending_i0 = i0;
+        s.pending_n = c;
+    }
+    for (int k = 0; k < 2; k++)
+        if ((rc = finalize(m->slot[(ci + k) & 1]))) return rc;
+    return check_device_flag(m);
+}
+
+int qb_encode_host(qb_model* m, const float* x_host, int64_t n, int normalize, uint8_t* codes_host, float* xhat_host) {
+    if (!m) return fail(QB_ERR_INVALID, "model is NULL");
+    if (n < 0) return fail(QB_ERR_INVALID, "n < 0");
+    if (n == 0) return QB_OK;
+    if (!x_host || !codes_host) return fail(QB_ERR_INVALID, "NULL buffer");
+    return host_loop(m, true, x_host, nullptr, n, normalize, codes_host, xhat_host);
+}
+
+int qb_decode_host(qb_model* m, const uint8_t* codes_host, int64_t n, int denormalize, float* out_host) {
+    if (!m) return fail(QB_ERR_INVALID, "model is NULL");
+    if (n < 0) return fail(QB_ERR_INVALID, "n < 0");
+    if (n == 0) return QB_OK;
+    if (!codes_host || !out_host) return fail(QB_ERR_INVALID, "NULL buffer");
+    for (int64_t i = 0; i < n * m->M; i++)
+        if (codes_host[i] >= m->K) return fail(QB_ERR_INVALID, "code out of range [0,K)");
+    return host_loop(m, false, nullptr, codes_host, n, denormalize, nullptr, out_host);
+}
+
+int64_t qb_launch_count(const qb_model* m) { return m ? m->launches : 0; }
+
+int qb_model_info(const qb_model* m, int step, int32_t* out, int n_out) {
+    if (!m || !out) return fail(QB_ERR_INVALID, "NULL argument");
+    if (step < 1 || step >= m->M) return fail(QB_ERR_INVALID, "step out of range (MLP steps are 1..M-1)");
+    const QbStepPlan& p = m->steps[step].plan;
+    const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk,
+                         p.n_hbuf, p.oc, p.n_ochunk, p.slot_bytes, p.n_stage, p.smem_total, (int32_t)p.block_w_bytes,
+                         (int32_t)p.w_blob_bytes, m->n_sm, (int32_t)default_chunk(m)};
+    const int nv = (int)(sizeof(v) / sizeof(v[0]));
+    for (int i = 0; i < n_out && i < nv; i++) out[i] = v[i];
+    return nv;
+}
+
+int qb_debug_step(qb_model* m, int step, const float* xhat_dev, const uint8_t* codes_dev, int64_t n, float* out_dev,
+                  void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!m) return fail(QB_ERR_INVALID, "model is NULL");
+    if (step < 1 || step >= m->M) return fail(QB_ERR_INVALID, "step out of range (MLP steps are 1..M-1)");
+    if (n <= 0) return QB_OK;
+    if (workspace_bytes < (size_t)n * m->De * 4 + 256) return fail(QB_ERR_WORKSPACE, "workspace too small (n*de*4+256)");
+    QB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    float* u = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(workspace_dev), 256));
+    const StepDev& s = m->steps[step];
+    qb::PrepParams pp;
+    std::memset(&pp, 0, sizeof(pp));
+    pp.D = m->D; pp.De = m->De; pp.K = m->K; pp.F = 1; pp.M = m->M; pp.n_beams = n;
+    pp.x = xhat_dev; pp.inv_std = 1.f; pp.xhat = xhat_dev; pp.wx_t = s.wx_t; pp.u = u;
+    QB_CUDA(qb::launch_prep(pp, st));
+    qb::MlpParams p = base_mlp(m, step);
+    p.mode = qb::QB_MODE_APPLY;
+    p.F_in = 1; p.F_out = 1; p.n_rows = n;
+    p.sel_code = codes_dev; p.code_stride = 1; p.code_off = 0;
+    p.u = u; p.xhat_in = xhat_dev; p.xhat_out = out_dev;
+    QB_CUDA(qb::launch_mlp(p, m->n_sm, st));
+    m->launches += 2;
+    return QB_OK;
+}
+
+}  // extern "C"

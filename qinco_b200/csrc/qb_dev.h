@@ -55,7 +55,7 @@ struct PrepParams {
     int64_t n_beams;
     const float* x;           // [n, D] raw input
     const float* mean;        // [D] or NULL
-    float inv_std;
+    float inv_std;            // DIVISOR applied after the mean shift: data_std, or 1 (name kept for the struct layout)
     const float* xhat;        // [n_beams, D] (unused for step0)
     const float* wx_t;        // [D][De]      (NULL: skip u)
     const float* sub_cb;      // [K][D] pre-selection codebook (step0: C_0); NULL: skip selection

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kPrepThreads) qb_prep_kernel(const PrepParams 
             const int64_t v = b / p.F;
             float xn = p.x[v * D + d];
             if (p.mean) xn -= p.mean[d];
-            xn *= p.inv_std;
+            xn /= p.inv_std;   // the reference divides: (x - mean) / std (qinco_base.py:533)
             if (!p.step0) xh = p.xhat[b * D + d];
             r = xn - xh;
             if (p.r) p.r[b * D + d] = r;

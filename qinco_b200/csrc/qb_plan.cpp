@@ -108,7 +108,7 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     p->slot_bytes = opt.slot_bytes > 0 ? opt.slot_bytes : 16384;
     if (p->slot_bytes % 1024) { *err = "slot_bytes must be a multiple of 1024"; return -1; }
     p->smem_ring = off;
-    const int budget = opt.smem_budget > 0 ? opt.smem_budget : 220 * 1024;
+    const int budget = opt.smem_budget > 0 ? opt.smem_budget : 216 * 1024;
     int n_stage = (budget - off) / p->slot_bytes;
     n_stage = std::min(n_stage, opt.max_stage > 0 ? opt.max_stage : 8);
     if (n_stage < 2) { *err = "not enough shared memory for a 2-slot weight ring (de/dh too large)"; return -1; }
@@ -262,3 +262,52 @@ void build_tables(int D, int De, int K, const float* codebook, const float* in_p
 }
 
 }  // namespace qb
+
+// ---- host-only test hooks (declared in include/qinco_b200.h): let the CPU test-suite check the planner and the packer
+// by replaying the op list in numpy, without a GPU.
+extern "C" {
+
+int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const int32_t* opts5, int32_t* plan_out,
+                   int n_plan_out, void* ops_out, int max_ops) {
+    qb::PlanOptions opt;
+    if (opts5) {
+        opt.hc = opts5[0]; opt.n_hbuf = opts5[1]; opt.slot_bytes = opts5[2]; opt.max_stage = opts5[3];
+        opt.max_slab_k = opts5[4];
+    }
+    QbStepPlan p;
+    std::vector<QbOp> ops;
+    std::string err;
+    if (qb::make_step_plan(D, De, Dh, L, K, qinco1_mode, opt, &p, &ops, &err)) return -1;
+    const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk,
+                         p.n_hbuf, p.oc, p.n_ochunk, p.tmem_e_col, p.tmem_h_col[0], p.tmem_h_col[1], p.smem_ae,
+                         p.smem_ah[0], p.smem_ah[1], p.smem_ring, p.slot_bytes, p.n_stage, p.smem_total,
+                         (int32_t)p.block_w_bytes, (int32_t)p.w_blob_bytes};
+    const int nv = (int)(sizeof(v) / sizeof(v[0]));
+    for (int i = 0; i < nv && i < n_plan_out; i++) plan_out[i] = v[i];
+    if ((int)ops.size() > max_ops) return -2;
+    if (ops_out) std::memcpy(ops_out, ops.data(), ops.size() * sizeof(QbOp));
+    return (int)ops.size();
+}
+
+int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int32_t* opts5, const float* const* up,
+                 const float* const* down, const float* out_proj, uint16_t* blob, int64_t blob_halfs) {
+    qb::PlanOptions opt;
+    if (opts5) {
+        opt.hc = opts5[0]; opt.n_hbuf = opts5[1]; opt.slot_bytes = opts5[2]; opt.max_stage = opts5[3];
+        opt.max_slab_k = opts5[4];
+    }
+    QbStepPlan p;
+    std::vector<QbOp> ops;
+    std::string err;
+    if (qb::make_step_plan(D, De, Dh, L, K, qinco1_mode, opt, &p, &ops, &err)) return -1;
+    if (blob_halfs * 2 < p.w_blob_bytes) return -2;
+    return qb::pack_step_weights(p, ops, up, down, out_proj, blob, &err);
+}
+
+int qb_plan_tables(int D, int De, int K, const float* codebook, const float* in_proj, const float* concat_w,
+                   const float* concat_b, float* t_blk, float* cb_blk, float* wx_t) {
+    qb::build_tables(D, De, K, codebook, in_proj, concat_w, concat_b, t_blk, cb_blk, wx_t);
+    return 0;
+}
+
+}  // extern "C"

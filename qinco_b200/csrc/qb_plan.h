@@ -14,7 +14,7 @@
 #include <stdint.h>
 
 #define QB_TILE_M 128
-#define QB_MAX_OPS 128
+#define QB_MAX_OPS 256
 
 enum QbABuf : uint16_t { QB_A_E = 0, QB_A_H0 = 1, QB_A_H1 = 2 };
 // barrier ids used in op wait/commit fields

@@ -1,0 +1,247 @@
+"""Host-side mirror of the reference's model surface for the encode/decode path.
+
+`QINCo` stands in for both reference classes a caller may hold:
+  * qinco.model.QINCo                    (reference qinco/model/qinco_base.py:419-549)
+  * qinco.model.QINCoInferenceWrapper    (reference qinco/model/qinco_inference.py:257-353)
+Same call surface — `model(x, step="encode") -> LongTensor [M, n]`, `model(codes, step="decode") -> [n, D]` in data
+space, `.encode(x_norm) -> (codes [M, n], xhat [n, D])`, `.decode(codes [M, n])` in normalised space, `.data_mean`,
+`.data_std`, `.load_state_dict`, `.build()`, `.built`, `.eval()`, `.to()` — but the work is done by libqinco_b200.so
+(hand-written sm_100a kernels) through the C ABI; tensors cross as raw device pointers.  Training is out of scope.
+
+Unlike the reference's GPU wrapper (which casts the whole model to fp16) the kernels keep fp32 residual streams,
+tables and distances and use fp16 only for the tensor-core operands.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_CFG_KEYS = ("M", "K", "L", "de", "dh", "A", "B", "qinco1_mode")
+
+
+def _cfg_get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    try:
+        v = getattr(cfg, key)
+    except (AttributeError, KeyError):
+        try:
+            v = cfg[key]
+        except Exception:
+            return default
+    return v
+
+
+def normalize_cfg(cfg) -> dict:
+    """Accept a plain dict ({D,M,K,L,de,dh,A,B,qinco1_mode}) or the reference's cfg object (cfg._D, cfg._M_ivf, ...)."""
+    D = _cfg_get(cfg, "D") or _cfg_get(cfg, "_D")
+    if D is None:
+        raise ValueError("cfg needs D (or _D)")
+    M = _cfg_get(cfg, "_M_ivf") or _cfg_get(cfg, "M")
+    out = dict(D=int(D), M=int(M), K=int(_cfg_get(cfg, "K", 256)), L=int(_cfg_get(cfg, "L")),
+               de=int(_cfg_get(cfg, "de") or D), dh=int(_cfg_get(cfg, "dh")), A=int(_cfg_get(cfg, "A", 0) or 0),
+               B=int(_cfg_get(cfg, "B", 1) or 1), qinco1_mode=bool(_cfg_get(cfg, "qinco1_mode", False)))
+    if _cfg_get(cfg, "ivf_in_use", False) or _cfg_get(cfg, "_ivf_book", None):
+        raise NotImplementedError("IVF first step is not built yet (SURVEY.md section 8f row 2)")
+    return out
+
+
+def _to_numpy_state(sd) -> dict:
+    out = {}
+    for k, v in sd.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().float().cpu().numpy()
+        out[k] = np.ascontiguousarray(np.asarray(v, dtype=np.float32))
+    return out
+
+
+class QINCo:
+    """B200 drop-in for the encode/decode surface of the reference model objects (see module docstring)."""
+
+    def __init__(self, cfg, state_dict=None, device=None, plan_opts=None):
+        self.cfg = normalize_cfg(cfg)
+        self.D, self.M, self.K = self.cfg["D"], self.cfg["M"], self.cfg["K"]
+        acc = _cfg_get(cfg, "_accelerator", None)
+        if device is None and acc is not None:
+            device = getattr(acc, "device", None)
+        self.device = torch.device(device if device is not None else "cuda:0")
+        self.data_mean = torch.zeros(self.D)
+        self.data_std = torch.zeros(())
+        self.built = False
+        self._plan_opts = plan_opts
+        self._h = None
+        self._weights = None
+        self._ws = None
+        self.qinco_model = self            # callers reach through the wrapper for `.qinco_model.steps[0]`
+        self.steps = SimpleNamespace()
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # ---- nn.Module-ish surface the callers use -----------------------------------------------------------------
+    def eval(self):
+        return self
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("training is out of scope for the B200 encode/decode path")
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device != self.device:
+            self.device = device
+            if self._weights is not None:
+                self.build()
+        return self
+
+    def parameters(self):
+        yield self.data_mean
+        yield self.data_std
+
+    def state_dict(self):
+        return {k: torch.from_numpy(v.copy()) for k, v in (self._weights or {}).items()}
+
+    def load_state_dict(self, state_dict, strict=True, **kwargs):
+        """Keys are the reference's; training-only buffers (xtarget_*) are ignored."""
+        w = _to_numpy_state(state_dict)
+        w = {k: v for k, v in w.items() if not k.endswith(("xtarget_mean", "xtarget_var"))}
+        missing = [k for k in self._expected_keys() if k not in w]
+        if missing and strict:
+            raise KeyError(f"missing keys in state dict: {missing[:6]}{'...' if len(missing) > 6 else ''}")
+        c = self.cfg
+        shapes = {"steps.0.codebook.weight": (c["K"], c["D"])}
+        for k, shp in shapes.items():
+            if tuple(w[k].shape) != shp:
+                raise ValueError(f"{k}: expected shape {shp}, got {tuple(w[k].shape)}")
+        w.setdefault("data_mean", np.zeros(self.D, np.float32))
+        w.setdefault("data_std", np.array(1.0, np.float32))
+        self._weights = w
+        self.build()
+
+    def _expected_keys(self):
+        c = self.cfg
+        keys = [f"steps.{m}.codebook.weight" for m in range(c["M"])]
+        for m in range(1, c["M"]):
+            keys += [f"steps.{m}.concat.mlp.weight", f"steps.{m}.concat.mlp.bias"]
+            if c["A"] > 0:
+                keys.append(f"steps.{m}.substep.codebook.weight")
+            for l in range(c["L"]):
+                keys += [f"steps.{m}.residual_blocks.{l}.up_proj.weight", f"steps.{m}.residual_blocks.{l}.down_proj.weight"]
+            if c["de"] != c["D"]:
+                keys += [f"steps.{m}.in_proj.weight", f"steps.{m}.out_proj.weight"]
+        return keys
+
+    def build(self):
+        """Pack + upload the weights (the counterpart of QINCoInferenceWrapper.build, qinco_inference.py:290-330)."""
+        if self._weights is None:
+            raise RuntimeError("load_state_dict first")
+        if self.device.type != "cuda":
+            raise RuntimeError("qinco_b200 has no CPU path: the model must live on a CUDA (sm_100a) device")
+        if not torch.cuda.is_available():
+            raise RuntimeError("qinco_b200 needs a CUDA device (there is no CPU fallback)")
+        if self._h is not None:
+            self._h.close()
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        self._h = _lib.Handle(self.cfg, self._weights, device=idx, plan_opts=self._plan_opts)
+        self.data_mean = torch.from_numpy(self._weights["data_mean"].copy()).to(self.device)
+        self.data_std = torch.tensor(float(self._weights["data_std"]), device=self.device)
+        self._ws = None
+        self.built = True
+        return self
+
+    # ---- raw layer: uint8 [n, M] codes, raw pointers -----------------------------------------------------------
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _check_x(self, x):
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("x must be a torch.Tensor")
+        if x.dim() != 2 or x.shape[1] != self.D:
+            raise ValueError(f"x must be [n, {self.D}], got {tuple(x.shape)}")
+        if x.device != self.device:
+            raise ValueError(f"x is on {x.device}, the model on {self.device}")
+        return x.float().contiguous()
+
+    def encode_u8(self, x, normalize=False, want_xhat=True):
+        """x [n, D] fp32 on the model's device -> (codes uint8 [n, M], xhat [n, D] or None); asynchronous."""
+        if not self.built:
+            raise RuntimeError("model not built")
+        x = self._check_x(x)
+        n = x.shape[0]
+        codes = torch.empty((n, self.M), dtype=torch.uint8, device=self.device)
+        xhat = torch.empty((n, self.D), dtype=torch.float32, device=self.device) if want_xhat else None
+        if n:
+            nbytes = self._h.encode_workspace_bytes(n)
+            ws = self._workspace(nbytes)
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream().cuda_stream
+                self._h.encode(x.data_ptr(), n, normalize, codes.data_ptr(), xhat.data_ptr() if want_xhat else None,
+                               ws.data_ptr(), ws.numel(), stream)
+        return codes, xhat
+
+    def decode_u8(self, codes_u8, denormalize=False):
+        """codes uint8 [n, M] on the model's device -> [n, D] fp32; asynchronous."""
+        if not self.built:
+            raise RuntimeError("model not built")
+        assert codes_u8.dtype == torch.uint8 and codes_u8.dim() == 2 and codes_u8.shape[1] == self.M
+        codes_u8 = codes_u8.contiguous()
+        n = codes_u8.shape[0]
+        out = torch.empty((n, self.D), dtype=torch.float32, device=self.device)
+        if n:
+            nbytes = self._h.decode_workspace_bytes(n)
+            ws = self._workspace(nbytes)
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream().cuda_stream
+                self._h.decode(codes_u8.data_ptr(), n, denormalize, out.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        return out
+
+    def _codes_to_u8(self, codes_MB):
+        if not isinstance(codes_MB, torch.Tensor):
+            codes_MB = torch.as_tensor(np.asarray(codes_MB))
+        if codes_MB.dim() != 2 or codes_MB.shape[0] != self.M:
+            raise AssertionError(f"codes must be [M={self.M}, n], got {tuple(codes_MB.shape)}")   # qinco_base.py:449
+        codes_MB = codes_MB.to(self.device)
+        if codes_MB.numel() and (int(codes_MB.min()) < 0 or int(codes_MB.max()) >= self.K):
+            raise IndexError(f"codes out of range [0, {self.K})")
+        return codes_MB.t().contiguous().to(torch.uint8)
+
+    # ---- the reference surface ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode(self, x_target_BD):
+        """Normalised space: x [n, D] -> (codes LongTensor [M, n], xhat [n, D])   (qinco_base.py:454-485)."""
+        codes, xhat = self.encode_u8(x_target_BD, normalize=False, want_xhat=True)
+        return codes.t().contiguous().long(), xhat
+
+    @torch.no_grad()
+    def decode(self, codes_MB):
+        """Normalised space: codes [M, n] (int64/int32/uint8) -> xhat [n, D] fp32   (qinco_base.py:447-452)."""
+        return self.decode_u8(self._codes_to_u8(codes_MB), denormalize=False)
+
+    @torch.no_grad()
+    def forward(self, x_in, *args, step="train", **kwargs):
+        assert step in ["train", "encode", "decode"]
+        if step == "train":
+            raise Exception("Don't use the B200 inference model for training!")
+        assert float(self.data_std) > 0                                               # qinco_base.py:526
+        if step == "encode":                                                          # :532-534
+            codes, _ = self.encode_u8(x_in, normalize=True, want_xhat=False)
+            return codes.t().contiguous().long()
+        return self.decode_u8(self._codes_to_u8(x_in), denormalize=True)              # :536-537
+
+    __call__ = forward
+
+    def synchronize(self):
+        """Wait for outstanding work and surface device-side failures."""
+        torch.cuda.synchronize(self.device)
+        self._h.check()
+
+    @property
+    def launch_count(self):
+        return self._h.launch_count if self._h else 0

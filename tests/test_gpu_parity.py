@@ -1,0 +1,228 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed reference outputs.
+
+Tolerances (BASELINE.json north_star): integer codes round-trip bit-exact; reconstruction within 1e-4 relative MSE of
+the reference PyTorch fp32 path on the same inputs.  Encode agreement is judged on MSE (fp16 tensor-core operands can
+flip near-tied candidates), plus per-decision optimality for greedy (B=1) models.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_V2
+from oracle import qinco_oracle as orc
+from qinco_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+DEC_TOL = 1e-4        # relative MSE of decode vs reference (north_star)
+STEP_TOL = 1e-5       # one MLP step, relative MSE
+ENC_TOL_SMALL = 5e-3  # |MSE_ours - MSE_ref| / MSE_ref on the tiny golden samples (tens of vectors: one flipped path moves it)
+ENC_TOL_LARGE = 1e-4  # ... on thousands of vectors (north_star)
+
+
+@pytest.fixture(scope="module")
+def models(golden_loader):
+    from qinco_b200.model import QINCo
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cfg, w, z = golden_loader(name)
+            cache[name] = (QINCo(cfg, w, device="cuda:0"), cfg, w, z)
+        return cache[name]
+    yield get
+    for m, *_ in cache.values():
+        m._h.close()
+
+
+def rel_mse(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-30))
+
+
+@pytest.mark.parametrize("name", GOLDEN_V2)
+def test_one_step_matches_oracle(name, models):
+    """qb_debug_step == xhat + QINCoStep.forward(C_m[code], xhat)   (qinco_base.py:262-290), ragged row count."""
+    model, cfg, w, z = models(name)
+    rng = np.random.default_rng(7)
+    n = 333
+    for step in sorted({1, cfg["M"] - 1}):
+        xhat = rng.standard_normal((n, cfg["D"]), dtype=np.float32)
+        codes = rng.integers(0, cfg["K"], size=n).astype(np.uint8)
+        ref = xhat + orc.step_mlp(cfg, w, step, w[f"steps.{step}.codebook.weight"][codes], xhat)
+        xt = torch.from_numpy(xhat).cuda()
+        ct = torch.from_numpy(codes).cuda()
+        out = torch.empty_like(xt)
+        ws = torch.empty(n * cfg["de"] * 4 + 512, dtype=torch.uint8, device="cuda")
+        model._h.debug_step(step, xt.data_ptr(), ct.data_ptr(), n, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                            torch.cuda.current_stream().cuda_stream)
+        model.synchronize()
+        got = out.cpu().numpy()
+        err = rel_mse(got, ref)
+        if err > STEP_TOL:   # diagnostics that localise an operand-layout bug
+            d = np.abs(got - ref)
+            print(f"\n{name} step {step}: rel_mse={err:.3e} max|d|={d.max():.3e}")
+            print("  per-32-row block max:", np.round([d[i:i + 32].max() for i in range(0, n, 32)], 4))
+            print("  per-8-col block max:", np.round([d[:, j:j + 8].max() for j in range(0, cfg['D'], 8)], 4))
+        assert err <= STEP_TOL, f"{name} step {step}: rel mse {err:.3e}"
+
+
+@pytest.mark.parametrize("name", GOLDEN_V2)
+def test_decode_matches_reference(name, models):
+    model, cfg, w, z = models(name)
+    codes = torch.from_numpy(z["codes_ref"]).cuda()
+    dec = model(codes, step="decode")
+    model.synchronize()
+    assert dec.dtype == torch.float32 and tuple(dec.shape) == (codes.shape[1], cfg["D"])
+    err = rel_mse(dec.cpu().numpy(), z["dec_ref"])
+    assert err <= DEC_TOL, f"{name}: decode rel mse {err:.3e}"
+    # normalised-space decode and int32 codes (search_tasks.py:428-445 passes int32)
+    xh = model.decode(codes.int())
+    assert rel_mse(xh.cpu().numpy(), z["xhat_ref"]) <= DEC_TOL
+
+
+def _greedy_decisions_near_optimal(cfg, w, xn, codes_MB, tol=2e-3):
+    """For B=1 models: every chosen code's fp32 distance is within tol of the step's minimum (oracle arithmetic)."""
+    n = len(xn)
+    xhat = np.zeros((n, cfg["D"]), np.float32)
+    worst = 0.0
+    for m in range(cfg["M"]):
+        cb = w[f"steps.{m}.codebook.weight"]
+        if m == 0:
+            cand = np.broadcast_to(cb[None], (n,) + cb.shape)
+        else:
+            xh = xhat[:, None, :]
+            cand = orc.step_mlp(cfg, w, m, np.broadcast_to(cb[None], (n,) + cb.shape), xh) + xh
+        d = ((xn[:, None, :] - cand) ** 2).sum(-1)
+        chosen = d[np.arange(n), codes_MB[m]]
+        worst = max(worst, float(((chosen - d.min(1)) / d.min(1)).max()))
+        xhat = cand[np.arange(n), codes_MB[m]].astype(np.float32)
+    return worst <= tol, worst
+
+
+@pytest.mark.parametrize("name", GOLDEN_V2)
+def test_encode_matches_reference(name, models):
+    model, cfg, w, z = models(name)
+    x = z["x"]
+    xn = (x - w["data_mean"]) / np.float32(w["data_std"])
+    codes = model(torch.from_numpy(x).cuda(), step="encode")
+    model.synchronize()
+    assert codes.dtype == torch.int64 and tuple(codes.shape) == (cfg["M"], len(x))
+    c = codes.cpu().numpy()
+    assert c.min() >= 0 and c.max() < cfg["K"]
+    agree = float((c == z["codes_ref"]).all(0).mean())
+    # MSE of OUR codes decoded by the ORACLE (reference arithmetic) vs the reference's own MSE
+    mse_ours = orc.mse(xn, orc.decode(cfg, w, c))
+    mse_ref = orc.mse(xn, z["xhat_ref"])
+    rel = abs(mse_ours - mse_ref) / mse_ref
+    print(f"\n{name}: vectors with identical codes {agree:.3f}, mse ours {mse_ours:.6f} ref {mse_ref:.6f} rel {rel:.2e}")
+    assert rel <= ENC_TOL_SMALL
+    assert agree >= 0.8
+    if cfg["A"] == 0 and cfg["B"] == 1:
+        ok, worst = _greedy_decisions_near_optimal(cfg, w, xn, c)
+        assert ok, f"a greedy decision is {worst:.2e} worse than the optimum"
+    # encode()'s xhat is decode(codes) (SURVEY section 4 invariant i) and codes round-trip through uint8 bit-exactly
+    codes2, xhat = model.encode(torch.from_numpy(xn).cuda())
+    assert torch.equal(codes2, codes)
+    dec = model.decode(codes2)
+    model.synchronize()
+    assert rel_mse(xhat.cpu().numpy(), dec.cpu().numpy()) <= 1e-10
+    u8, _ = model.encode_u8(torch.from_numpy(xn).cuda())
+    assert torch.equal(u8.t().long(), codes)
+
+
+def test_encode_large_sample_mse():
+    """QINCo2-S shape (BASELINE config 2), 4096 vectors: encode MSE within 1e-4 of the fp32 oracle's."""
+    from qinco_b200.model import QINCo
+    cfg = synth.make_cfg(None, D=128, M=8, K=256, L=2, de=128, dh=256, A=0, B=1)
+    w = synth.make_weights(cfg, seed=4321, n_train=4096, kmeans_iters=2)
+    x = synth.make_data(4096, 128, seed=1234)
+    model = QINCo(cfg, w)
+    codes = model(torch.from_numpy(x).cuda(), step="encode").cpu().numpy()
+    model.synchronize()
+    ref_codes, ref_xhat = orc.encode(cfg, w, x)
+    mse_ours = orc.mse(x, orc.decode(cfg, w, codes))
+    mse_ref = orc.mse(x, ref_xhat)
+    agree = float((codes == ref_codes).all(0).mean())
+    rel = abs(mse_ours - mse_ref) / mse_ref
+    print(f"\nS 4096: identical-code vectors {agree:.4f}, mse ours {mse_ours:.6f} ref {mse_ref:.6f} rel {rel:.2e}")
+    assert rel <= ENC_TOL_LARGE
+    assert agree >= 0.97
+    ok, worst = _greedy_decisions_near_optimal(cfg, w, x[:512], codes[:, :512])
+    assert ok, worst
+    # size-independent properties on a bigger batch: determinism, chunking invariance, decode(encode) consistency
+    xb = torch.from_numpy(synth.make_data(40000, 128, seed=99)).cuda()
+    c1, xh1 = model.encode_u8(xb)
+    c2, _ = model.encode_u8(xb)
+    c3 = torch.cat([model.encode_u8(xb[i:i + 7777])[0] for i in range(0, len(xb), 7777)])
+    model.synchronize()
+    assert torch.equal(c1, c2) and torch.equal(c1, c3)
+    assert rel_mse(model.decode_u8(c1).cpu().numpy(), xh1.cpu().numpy()) <= 1e-10
+    model._h.close()
+
+
+def test_edge_cases(models):
+    model, cfg, w, z = models("tiny_a8_b4")
+    D, M = cfg["D"], cfg["M"]
+    # empty input
+    codes = model(torch.zeros((0, D), device="cuda"), step="encode")
+    assert tuple(codes.shape) == (M, 0) and codes.dtype == torch.int64
+    assert tuple(model(codes, step="decode").shape) == (0, D)
+    # single row and ragged sizes agree with the batched result
+    x = torch.from_numpy(z["x"]).cuda()
+    full = model(x, step="encode")
+    for n in (1, 2, 37):
+        assert torch.equal(model(x[:n], step="encode"), full[:, :n])
+    # out-of-range codes are rejected
+    bad = full.clone()
+    bad[0, 0] = cfg["K"]
+    with pytest.raises(IndexError):
+        model(bad, step="decode")
+    with pytest.raises(AssertionError):
+        model.decode(full[:-1])
+    # workspace too small -> error status, no launch
+    from qinco_b200._lib import QbError
+    xs = x[:8].contiguous()
+    out = torch.empty((8, M), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(4096, dtype=torch.uint8, device="cuda")
+    with pytest.raises(QbError) as e:
+        model._h.encode(xs.data_ptr(), 8, False, out.data_ptr(), None, ws.data_ptr(), ws.numel(), 0)
+    assert e.value.code == -3
+    model.synchronize()
+
+
+def test_single_step_model():
+    """M == 1: a plain nearest-codeword quantiser (qinco_base.py:218,263), beam 1 on exit."""
+    from qinco_b200.model import QINCo
+    cfg = synth.make_cfg(None, D=16, M=1, K=32, L=1, de=16, dh=16, A=0, B=4)
+    w = synth.make_weights(cfg, seed=6, n_train=512, kmeans_iters=1, data_mean=0.3, data_std=1.7)
+    x = synth.make_data(50, 16, seed=9, mean=0.3, std=1.7)
+    model = QINCo(cfg, w)
+    codes = model(torch.from_numpy(x).cuda(), step="encode")
+    ref = orc.forward(cfg, w, x, "encode")
+    np.testing.assert_array_equal(codes.cpu().numpy(), ref)
+    dec = model(codes, step="decode").cpu().numpy()
+    assert rel_mse(dec, orc.forward(cfg, w, ref, "decode")) <= 1e-12
+    model._h.close()
+
+
+def test_v1_codec_matches_reference(golden_loader):
+    from qinco_b200 import codec
+    cfg, w, z = golden_loader("v1_codec")
+    model = codec.QINCoV1(cfg=cfg, weights=w, db_scale=float(z["db_scale"]))
+    codes = codec.encode(model, z["x"], bs=40, is_float16=False)
+    assert codes.dtype == np.int64 and codes.shape == z["codes_ref"].shape
+    agree = float((codes == z["codes_ref"]).all(1).mean())
+    assert agree >= 0.9, agree
+    dec = codec.decode(model, z["codes_ref"], bs=40, is_float16=False)
+    assert dec.dtype == np.float32
+    assert rel_mse(dec, z["dec_ref"]) <= DEC_TOL
+    # the v1 model's own tensor surface (model_qinco.py:91-118)
+    xt = torch.from_numpy(z["x"] / np.float32(z["db_scale"])).cuda()
+    c, xh = model.encode(xt)
+    assert tuple(c.shape) == (len(xt), cfg["M"]) and c.dtype == torch.int64
+    np.testing.assert_array_equal(c.cpu().numpy(), codes)
+    assert rel_mse(model.decode(c).cpu().numpy(), xh.cpu().numpy()) <= 1e-10
+    # from a v1-keyed state dict
+    m2 = codec.QINCoV1(synth.to_v1_state(cfg, w), db_scale=float(z["db_scale"]))
+    np.testing.assert_array_equal(codec.encode(m2, z["x"], bs=96, verbose=False), codes)

@@ -1,0 +1,205 @@
+"""CPU tests of the host logic: the C-ABI library loads and exports every declared symbol, fails loudly without a GPU,
+and the tcgen05 step planner + weight packer are right — checked by replaying the op list in numpy (a software model
+of the kernel's dataflow: fp16 operands, fp32 accumulators in 'TMEM' columns) against the oracle's MLP.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import qinco_oracle as orc
+from qinco_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+OP_DTYPE = np.dtype([("w_off", "<u4"), ("w_bytes", "<u4"), ("n", "<u2"), ("k", "<u2"), ("a_buf", "<u2"), ("a_kc", "<u2"),
+                     ("d_col", "<u2"), ("accumulate", "u1"), ("wait_a", "u1"), ("wait_d", "u1"), ("commit", "u1"),
+                     ("pad", "u1", 10)])
+PLAN_FIELDS = ["D", "De", "Dh", "L", "K", "has_proj", "skip", "n_ops_block", "n_ops_out", "hc", "n_hchunk", "n_hbuf", "oc",
+               "n_ochunk", "tmem_e_col", "tmem_h_col0", "tmem_h_col1", "smem_ae", "smem_ah0", "smem_ah1", "smem_ring",
+               "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes"]
+BAR_AE_READY, BAR_AH0_READY, BAR_AH1_READY = 1, 2, 3
+BAR_HACC0_FULL, BAR_HACC1_FULL, BAR_EACC_FULL = 6, 7, 8
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "qinco_b200.h")).read()
+    declared = set(re.findall(r"\b(qb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"qb_model_desc", "qb_status"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.qb_version() >= 100
+    assert OP_DTYPE.itemsize == 32
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the product path must fail loudly (QB_ERR_CUDA), never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cfg = synth.make_cfg(None, D=16, M=2, K=32, L=1, de=16, dh=16)
+    w = synth.make_weights(cfg, seed=1, n_train=256, kmeans_iters=1)
+    with pytest.raises(_lib.QbError) as e:
+        _lib.Handle(cfg, w)
+    assert e.value.code == -2
+    from qinco_b200.model import QINCo
+    with pytest.raises(RuntimeError):
+        QINCo(cfg, w, device="cuda:0")
+    with pytest.raises(RuntimeError):
+        QINCo(cfg, w, device="cpu")
+
+
+def test_invalid_descriptions_are_rejected(lib):
+    cfg = synth.make_cfg(None, D=24, M=2, K=32, L=1, de=24, dh=16)   # D not a multiple of 16
+    w = synth.make_weights(cfg, seed=1, n_train=256, kmeans_iters=1)
+    with pytest.raises(_lib.QbError) as e:
+        _lib.Handle(cfg, w)
+    assert e.value.code == -1 and "multiple of 16" in str(e.value)
+
+
+def export_plan(lib, cfg, opts=None):
+    o = (C.c_int32 * 5)(*(opts or [0] * 5))
+    plan = (C.c_int32 * 32)()
+    ops = np.zeros(256, OP_DTYPE)
+    n = lib.qb_plan_export(cfg["D"], cfg["de"], cfg["dh"], cfg["L"], cfg["K"], int(cfg["qinco1_mode"]), o, plan, 32,
+                           ops.ctypes.data_as(C.c_void_p), 256)
+    assert n >= 0, n
+    return dict(zip(PLAN_FIELDS, list(plan))), ops[:n]
+
+
+def pack(lib, cfg, w, m, plan, opts=None):
+    o = (C.c_int32 * 5)(*(opts or [0] * 5))
+    L = cfg["L"]
+    ups = _lib._PtrArray([w[f"steps.{m}.residual_blocks.{l}.up_proj.weight"] for l in range(L)])
+    downs = _lib._PtrArray([w[f"steps.{m}.residual_blocks.{l}.down_proj.weight"] for l in range(L)])
+    outp = _lib._f32(w[f"steps.{m}.out_proj.weight"]) if cfg["de"] != cfg["D"] else None
+    blob = np.zeros((plan["w_blob_bytes"] + 1) // 2, np.uint16)
+    fp = C.POINTER(C.c_float)
+    lib.qb_plan_pack.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    rc = lib.qb_plan_pack(cfg["D"], cfg["de"], cfg["dh"], L, cfg["K"], int(cfg["qinco1_mode"]), C.cast(o, C.c_void_p),
+                          C.cast(ups.arr, C.c_void_p), C.cast(downs.arr, C.c_void_p),
+                          outp.ctypes.data_as(C.c_void_p) if outp is not None else None,
+                          blob.ctypes.data_as(C.c_void_p), len(blob))
+    assert rc == 0, rc
+    return blob
+
+
+def tables(lib, cfg, w, m):
+    D, De, K = cfg["D"], cfg["de"], cfg["K"]
+    t_blk, cb_blk, wx_t = np.zeros(De * K, np.float32), np.zeros(D * K, np.float32), np.zeros(D * De, np.float32)
+    inp = _lib._f32(w[f"steps.{m}.in_proj.weight"]) if De != D else None
+    vp = C.c_void_p
+    lib.qb_plan_tables.argtypes = [C.c_int] * 3 + [vp] * 7
+    p = lambda a: a.ctypes.data_as(vp) if a is not None else None  # noqa: E731
+    lib.qb_plan_tables(D, De, K, p(_lib._f32(w[f"steps.{m}.codebook.weight"])), p(inp),
+                       p(_lib._f32(w[f"steps.{m}.concat.mlp.weight"])), p(_lib._f32(w[f"steps.{m}.concat.mlp.bias"])),
+                       p(t_blk), p(cb_blk), p(wx_t))
+    T = t_blk.reshape(De // 8, K, 8).transpose(1, 0, 2).reshape(K, De)
+    CB = cb_blk.reshape(D // 8, K, 8).transpose(1, 0, 2).reshape(K, D)
+    return T, CB, wx_t.reshape(D, De)
+
+
+def f16(a):
+    return a.astype(np.float16).astype(np.float32)
+
+
+def replay(plan, ops, blob, T, CB, WxT, codes, xhat):
+    """Software model of qb_mlp_kernel for one tile of rows: returns xhat + f_m(C_m[code], xhat)."""
+    n = len(codes)
+    De, Dh, D, L, hc = plan["De"], plan["Dh"], plan["D"], plan["L"], plan["hc"]
+    tmem = np.zeros((n, 512), np.float32)
+    A = {0: None, 1: None, 2: None}
+    hcol = [plan["tmem_h_col0"], plan["tmem_h_col1"]]
+    e = T[codes] + xhat @ WxT                       # init epilogue
+    tmem[:, :De] = e
+    ae_pending = f16(e)
+    h_chunk_of_buf = {}
+    bytes_view = blob.view(np.uint8)
+
+    def run(op, base, state):
+        nonlocal ae_pending
+        if op["wait_a"] == BAR_AE_READY:
+            A[0] = ae_pending
+        elif op["wait_a"] in (BAR_AH0_READY, BAR_AH1_READY):
+            buf = op["wait_a"] - BAR_AH0_READY
+            cw = state["h_width"][buf]
+            A[1 + buf] = f16(np.maximum(tmem[:, hcol[buf]:hcol[buf] + cw], 0))
+        slab = bytes_view[base + op["w_off"]: base + op["w_off"] + op["w_bytes"]].view(np.float16).astype(np.float32)
+        nn, kk = int(op["n"]), int(op["k"])
+        W = slab.reshape(kk // 8, nn, 8).transpose(1, 0, 2).reshape(nn, kk)
+        a = A[int(op["a_buf"])][:, int(op["a_kc"]) * 8: int(op["a_kc"]) * 8 + kk]
+        prod = a @ W.T
+        c0 = int(op["d_col"])
+        if op["accumulate"]:
+            tmem[:, c0:c0 + nn] += prod
+        else:
+            tmem[:, c0:c0 + nn] = prod
+        if op["commit"] in (BAR_HACC0_FULL, BAR_HACC1_FULL):
+            state["h_width"][op["commit"] - BAR_HACC0_FULL] = nn
+
+    state = {"h_width": [0, 0]}
+    for l in range(L):
+        for op in ops[:plan["n_ops_block"]]:
+            run(op, l * plan["block_w_bytes"], state)
+        assert ops[plan["n_ops_block"] - 1]["commit"] == BAR_EACC_FULL
+        ae_pending = f16(tmem[:, :De])
+    if plan["has_proj"]:
+        o = np.zeros((n, D), np.float32)
+        q = 0
+        for op in ops[plan["n_ops_block"]:]:
+            run(op, 0, state)
+            if op["commit"] in (BAR_HACC0_FULL, BAR_HACC1_FULL):
+                buf = op["commit"] - BAR_HACC0_FULL
+                cw = min(plan["oc"], D - q * plan["oc"])
+                o[:, q * plan["oc"]: q * plan["oc"] + cw] = tmem[:, hcol[buf]:hcol[buf] + cw]
+                q += 1
+        assert q == plan["n_ochunk"]
+    else:
+        o = tmem[:, :D].copy()
+    if plan["skip"]:
+        o = o + CB[codes]
+    return xhat + o
+
+
+SHAPES = {
+    "S": dict(D=128, M=2, K=256, L=2, de=128, dh=256, A=0, B=1, qinco1_mode=False),
+    "Q1": dict(D=128, M=2, K=256, L=3, de=128, dh=256, A=0, B=1, qinco1_mode=True),
+    "L": dict(D=128, M=2, K=256, L=2, de=384, dh=384, A=0, B=1, qinco1_mode=False),
+    "deep": dict(D=96, M=2, K=256, L=2, de=384, dh=384, A=0, B=1, qinco1_mode=False),
+    "contriever": dict(D=768, M=2, K=64, L=1, de=384, dh=384, A=0, B=1, qinco1_mode=False),
+    "odd": dict(D=96, M=2, K=100, L=3, de=192, dh=160, A=0, B=1, qinco1_mode=False),
+    "tiny": dict(D=16, M=2, K=64, L=2, de=32, dh=48, A=0, B=1, qinco1_mode=False),
+    "noblock": dict(D=32, M=2, K=16, L=0, de=32, dh=32, A=0, B=1, qinco1_mode=False),
+}
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+@pytest.mark.parametrize("opts", [None, [64, 1, 8192, 3, 64]])
+def test_op_list_replay_matches_oracle(lib, name, opts):
+    cfg = synth.make_cfg(None, **SHAPES[name])
+    w = synth.make_weights(cfg, seed=3, n_train=512, kmeans_iters=1, fp16_exact=True)
+    plan, ops = export_plan(lib, cfg, opts)
+    # structural invariants of the plan
+    assert plan["smem_total"] <= 227 * 1024 and plan["n_stage"] >= 2
+    assert plan["tmem_h_col0"] + plan["n_hbuf"] * ((plan["hc"] + 31) // 32 * 32) <= 512
+    for op in ops:
+        assert op["w_bytes"] == int(op["n"]) * int(op["k"]) * 2 <= plan["slot_bytes"]
+        assert op["n"] % 16 == 0 and 16 <= op["n"] <= 256 and op["k"] % 16 == 0 and op["w_off"] % 16 == 0
+    blob = pack(lib, cfg, w, 1, plan, opts)
+    T, CB, WxT = tables(lib, cfg, w, 1)
+    rng = np.random.default_rng(0)
+    n = 64
+    codes = rng.integers(0, cfg["K"], n)
+    xhat = rng.standard_normal((n, cfg["D"]), dtype=np.float32)
+    got = replay(plan, ops, blob, T, CB, WxT, codes, xhat)
+    ref = xhat + orc.step_mlp(cfg, w, 1, w["steps.1.codebook.weight"][codes], xhat)
+    rel = float(((got - ref) ** 2).sum() / (ref ** 2).sum())
+    assert rel <= 1e-6, rel   # only the fp16 rounding of activations separates them (weights are fp16-exact)
