@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the QINCo2 encode hot path on B200 (contract: see the task brief / DESIGN.md section "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2a16|c3|c3a0|q1] [--n VECTORS_PER_GPU]
+    python bench.py --impl reference ...      # the reference's PyTorch-CPU path (oracle/torch_port.py) on the host cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one encode pass over one batch of synthetic vectors (n per GPU, resident in HBM for `value`; pinned host
+buffers through the C-ABI host call for `e2e`).  Rows are sharded by rank (weak scaling: n per GPU is fixed) and the
+final uint8 codes are all-gathered once per step with NCCL, inside the timed region.  One JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vectors/sec encoded (8x8 RQ, d=128)"
+UNIT = "vectors/s"
+
+# BASELINE.json configs; model hyper-parameters are the reference presets
+# (reference config/model_args/qinco2-S.yaml, qinco2-L.yaml, qinco1.yaml)
+WORKLOADS = {
+    "c2": dict(name="QINCo2-S 8x8 K=256 d=128 A=0 beam=1", cfg=dict(D=128, M=8, K=256, L=2, de=128, dh=256, A=0, B=1, qinco1_mode=False), n=1_000_000),
+    "c2a16": dict(name="QINCo2-S 8x8 K=256 d=128 A=16 beam=1", cfg=dict(D=128, M=8, K=256, L=2, de=128, dh=256, A=16, B=1, qinco1_mode=False), n=1_000_000),
+    "c3": dict(name="QINCo2-L 8x8 K=256 d=128 A=16 beam=16", cfg=dict(D=128, M=8, K=256, L=16, de=384, dh=384, A=16, B=16, qinco1_mode=False), n=100_000),
+    "c3a0": dict(name="QINCo2-L 8x8 K=256 d=128 A=0 beam=16", cfg=dict(D=128, M=8, K=256, L=16, de=384, dh=384, A=0, B=16, qinco1_mode=False), n=8_192),
+    "q1": dict(name="QINCo1 8x8 K=256 d=128 L=16 beam=1", cfg=dict(D=128, M=8, K=256, L=16, de=128, dh=256, A=0, B=1, qinco1_mode=True), n=200_000),
+}
+
+
+def flops_min_per_candidate(cfg):
+    """hoisted minimum MACs per candidate row x 2."""
+    D, De, Dh, L = cfg["D"], cfg["de"], cfg["dh"], cfg["L"]
+    p = D * De if De != D else 0
+    return 2 * (2 * L * De * Dh + p + D)
+
+
+def encode_flops_min_per_vector(cfg):
+    D, De, M, K, A, B = cfg["D"], cfg["de"], cfg["M"], cfg["K"], cfg["A"], cfg["B"]
+    C = A or K
+    mac = K * D
+    for m in range(1, M):
+        f_in = B
+        mac += (f_in * K * D if A > 0 else 0) + f_in * C * (flops_min_per_candidate(cfg) // 2) + f_in * D * De
+    return 2 * mac
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(tflops=float(j.get("bf16_tflops_sustained") or j["bf16_tflops"]), hbm=float(j["hbm_gbs"]),
+                    source="MEASURED_PEAKS.json (bf16 dense, sustained)")
+    return dict(tflops=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_model_inputs(wl, n, rank):
+    import torch
+    from qinco_b200 import synth
+    cfg = synth.make_cfg(None, **wl["cfg"])
+    w = synth.make_weights(cfg, seed=4321, gain=0.5, n_train=8192, kmeans_iters=3)
+    g = torch.Generator().manual_seed(1234 + rank)
+    x = torch.randn(n, cfg["D"], generator=g, dtype=torch.float32)
+    return cfg, w, x
+
+
+def cpu_port_rate(cfg, w, x_np, budget_s=12.0):
+    """Reference PyTorch-CPU encode (oracle/torch_port.py) on a bounded sample: (vec/s, sample size, codes, xhat, threads)."""
+    import torch
+    from oracle.torch_port import TorchPort
+    threads = os.cpu_count() or 1
+    port = TorchPort(cfg, w, threads=threads)
+    probe = min(len(x_np), 256)
+    t0 = time.perf_counter()
+    port.encode(x_np[:probe])
+    rate0 = probe / (time.perf_counter() - t0)
+    n = int(min(len(x_np), max(256, min(8192, rate0 * budget_s)) // 64 * 64))
+    t0 = time.perf_counter()
+    codes, xhat = port.encode(x_np[:n])
+    dt = time.perf_counter() - t0
+    return n / dt, n, codes.numpy(), xhat.numpy(), torch.get_num_threads(), port
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU path, rank 0 only, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle.torch_port import TorchPort
+    cfg, w, x = make_model_inputs(wl, 4096, 0)
+    threads = os.cpu_count() or 1
+    port = TorchPort(cfg, w, threads=threads)
+    xn = x.numpy()
+    t0 = time.perf_counter()
+    port.encode(xn[:128])
+    rate0 = 128 / (time.perf_counter() - t0)
+    n = int(max(64, min(4096, rate0 * 4.0)) // 64 * 64)       # ~4 s of CPU work per step
+    for _ in range(args.warmup):
+        port.encode(xn[:max(64, n // 8)])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        port.encode(xn[:n])
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    sample = f"{n} of the workload's vectors per step (bounded CPU sample), torch CPU fp32, {torch.get_num_threads()} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "vectors_per_step": n, "device": "cpu"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="vectors per GPU per step (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.n or wl["n"]
+
+    from qinco_b200.model import QINCo
+    cfg, w, x_host = make_model_inputs(wl, n, rank)
+    model = QINCo(cfg, w, device=dev)
+    h = model._h
+    x_pin = x_host.pin_memory()
+    x_dev = x_pin.to(dev, non_blocking=True)
+    gathered = torch.empty((world * n, cfg["M"]), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def step():
+        codes, _ = model.encode_u8(x_dev, normalize=True, want_xhat=False)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, codes)
+        return codes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    h.timing_read()
+    h.timing_enable(True)
+    launches0 = h.launch_count
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        codes = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    launches = h.launch_count - launches0
+    kinds = h.timing_read()
+    h.timing_enable(False)
+    model.synchronize()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * n * args.steps / (ms * 1e-3)
+
+    # ---- end to end: pinned host buffers through the C-ABI host call (H2D + encode + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        x_np = x_pin.numpy()
+        h.encode_host(x_np[: min(n, 65536)], normalize=True)       # warm the staging buffers
+        barrier()
+        t0 = time.perf_counter()
+        k_e2e = max(1, min(args.steps, 3))
+        for _ in range(k_e2e):
+            codes_host, _ = h.encode_host(x_np, normalize=True)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, torch.from_numpy(codes_host).to(dev))
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * k_e2e / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": n * cfg["D"] * 4,
+               "d2h_bytes_per_step": n * cfg["M"], "api": "qb_encode_host (C ABI, host buffers; what codec.encode calls)",
+               "steps": k_e2e}
+        assert np.array_equal(codes_host, codes.cpu().numpy()), "host path and device path disagree"
+
+    if rank == 0:
+        peaks = load_peaks()
+        ms_score, n_score, rows_score = kinds["mlp_score"]
+        fl_launch = flops_min_per_candidate(cfg)
+        achieved = rows_score * fl_launch / (ms_score * 1e-3) / 1e12 if ms_score > 0 else 0.0
+        step_ms = {k: v[0] / args.steps for k, v in kinds.items()}
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands, f32 accumulate/residual/distances", "data": "synthetic",
+            "config": {"workload": wl["name"], "vectors_per_gpu_per_step": n, "global_vectors_per_step": world * n,
+                       "sharding": f"rows over {world} rank(s), one NCCL all-gather of uint8 codes per step",
+                       "l2": f"inputs larger than L2 ({n * cfg['D'] * 4 / 2**20:.0f} MiB of vectors per step)"},
+            "gpu_launches": int(launches),
+            "flops_min_per_vector": encode_flops_min_per_vector(cfg),
+            "tflops_whole_step": value / world * encode_flops_min_per_vector(cfg) / 1e12,
+            "roofline": {"bound": "tensor", "kernel": "qb_mlp_kernel (score)", "achieved": achieved, "peak": peaks["tflops"],
+                         "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
+                         "peak_source": peaks["source"], "launches": int(n_score),
+                         "avg_launch_ms": ms_score / max(n_score, 1),
+                         "flops_per_row": fl_launch, "rows_per_launch": rows_score / max(n_score, 1),
+                         "kernel_share_of_step": ms_score / max(sum(v[0] for v in kinds.values()), 1e-9),
+                         "hbm_gbs_algorithmic": value / world * (4 * cfg["D"] + cfg["M"]) / 1e9},
+            "kernel_ms_per_step": step_ms,
+            "clocks": clocks,
+        }
+        if e2e:
+            out["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            ns = min(n, 8192)
+            rate, n_s, ref_codes, ref_xhat, threads, port = cpu_port_rate(cfg, w, x_host[:ns].numpy())
+            out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": f"first {n_s} vectors of the workload, oracle/torch_port.py (reference op "
+                                             f"sequence in PyTorch CPU fp32), os.cpu_count()={os.cpu_count()}"}
+            # parity on the same sample (decode MSE vs ref; encode MSE of our codes decoded by the reference arithmetic)
+            xs = x_host[:n_s].numpy()
+            ours = codes[:n_s].cpu().numpy().T.astype(np.int64)
+            dec_ours = model.decode(torch.from_numpy(ref_codes).to(dev)).cpu().numpy()
+            dec_ref = port.decode(ref_codes).numpy()
+            mse_ref = float(((xs - ref_xhat) ** 2).sum(1).mean())
+            mse_ours = float(((xs - port.decode(ours).numpy()) ** 2).sum(1).mean())
+            out["parity"] = {"sample": n_s,
+                             "decode_rel_mse_vs_ref": float(((dec_ours - dec_ref) ** 2).sum() / (dec_ref ** 2).sum()),
+                             "encode_mse_ref": mse_ref, "encode_mse_ours": mse_ours,
+                             "encode_mse_rel_diff": abs(mse_ours - mse_ref) / mse_ref,
+                             "vectors_with_identical_codes": float((ours == ref_codes).all(0).mean())}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,7 @@ STATUS = {0: "QB_OK", -1: "QB_ERR_INVALID", -2: "QB_ERR_CUDA", -3: "QB_ERR_WORKS
 # every symbol include/qinco_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ["qb_version", "qb_last_error", "qb_model_create", "qb_model_destroy", "qb_encode_workspace_bytes",
            "qb_decode_workspace_bytes", "qb_encode", "qb_decode", "qb_encode_host", "qb_decode_host", "qb_check",
-           "qb_launch_count", "qb_model_info", "qb_debug_step", "qb_plan_export", "qb_plan_pack", "qb_plan_tables"]
+           "qb_launch_count", "qb_timing_enable", "qb_timing_read", "qb_model_info", "qb_debug_step", "qb_plan_export", "qb_plan_pack", "qb_plan_tables"]
 
 _fpp = C.POINTER(C.POINTER(C.c_float))
 
@@ -78,6 +78,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.qb_check.argtypes = [vp]
     lib.qb_launch_count.argtypes = [vp]
     lib.qb_launch_count.restype = i64
+    lib.qb_timing_enable.argtypes = [vp, C.c_int]
+    lib.qb_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
     lib.qb_model_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.c_int]
     lib.qb_debug_step.argtypes = [vp, C.c_int, vp, vp, i64, vp, vp, sz, vp]
     _lib = lib
@@ -200,6 +202,20 @@ class Handle:
 
     def check(self):
         check(self._lib.qb_check(self._h))
+
+    KINDS = ["prep", "mlp_score", "select", "mlp_apply", "other"]
+
+    def timing_enable(self, on: bool = True):
+        check(self._lib.qb_timing_enable(self._h, int(on)))
+
+    def timing_read(self) -> dict:
+        """{kind: (ms, launches, rows)} since the last read (synchronises on the recorded events)."""
+        n = len(self.KINDS)
+        ms, cnt, rows = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_int64 * n)()
+        rc = self._lib.qb_timing_read(self._h, ms, cnt, rows, n)
+        if rc < 0:
+            check(rc)
+        return {k: (ms[i], cnt[i], rows[i]) for i, k in enumerate(self.KINDS)}
 
     @property
     def launch_count(self) -> int:

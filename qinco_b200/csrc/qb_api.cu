@@ -76,6 +76,11 @@ struct qb_model {
     uint32_t* err_dev = nullptr;
     int64_t launches = 0;
     std::vector<void*> dev_allocs;
+    // optional per-kernel timing (qb_timing_*): CUDA events recorded around every launch on the launch stream
+    bool timing = false;
+    struct Timed { cudaEvent_t a, b; int kind; int64_t rows; };
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> ev_pool;
     // host-variant staging
     int64_t host_chunk = 0;
     HostSlot slot[2];
@@ -169,6 +174,32 @@ void carve(const qb_model* m, void* ws, int64_t nc, Workspace* w) {
     w->selc = take(n * B);
 }
 
+enum { KIND_PREP = 0, KIND_SCORE = 1, KIND_SELECT = 2, KIND_APPLY = 3, KIND_OTHER = 4, KIND_COUNT = 5 };
+
+cudaEvent_t take_event(qb_model* m) {
+    if (!m->ev_pool.empty()) {
+        cudaEvent_t e = m->ev_pool.back();
+        m->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// Runs `launch` (returns cudaError_t) and counts it; with timing on, brackets it with events on `st`.
+template <typename F>
+cudaError_t timed_launch(qb_model* m, int kind, int64_t rows, cudaStream_t st, F&& launch) {
+    m->launches++;
+    if (!m->timing) return launch();
+    qb_model::Timed t{take_event(m), take_event(m), kind, rows};
+    cudaEventRecord(t.a, st);
+    cudaError_t e = launch();
+    cudaEventRecord(t.b, st);
+    m->timed.push_back(t);
+    return e;
+}
+
 qb::MlpParams base_mlp(const qb_model* m, int step) {
     const StepDev& s = m->steps[step];
     qb::MlpParams p;
@@ -202,8 +233,7 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, uint8_t*
         p.xhat = m->cb0; p.sub_cb = m->cb0_t;
         p.xhat_out = (M == 1 && xhat_out) ? xhat_out : w.xhat[cur];
         p.hist_out = (M == 1) ? codes : w.hist[cur];
-        QB_CUDA(qb::launch_prep(p, st));
-        m->launches++;
+        QB_CUDA(timed_launch(m, KIND_PREP, n, st, [&] { return qb::launch_prep(p, st); }));
     }
     int F_in = F1;
     for (int step = 1; step < M; step++) {
@@ -217,8 +247,7 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, uint8_t*
             p.n_beams = n * F_in; p.x = x; p.mean = mean; p.inv_std = inv_std_div;
             p.xhat = w.xhat[cur]; p.wx_t = s.wx_t; p.sub_cb = A > 0 ? s.sub_cb_t : nullptr;
             p.r = w.r; p.u = w.u; p.idx = w.idx;
-            QB_CUDA(qb::launch_prep(p, st));
-            m->launches++;
+            QB_CUDA(timed_launch(m, KIND_PREP, p.n_beams, st, [&] { return qb::launch_prep(p, st); }));
         }
         {
             qb::MlpParams p = base_mlp(m, step);
@@ -226,8 +255,7 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, uint8_t*
             p.C = C; p.A = A;
             p.n_rows = n * F_in * C;
             p.idx = w.idx; p.u = w.u; p.r = w.r; p.dist = w.dist;
-            QB_CUDA(qb::launch_mlp(p, m->n_sm, st));
-            m->launches++;
+            QB_CUDA(timed_launch(m, KIND_SCORE, p.n_rows, st, [&] { return qb::launch_mlp(p, m->n_sm, st); }));
         }
         {
             qb::SelectParams p;
@@ -236,8 +264,7 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, uint8_t*
             p.dist = w.dist; p.idx = A > 0 ? w.idx : nullptr;
             p.hist_in = w.hist[cur]; p.hist_out = last ? codes : w.hist[cur ^ 1];
             p.sel_parent = w.selp; p.sel_code = w.selc;
-            QB_CUDA(qb::launch_select(p, st));
-            m->launches++;
+            QB_CUDA(timed_launch(m, KIND_SELECT, n, st, [&] { return qb::launch_select(p, st); }));
         }
         if (!last || xhat_out) {
             qb::MlpParams p = base_mlp(m, step);
@@ -247,8 +274,7 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, uint8_t*
             p.sel_parent = w.selp; p.sel_code = w.selc; p.code_stride = 1; p.code_off = 0;
             p.u = w.u; p.xhat_in = w.xhat[cur];
             p.xhat_out = last ? xhat_out : w.xhat[cur ^ 1];
-            QB_CUDA(qb::launch_mlp(p, m->n_sm, st));
-            m->launches++;
+            QB_CUDA(timed_launch(m, KIND_APPLY, p.n_rows, st, [&] { return qb::launch_mlp(p, m->n_sm, st); }));
         }
         cur ^= 1;
         F_in = F_out;
@@ -269,12 +295,11 @@ int decode_chunk(qb_model* m, const uint8_t* codes, int64_t n, int denormalize, 
     const float* shift = (denormalize && m->has_mean) ? m->mean : nullptr;
     const bool affine = denormalize && (scale != 1.f || shift);
     int cur = 0;
-    QB_CUDA(qb::launch_decode_init(m->cb0, codes, n, M, D, m->K, (M == 1 && !affine) ? out : xh[cur], m->err_dev, st));
-    m->launches++;
-    if (M == 1 && affine) {
-        QB_CUDA(qb::launch_affine(xh[cur], out, n, D, scale, shift, st));
-        m->launches++;
-    }
+    QB_CUDA(timed_launch(m, KIND_OTHER, n, st, [&] {
+        return qb::launch_decode_init(m->cb0, codes, n, M, D, m->K, (M == 1 && !affine) ? out : xh[cur], m->err_dev, st);
+    }));
+    if (M == 1 && affine)
+        QB_CUDA(timed_launch(m, KIND_OTHER, n, st, [&] { return qb::launch_affine(xh[cur], out, n, D, scale, shift, st); }));
     for (int step = 1; step < M; step++) {
         const StepDev& s = m->steps[step];
         const bool last = step == M - 1;
@@ -284,8 +309,7 @@ int decode_chunk(qb_model* m, const uint8_t* codes, int64_t n, int denormalize, 
             p.D = D; p.De = m->De; p.K = m->K; p.A = 0; p.F = 1; p.step0 = 0; p.M = M;
             p.n_beams = n; p.x = xh[cur]; p.inv_std = 1.f;
             p.xhat = xh[cur]; p.wx_t = s.wx_t; p.u = u;
-            QB_CUDA(qb::launch_prep(p, st));
-            m->launches++;
+            QB_CUDA(timed_launch(m, KIND_PREP, n, st, [&] { return qb::launch_prep(p, st); }));
         }
         {
             qb::MlpParams p = base_mlp(m, step);
@@ -295,8 +319,7 @@ int decode_chunk(qb_model* m, const uint8_t* codes, int64_t n, int denormalize, 
             p.u = u; p.xhat_in = xh[cur];
             p.xhat_out = last ? out : xh[cur ^ 1];
             if (last) { p.out_scale = scale; p.out_shift = shift; }
-            QB_CUDA(qb::launch_mlp(p, m->n_sm, st));
-            m->launches++;
+            QB_CUDA(timed_launch(m, KIND_APPLY, n, st, [&] { return qb::launch_mlp(p, m->n_sm, st); }));
         }
         cur ^= 1;
     }
@@ -449,6 +472,8 @@ int qb_model_destroy(qb_model* m) {
     if (m->s_comp) cudaStreamDestroy(m->s_comp);
     if (m->s_d2h) cudaStreamDestroy(m->s_d2h);
     if (m->err_host) cudaFreeHost(m->err_host);
+    for (auto& t : m->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto e : m->ev_pool) cudaEventDestroy(e);
     delete m;
     return QB_OK;
 }
@@ -589,6 +614,28 @@ int qb_decode_host(qb_model* m, const uint8_t* codes_host, int64_t n, int denorm
 }
 
 int64_t qb_launch_count(const qb_model* m) { return m ? m->launches : 0; }
+
+int qb_timing_enable(qb_model* m, int on) {
+    if (!m) return fail(QB_ERR_INVALID, "model is NULL");
+    m->timing = on != 0;
+    return QB_OK;
+}
+
+int qb_timing_read(qb_model* m, double* ms_out, int64_t* launches_out, int64_t* rows_out, int n_kinds) {
+    if (!m || !ms_out || !launches_out || !rows_out) return fail(QB_ERR_INVALID, "NULL argument");
+    QB_CUDA(cudaSetDevice(m->device));
+    for (int k = 0; k < n_kinds; k++) { ms_out[k] = 0; launches_out[k] = 0; rows_out[k] = 0; }
+    for (auto& t : m->timed) {
+        QB_CUDA(cudaEventSynchronize(t.b));
+        float ms = 0.f;
+        QB_CUDA(cudaEventElapsedTime(&ms, t.a, t.b));
+        if (t.kind < n_kinds) { ms_out[t.kind] += ms; launches_out[t.kind]++; rows_out[t.kind] += t.rows; }
+        m->ev_pool.push_back(t.a);
+        m->ev_pool.push_back(t.b);
+    }
+    m->timed.clear();
+    return KIND_COUNT;
+}
 
 int qb_model_info(const qb_model* m, int step, int32_t* out, int n_out) {
     if (!m || !out) return fail(QB_ERR_INVALID, "NULL argument");

@@ -85,3 +85,15 @@ def test_edge_cases():
     c, h = orc.encode(cfg1, w1, x)
     d = orc.exact_pairwise_distance(x, w1["steps.0.codebook.weight"])
     np.testing.assert_array_equal(c[0], d.argmin(1))
+
+
+@pytest.mark.parametrize("name", GOLDEN_V2)
+def test_torch_port_matches_reference(name, golden_loader):
+    """oracle/torch_port.py (the timed CPU baseline) returns the reference's codes on every fixture."""
+    from oracle.torch_port import TorchPort
+    cfg, w, z = golden_loader(name)
+    port = TorchPort(cfg, w)
+    codes = port.forward(z["x"], "encode").numpy()
+    np.testing.assert_array_equal(codes, z["codes_ref"])
+    dec = port.forward(z["codes_ref"], "decode").numpy()
+    assert ((dec - z["dec_ref"]) ** 2).sum() / (z["dec_ref"] ** 2).sum() <= 1e-10
