@@ -58,8 +58,9 @@ typedef struct {
     const float* const* out_proj;          /* [M] or NULL when De == D */
     const float* data_mean;                /* [D] or NULL (zeros) */
     float data_std;                        /* > 0 */
-    /* kernel planner overrides, 0 = automatic */
-    int32_t opt_hc, opt_n_hbuf, opt_slot_bytes, opt_max_stage, opt_max_slab_k;
+    /* kernel planner overrides, 0 = automatic; opt_n_tiles = n_tiles | ctas_per_sm << 8 */
+    int32_t opt_hc, opt_n_tiles, opt_slot_bytes, opt_max_stage, opt_max_slab_k;
+    int32_t opt_stagger;     /* start delay (cycles) of the second CTA per SM; 0 = automatic, < 0 = none */
 } qb_model_desc;
 
 int qb_version(void);
@@ -111,7 +112,7 @@ int qb_debug_step(qb_model* m, int step, const float* xhat_dev, const uint8_t* c
 
 /* Host-only test hooks (no CUDA call): export the tcgen05 op list of one step (32-byte QbOp records, csrc/qb_plan.h),
  * pack weights into the slab blob and build the hoisted tables, so the CPU test-suite can replay the kernel's dataflow
- * in numpy.  opts5 = {hc, n_hbuf, slot_bytes, max_stage, max_slab_k} or NULL. */
+ * in numpy.  opts5 = {hc, n_tiles, slot_bytes, max_stage, max_slab_k} or NULL. */
 int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const int32_t* opts5, int32_t* plan_out,
                    int n_plan_out, void* ops_out, int max_ops);
 int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int32_t* opts5, const float* const* up,

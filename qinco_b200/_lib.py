@@ -33,8 +33,8 @@ class QbModelDesc(C.Structure):
         ("codebook", _fpp), ("substep_codebook", _fpp), ("concat_w", _fpp), ("concat_b", _fpp), ("up_w", _fpp),
         ("down_w", _fpp), ("in_proj", _fpp), ("out_proj", _fpp),
         ("data_mean", C.POINTER(C.c_float)), ("data_std", C.c_float),
-        ("opt_hc", C.c_int32), ("opt_n_hbuf", C.c_int32), ("opt_slot_bytes", C.c_int32), ("opt_max_stage", C.c_int32),
-        ("opt_max_slab_k", C.c_int32),
+        ("opt_hc", C.c_int32), ("opt_n_tiles", C.c_int32), ("opt_slot_bytes", C.c_int32), ("opt_max_stage", C.c_int32),
+        ("opt_max_slab_k", C.c_int32), ("opt_stagger", C.c_int32),
     ]
 
 
@@ -109,7 +109,7 @@ class _PtrArray:
         return C.cast(self.arr, _fpp)
 
 
-INFO_FIELDS = ["D", "De", "Dh", "L", "K", "has_proj", "skip", "n_ops_block", "n_ops_out", "hc", "n_hchunk", "n_hbuf",
+INFO_FIELDS = ["D", "De", "Dh", "L", "K", "has_proj", "skip", "n_ops_block", "n_ops_out", "hc", "n_hchunk", "ctas_per_sm",
                "oc", "n_ochunk", "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes", "n_sm",
                "default_chunk"]
 

@@ -43,7 +43,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct StepDev {
     QbStepPlan plan;
-    QbOp* ops = nullptr;
+    std::vector<QbOp> ops;
     uint8_t* w_blob = nullptr;
     float* t_blk = nullptr;
     float* cb_blk = nullptr;
@@ -67,6 +67,7 @@ struct HostSlot {
 struct qb_model {
     int D = 0, De = 0, Dh = 0, L = 0, M = 0, K = 0, A = 0, B = 0, q1 = 0, device = 0, n_sm = 0;
     float data_std = 1.f;
+    int stagger = 0;
     bool has_mean = false;
     float* cb0 = nullptr;      // [K][D]
     float* cb0_t = nullptr;    // [D][K]
@@ -205,12 +206,14 @@ qb::MlpParams base_mlp(const qb_model* m, int step) {
     qb::MlpParams p;
     std::memset(&p, 0, sizeof(p));
     p.plan = s.plan;
-    p.ops = s.ops;
+    p.n_ops = (int32_t)s.ops.size();
+    std::memcpy(p.ops, s.ops.data(), s.ops.size() * sizeof(QbOp));
     p.w_blob = s.w_blob;
     p.t_blk = s.t_blk;
     p.cb_blk = s.cb_blk;
     p.out_scale = 1.f;
     p.err_flag = m->err_dev;
+    p.stagger_cycles = m->stagger;
     return p;
 }
 
@@ -413,8 +416,14 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         if ((rc = dev_upload(m, d->data_mean, (size_t)D, &m->mean))) return bail(rc);
     }
     m->steps.resize(m->M);
+    {   // default stagger: ~1.5x the ideal MMA time of one tile (128 rows x 2*L*De*Dh MACs at ~3800 MAC/cycle)
+        const double mma = 128.0 * 2.0 * m->L * m->De * m->Dh / 3800.0;
+        m->stagger = d->opt_stagger > 0 ? d->opt_stagger : 0;
+        (void)mma;
+    }
     qb::PlanOptions opt;
-    opt.hc = d->opt_hc; opt.n_hbuf = d->opt_n_hbuf; opt.slot_bytes = d->opt_slot_bytes;
+    opt.hc = d->opt_hc; opt.n_tiles = d->opt_n_tiles & 0xff; opt.ctas_per_sm = d->opt_n_tiles >> 8;
+    opt.slot_bytes = d->opt_slot_bytes;
     opt.max_stage = d->opt_max_stage; opt.max_slab_k = d->opt_max_slab_k;
     int max_smem = 0;
     for (int s = 1; s < m->M; s++) {
@@ -430,7 +439,7 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         std::vector<float> t_blk((size_t)De * K), cb_blk((size_t)D * K), wx_t((size_t)D * De);
         qb::build_tables(D, De, K, d->codebook[s], De != D ? d->in_proj[s] : nullptr, d->concat_w[s], d->concat_b[s],
                          t_blk.data(), cb_blk.data(), wx_t.data());
-        if ((rc = dev_upload(m, ops.data(), std::max<size_t>(ops.size(), 1), &sd.ops))) return bail(rc);
+        sd.ops = ops;
         if ((rc = dev_upload(m, (const uint8_t*)blob.data(), blob.size() * 2, &sd.w_blob))) return bail(rc);
         if ((rc = dev_upload(m, t_blk.data(), t_blk.size(), &sd.t_blk))) return bail(rc);
         if ((rc = dev_upload(m, cb_blk.data(), cb_blk.size(), &sd.cb_blk))) return bail(rc);
@@ -642,7 +651,7 @@ int qb_model_info(const qb_model* m, int step, int32_t* out, int n_out) {
     if (step < 1 || step >= m->M) return fail(QB_ERR_INVALID, "step out of range (MLP steps are 1..M-1)");
     const QbStepPlan& p = m->steps[step].plan;
     const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk,
-                         p.n_hbuf, p.oc, p.n_ochunk, p.slot_bytes, p.n_stage, p.smem_total, (int32_t)p.block_w_bytes,
+                         p.ctas_per_sm, p.oc, p.n_ochunk, p.slot_bytes, p.n_stage, p.smem_total, (int32_t)p.block_w_bytes,
                          (int32_t)p.w_blob_bytes, m->n_sm, (int32_t)default_chunk(m)};
     const int nv = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < n_out && i < nv; i++) out[i] = v[i];

@@ -8,6 +8,7 @@
 namespace qb {
 
 enum { QB_MODE_SCORE = 0, QB_MODE_APPLY = 1 };
+enum { QB_TRACE_EVENTS = 2048 };
 
 // One launch of the tcgen05 MLP kernel over `n_rows` candidate rows of step m.
 //   score: row -> beam b = row / C, slot a = row % C, code = A ? idx[b*A + a] : a;
@@ -17,7 +18,9 @@ enum { QB_MODE_SCORE = 0, QB_MODE_APPLY = 1 };
 //          decode :282-290, :447-452)
 struct MlpParams {
     QbStepPlan plan;
-    const QbOp* ops;          // device copy of the plan's op list
+    QbOp ops[QB_MAX_OPS];     // the plan's op list; lives in the kernel-parameter constant bank so the MMA / producer
+                              // warps read it through the uniform datapath
+    int32_t n_ops;
     const uint8_t* w_blob;    // packed fp16 slabs of this step
     const float* t_blk;       // [De/8][K][8]  T_m
     const float* cb_blk;      // [D/8][K][8]   C_m (outer skip), unused in qinco1_mode
@@ -37,7 +40,10 @@ struct MlpParams {
     float* xhat_out;          // apply: [n_rows, D]
     float out_scale;          // apply
     const float* out_shift;   // apply: [D] or NULL
+    int32_t exp_flags;        // timing experiments (QB_EXP env): skip parts of the epilogue; results are wrong when != 0
+    int32_t stagger_cycles;   // experiment: start delay of one of two co-resident CTAs (0 = none)
     uint32_t* err_flag;       // device word set non-zero when a barrier wait timed out
+    unsigned long long* trace;   // debug: per-role event log of CTA 0 ([3][QB_TRACE_EVENTS] of clock<<16 | id), or NULL
 };
 
 cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream);

@@ -11,11 +11,12 @@ namespace qb {
 
 struct PlanOptions {
     int hc = 0;           // H chunk width (0 = auto)
-    int n_hbuf = 0;       // Hacc / A_H buffers (0 = auto)
+    int n_tiles = 0;      // 128-row tiles in flight per CTA (0 = auto: 2 when TMEM and shared memory allow)
+    int ctas_per_sm = 0;  // co-resident CTAs per SM (0 = auto: 2 when TMEM and shared memory allow)
     int slot_bytes = 0;   // weight ring slot size (0 = 16 KiB)
-    int max_stage = 0;    // cap on ring depth (0 = 8)
-    int max_slab_k = 0;   // cap on slab K (0 = 128)
-    int smem_budget = 0;  // bytes of dynamic shared memory the kernel may use (0 = 216 KiB; static smem holds the op list)
+    int max_stage = 0;    // cap on ring depth (0 = QB_MAX_STAGE)
+    int max_slab_k = 0;   // cap on slab K (0 = what fits a slot)
+    int smem_budget = 0;  // bytes of dynamic shared memory the kernel may use (0 = 220 KiB, or 110 KiB with two CTAs per SM)
 };
 
 uint16_t f32_to_f16(float f);

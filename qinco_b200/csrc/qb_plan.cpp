@@ -70,115 +70,102 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     p->has_proj = De != D;
     p->skip = qinco1_mode ? 0 : 1;
 
-    // ---- TMEM columns: Eacc [0,De) | Hacc0 | Hacc1 -------------------------------------------------------------
+    // ---- TMEM columns per tile: Eacc [0,De) | Hacc [e_cols, e_cols + hc) ------------------------------------------
     const int e_cols = round_up(De, 32);
-    int hc = opt.hc > 0 ? opt.hc : 128;
-    int n_hbuf = opt.n_hbuf > 0 ? opt.n_hbuf : 2;
     const int h_need = std::max(L > 0 ? Dh : 0, p->has_proj ? D : 0);
+    int hc = opt.hc > 0 ? opt.hc : 128;
     hc = std::min(hc, round_up(std::max(h_need, 16), 16));
-    if (opt.hc <= 0 || opt.n_hbuf <= 0) {            // auto: prefer two 128-wide buffers, then one, then two 64-wide
-        if (e_cols + 2 * round_up(hc, 32) > 512) {
-            if (e_cols + round_up(hc, 32) <= 512) n_hbuf = 1;
-            else { hc = 64; n_hbuf = (e_cols + 128 <= 512) ? 2 : 1; }
-        }
-    }
     if (hc % 16 || hc > 256) { *err = "hc must be a multiple of 16 and <= 256"; return -1; }
-    {   // a second buffer only helps when some phase has more than one chunk
-        const int nh = L > 0 ? (Dh + hc - 1) / hc : 0;
-        const int no = p->has_proj ? (D + std::min(D, hc) - 1) / std::min(D, hc) : 0;
-        if (std::max(nh, no) <= 1) n_hbuf = 1;
+    const int h_cols = h_need > 0 ? round_up(hc, 32) : 0;
+    if (e_cols + h_cols > 512) { *err = "de too large for TMEM: round32(de) + round32(hc) must be <= 512 columns"; return -1; }
+    const int a_kc_bytes = QB_TILE_M * 16;  // one 8-element k-chunk of a 128-row A operand
+    const int ae_bytes = (De / 8) * a_kc_bytes;
+    p->slot_bytes = opt.slot_bytes > 0 ? opt.slot_bytes : 16384;
+    if (p->slot_bytes % 1024) { *err = "slot_bytes must be a multiple of 1024"; return -1; }
+    if (opt.n_tiles > 1) { *err = "n_tiles > 1 is not supported by this kernel generation"; return -1; }
+    // two CTAs per SM: each gets half of TMEM and of the shared memory (228 KB per SM, 1 KB reserved per CTA)
+    int ctas = opt.ctas_per_sm > 0 ? opt.ctas_per_sm : 2;
+    if (ctas == 2 && (e_cols + h_cols > 256 || 110 * 1024 - ae_bytes < 3 * p->slot_bytes)) {
+        if (opt.ctas_per_sm == 2) { *err = "two CTAs per SM do not fit (TMEM columns or shared memory)"; return -1; }
+        ctas = 1;
     }
-    if (e_cols + n_hbuf * round_up(hc, 32) > 512) {
-        *err = "de too large for TMEM: round32(de) + n_hbuf*round32(hc) must be <= 512 columns";
-        return -1;
+    if (ctas > 2) { *err = "ctas_per_sm must be 1 or 2"; return -1; }
+    const int budget = opt.smem_budget > 0 ? opt.smem_budget : (ctas == 2 ? 110 * 1024 : 220 * 1024);
+    p->ctas_per_sm = ctas;
+    {
+        int c = 32;
+        while (c < e_cols + h_cols) c *= 2;
+        p->tmem_alloc_cols = c;
     }
-    p->hc = hc; p->n_hbuf = n_hbuf;
+    p->hc = hc;
     p->n_hchunk = L > 0 ? (Dh + hc - 1) / hc : 0;
     p->oc = p->has_proj ? std::min(D, hc) : 0;
     p->n_ochunk = p->has_proj ? (D + p->oc - 1) / p->oc : 0;
     p->tmem_e_col = 0;
-    p->tmem_h_col[0] = e_cols;
-    p->tmem_h_col[1] = e_cols + round_up(hc, 32);
+    p->tmem_h_col = e_cols;
+    p->tmem_tile_cols = e_cols + h_cols;
 
     // ---- shared memory ------------------------------------------------------------------------------------------
-    const int a_kc_bytes = QB_TILE_M * 16;  // one 8-element k-chunk of a 128-row A operand
     int off = 0;
-    p->smem_ae = off; off += (De / 8) * a_kc_bytes;
-    for (int i = 0; i < 2; i++) { p->smem_ah[i] = off; if (i < n_hbuf && L > 0) off += (hc / 8) * a_kc_bytes; }
-    p->slot_bytes = opt.slot_bytes > 0 ? opt.slot_bytes : 16384;
-    if (p->slot_bytes % 1024) { *err = "slot_bytes must be a multiple of 1024"; return -1; }
+    p->smem_ae = off; off += ae_bytes;
     p->smem_ring = off;
-    const int budget = opt.smem_budget > 0 ? opt.smem_budget : 216 * 1024;
     int n_stage = (budget - off) / p->slot_bytes;
-    n_stage = std::min(n_stage, opt.max_stage > 0 ? opt.max_stage : 8);
-    if (n_stage < 2) { *err = "not enough shared memory for a 2-slot weight ring (de/dh too large)"; return -1; }
+    n_stage = std::min(n_stage, opt.max_stage > 0 ? std::min(opt.max_stage, QB_MAX_STAGE) : QB_MAX_STAGE);
+    if (n_stage < 2) { *err = "not enough shared memory for a 2-slot weight ring (de too large)"; return -1; }
     p->n_stage = n_stage;
     p->smem_total = off + n_stage * p->slot_bytes;
 
     // ---- op list ------------------------------------------------------------------------------------------------
     ops->clear();
     uint32_t w_off = 0;
-    auto slab_k = [&](int n, int k_total) {
-        int k = (p->slot_bytes / (2 * n)) / 16 * 16;
-        k = std::min(k, opt.max_slab_k > 0 ? opt.max_slab_k : 128);
-        return std::max(16, std::min(k, k_total));
-    };
-    // GEMM  D[128, n] (+)= A[128, k_total] . W[rows n][cols k_total]^T, split into K slabs
-    auto emit_gemm = [&](int n, int k_total, uint16_t a_buf, int a_kc0, int d_col, bool acc_first,
+    // GEMM  D[128, n] (+)= A[128, k_total] . W[rows n][cols k_total]^T, W cut along K into ring-slot-sized slabs
+    auto emit_gemm = [&](int n, int k_total, uint8_t a_src, int a_unit0, int d_col, bool acc_first,
                          uint8_t wait_a, uint8_t wait_d, uint8_t commit) {
-        const int ks = slab_k(n, k_total);
-        for (int k0 = 0; k0 < k_total; k0 += ks) {
-            QbOp op;
-            std::memset(&op, 0, sizeof(op));
-            const int k = std::min(ks, k_total - k0);
-            op.w_off = w_off; op.w_bytes = (uint32_t)(n * k * 2);
-            w_off += op.w_bytes;
-            op.n = (uint16_t)n; op.k = (uint16_t)k; op.a_buf = a_buf; op.a_kc = (uint16_t)(a_kc0 + k0 / 8);
-            op.d_col = (uint16_t)d_col;
-            op.accumulate = (acc_first || k0 > 0) ? 1 : 0;
-            op.wait_a = (k0 == 0) ? wait_a : QB_BAR_NONE;
-            op.wait_d = (k0 == 0) ? wait_d : QB_BAR_NONE;
-            op.commit = (k0 + k >= k_total) ? commit : QB_BAR_NONE;
-            ops->push_back(op);
-        }
+        int ks = (p->slot_bytes / (2 * n)) / 16 * 16;
+        if (opt.max_slab_k > 0) ks = std::min(ks, opt.max_slab_k);
+        ks = std::max(16, std::min(ks, k_total));
+        const int n_slab = (k_total + ks - 1) / ks;
+        QbOp op;
+        std::memset(&op, 0, sizeof(op));
+        op.w_off = w_off;
+        op.slab_bytes = (uint32_t)(n * ks * 2);
+        op.last_bytes = (uint32_t)(n * (k_total - (n_slab - 1) * ks) * 2);
+        op.n = (uint16_t)n; op.ks = (uint16_t)ks; op.k_total = (uint16_t)k_total;
+        op.a_off = (uint16_t)a_unit0; op.d_col = (uint16_t)d_col;
+        op.n_slab = (uint8_t)n_slab; op.a_src = a_src; op.accumulate = acc_first ? 1 : 0;
+        op.wait_a = wait_a; op.wait_d = wait_d; op.commit = commit;
+        w_off += (uint32_t)(n * k_total * 2);
+        ops->push_back(op);
     };
     const int n_eparts = (De + 255) / 256;
     const int epart = round_up((De + n_eparts - 1) / n_eparts, 16);
     if (L > 0) {                   // ops of ONE residual block, offsets relative to the block's weights
-        auto m1 = [&](int j) {
-            const int cw = std::min(hc, Dh - j * hc), buf = j % n_hbuf;
-            emit_gemm(cw, De, QB_A_E, 0, p->tmem_h_col[buf], false, j == 0 ? QB_BAR_AE_READY : QB_BAR_NONE,
-                      (uint8_t)(QB_BAR_HACC0_FREE + buf), (uint8_t)(QB_BAR_HACC0_FULL + buf));
-        };
-        auto m2 = [&](int j) {
-            const int cw = std::min(hc, Dh - j * hc), buf = j % n_hbuf;
+        for (int j = 0; j < p->n_hchunk; j++) {
+            const int cw = std::min(hc, Dh - j * hc);
+            // up-projection chunk: Hacc = A_E . Wup[j*hc .. +cw, :]^T
+            emit_gemm(cw, De, QB_A_E, 0, p->tmem_h_col, false, j == 0 ? QB_BAR_AE_READY : QB_BAR_NONE, QB_BAR_NONE,
+                      QB_BAR_HACC_FULL);
+            // down-projection of the chunk: Eacc[:, n0..] += relu(h)[:, chunk] . Wdn[n0.., j*hc .. +cw]^T
             for (int n0 = 0; n0 < De; n0 += epart) {
                 const int n = std::min(epart, De - n0);
                 const bool last = (j == p->n_hchunk - 1) && (n0 + n >= De);
-                emit_gemm(n, cw, (uint16_t)(QB_A_H0 + buf), 0, p->tmem_e_col + n0, true,
-                          n0 == 0 ? (uint8_t)(QB_BAR_AH0_READY + buf) : QB_BAR_NONE, QB_BAR_NONE,
-                          last ? QB_BAR_EACC_FULL : QB_BAR_NONE);
+                emit_gemm(n, cw, QB_A_H, p->tmem_h_col, p->tmem_e_col + n0, true,
+                          n0 == 0 ? QB_BAR_AH_READY : QB_BAR_NONE, QB_BAR_NONE, last ? QB_BAR_EACC_FULL : QB_BAR_NONE);
             }
-        };
-        if (n_hbuf == 2) {          // software pipeline: MMA1(j+1) is issued before MMA2(j)
-            m1(0);
-            for (int j = 0; j < p->n_hchunk; j++) { if (j + 1 < p->n_hchunk) m1(j + 1); m2(j); }
-        } else {
-            for (int j = 0; j < p->n_hchunk; j++) { m1(j); m2(j); }
         }
     }
     p->n_ops_block = (int)ops->size();
     p->block_w_bytes = w_off;
     w_off = (uint32_t)(p->block_w_bytes * L);      // out_proj slabs follow the L blocks
     for (int q = 0; q < p->n_ochunk; q++) {
-        const int cw = std::min(p->oc, D - q * p->oc), buf = q % n_hbuf;
-        emit_gemm(cw, De, QB_A_E, 0, p->tmem_h_col[buf], false, q == 0 ? QB_BAR_AE_READY : QB_BAR_NONE,
-                  (uint8_t)(QB_BAR_HACC0_FREE + buf), (uint8_t)(QB_BAR_HACC0_FULL + buf));
+        const int cw = std::min(p->oc, D - q * p->oc);
+        emit_gemm(cw, De, QB_A_E, 0, p->tmem_h_col, false, q == 0 ? QB_BAR_AE_READY : QB_BAR_NONE,
+                  q > 0 ? QB_BAR_HACC_FREE : QB_BAR_NONE, QB_BAR_HACC_FULL);
     }
     p->n_ops_out = (int)ops->size() - p->n_ops_block;
     if (ops->size() > QB_MAX_OPS) { *err = "op list too long"; return -1; }
-    for (auto& op : *ops)
-        if ((int)op.w_bytes > p->slot_bytes) { *err = "internal: slab larger than ring slot"; return -1; }
+    for (const QbOp& op : *ops)
+        if ((int)op.slab_bytes > p->slot_bytes || op.n_slab < 1) { *err = "internal: slab larger than ring slot"; return -1; }
     p->w_blob_bytes = std::max<int64_t>(w_off, 16);
     return 0;
 }
@@ -189,11 +176,15 @@ int pack_step_weights(const QbStepPlan& p, const std::vector<QbOp>& ops, const f
     const int D = p.D, De = p.De, Dh = p.Dh, hc = p.hc;
     const int n_eparts = (De + 255) / 256;
     const int epart = round_up((De + n_eparts - 1) / n_eparts, 16);
+    // slab s of an op holds columns [s*ks, ...) of W rows [row0, row0+n) as [k/8][n][8]
     auto put = [&](const QbOp& op, size_t base, const float* w, int ld, int row0, int col0) {
-        uint16_t* dst = blob + (base + op.w_off) / 2;
-        for (int k = 0; k < op.k; k++)
-            for (int r = 0; r < op.n; r++)
-                dst[((size_t)(k / 8) * op.n + r) * 8 + (k % 8)] = f32_to_f16(w[(size_t)(row0 + r) * ld + col0 + k]);
+        for (int s = 0; s < op.n_slab; s++) {
+            uint16_t* dst = blob + (base + op.w_off + (size_t)s * op.slab_bytes) / 2;
+            const int k0 = s * op.ks, kn = std::min<int>(op.ks, op.k_total - k0);
+            for (int k = 0; k < kn; k++)
+                for (int r = 0; r < op.n; r++)
+                    dst[((size_t)(k / 8) * op.n + r) * 8 + (k % 8)] = f32_to_f16(w[(size_t)(row0 + r) * ld + col0 + k0 + k]);
+        }
     };
     for (int l = 0; l <= p.L; l++) {
         const bool out_phase = (l == p.L);
@@ -202,29 +193,17 @@ int pack_step_weights(const QbStepPlan& p, const std::vector<QbOp>& ops, const f
         const size_t base = out_phase ? 0 : (size_t)l * (size_t)p.block_w_bytes;
         int rc = 0;
         auto take = [&](const float* w, int ld, int row0, int n, int col0, int k_total) {
-            int k0 = 0;
-            while (k0 < k_total) {
-                if (cursor >= end) return -1;
-                const QbOp& op = ops[cursor++];
-                if (op.n != n) return -1;
-                put(op, base, w, ld, row0, col0 + k0);
-                k0 += op.k;
-            }
-            return k0 == k_total ? 0 : -1;
+            if (cursor >= end) return -1;
+            const QbOp& op = ops[cursor++];
+            if (op.n != n || op.k_total != k_total) return -1;
+            put(op, base, w, ld, row0, col0);
+            return 0;
         };
         if (!out_phase) {
-            auto m1 = [&](int j) { return take(up[l], De, j * hc, std::min(hc, Dh - j * hc), 0, De); };
-            auto m2 = [&](int j) {
+            for (int j = 0; j < p.n_hchunk; j++) {
                 const int cw = std::min(hc, Dh - j * hc);
-                for (int n0 = 0; n0 < De; n0 += epart)
-                    if (take(down[l], Dh, n0, std::min(epart, De - n0), j * hc, cw)) return -1;
-                return 0;
-            };
-            if (p.n_hbuf == 2) {
-                rc |= m1(0);
-                for (int j = 0; j < p.n_hchunk; j++) { if (j + 1 < p.n_hchunk) rc |= m1(j + 1); rc |= m2(j); }
-            } else {
-                for (int j = 0; j < p.n_hchunk; j++) { rc |= m1(j); rc |= m2(j); }
+                rc |= take(up[l], De, j * hc, cw, 0, De);
+                for (int n0 = 0; n0 < De; n0 += epart) rc |= take(down[l], Dh, n0, std::min(epart, De - n0), j * hc, cw);
             }
         } else {
             for (int q = 0; q < p.n_ochunk; q++) rc |= take(out_proj, De, q * p.oc, std::min(p.oc, D - q * p.oc), 0, De);
@@ -271,16 +250,16 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
                    int n_plan_out, void* ops_out, int max_ops) {
     qb::PlanOptions opt;
     if (opts5) {
-        opt.hc = opts5[0]; opt.n_hbuf = opts5[1]; opt.slot_bytes = opts5[2]; opt.max_stage = opts5[3];
-        opt.max_slab_k = opts5[4];
+        opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.ctas_per_sm = opts5[1] >> 8; opt.slot_bytes = opts5[2];
+        opt.max_stage = opts5[3]; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
     std::vector<QbOp> ops;
     std::string err;
     if (qb::make_step_plan(D, De, Dh, L, K, qinco1_mode, opt, &p, &ops, &err)) return -1;
-    const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk,
-                         p.n_hbuf, p.oc, p.n_ochunk, p.tmem_e_col, p.tmem_h_col[0], p.tmem_h_col[1], p.smem_ae,
-                         p.smem_ah[0], p.smem_ah[1], p.smem_ring, p.slot_bytes, p.n_stage, p.smem_total,
+    const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.ctas_per_sm, p.tmem_alloc_cols,
+                         p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk, p.oc, p.n_ochunk, p.tmem_e_col, p.tmem_h_col,
+                         p.tmem_tile_cols, p.smem_ae, p.smem_ring, p.slot_bytes, p.n_stage, p.smem_total,
                          (int32_t)p.block_w_bytes, (int32_t)p.w_blob_bytes};
     const int nv = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < nv && i < n_plan_out; i++) plan_out[i] = v[i];
@@ -293,8 +272,8 @@ int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int
                  const float* const* down, const float* out_proj, uint16_t* blob, int64_t blob_halfs) {
     qb::PlanOptions opt;
     if (opts5) {
-        opt.hc = opts5[0]; opt.n_hbuf = opts5[1]; opt.slot_bytes = opts5[2]; opt.max_stage = opts5[3];
-        opt.max_slab_k = opts5[4];
+        opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.ctas_per_sm = opts5[1] >> 8; opt.slot_bytes = opts5[2];
+        opt.max_stage = opts5[3]; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
     std::vector<QbOp> ops;

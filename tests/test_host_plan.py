@@ -14,14 +14,14 @@ from qinco_b200 import _lib, synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-OP_DTYPE = np.dtype([("w_off", "<u4"), ("w_bytes", "<u4"), ("n", "<u2"), ("k", "<u2"), ("a_buf", "<u2"), ("a_kc", "<u2"),
-                     ("d_col", "<u2"), ("accumulate", "u1"), ("wait_a", "u1"), ("wait_d", "u1"), ("commit", "u1"),
-                     ("pad", "u1", 10)])
-PLAN_FIELDS = ["D", "De", "Dh", "L", "K", "has_proj", "skip", "n_ops_block", "n_ops_out", "hc", "n_hchunk", "n_hbuf", "oc",
-               "n_ochunk", "tmem_e_col", "tmem_h_col0", "tmem_h_col1", "smem_ae", "smem_ah0", "smem_ah1", "smem_ring",
+OP_DTYPE = np.dtype([("w_off", "<u4"), ("slab_bytes", "<u4"), ("last_bytes", "<u4"), ("n", "<u2"), ("ks", "<u2"),
+                     ("k_total", "<u2"), ("a_off", "<u2"), ("d_col", "<u2"), ("n_slab", "u1"), ("a_src", "u1"),
+                     ("accumulate", "u1"), ("wait_a", "u1"), ("wait_d", "u1"), ("commit", "u1"), ("pad", "u1", 4)])
+PLAN_FIELDS = ["D", "De", "Dh", "L", "K", "has_proj", "skip", "ctas_per_sm", "tmem_alloc_cols", "n_ops_block", "n_ops_out",
+               "hc", "n_hchunk", "oc", "n_ochunk", "tmem_e_col", "tmem_h_col", "tmem_tile_cols", "smem_ae", "smem_ring",
                "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes"]
-BAR_AE_READY, BAR_AH0_READY, BAR_AH1_READY = 1, 2, 3
-BAR_HACC0_FULL, BAR_HACC1_FULL, BAR_EACC_FULL = 6, 7, 8
+A_E, A_H = 0, 1
+BAR_AE_READY, BAR_AH_READY, BAR_HACC_FREE, BAR_HACC_FULL, BAR_EACC_FULL = 1, 2, 3, 4, 5
 
 
 @pytest.fixture(scope="module")
@@ -112,56 +112,66 @@ def f16(a):
 
 
 def replay(plan, ops, blob, T, CB, WxT, codes, xhat):
-    """Software model of qb_mlp_kernel for one tile of rows: returns xhat + f_m(C_m[code], xhat)."""
+    """Software model of qb_mlp_kernel for one tile of rows: returns xhat + f_m(C_m[code], xhat).
+
+    Every op is replayed slab by slab exactly as the MMA warp walks it (K=16 MMAs over ring slots), so the slab
+    offsets / sizes the producer streams are checked together with the operand offsets.
+    """
     n = len(codes)
-    De, Dh, D, L, hc = plan["De"], plan["Dh"], plan["D"], plan["L"], plan["hc"]
+    De, D, L = plan["De"], plan["D"], plan["L"]
+    hcol = plan["tmem_h_col"]
     tmem = np.zeros((n, 512), np.float32)
-    A = {0: None, 1: None, 2: None}
-    hcol = [plan["tmem_h_col0"], plan["tmem_h_col1"]]
-    e = T[codes] + xhat @ WxT                       # init epilogue
+    e = T[codes] + xhat @ WxT                          # init epilogue
     tmem[:, :De] = e
-    ae_pending = f16(e)
-    h_chunk_of_buf = {}
+    state = dict(AE=None, AH=None, ae_pending=f16(e), hw=0, oq=0)
+    out = np.zeros((n, D), np.float32)
     bytes_view = blob.view(np.uint8)
 
-    def run(op, base, state):
-        nonlocal ae_pending
+    def run(op, base, out_phase):
         if op["wait_a"] == BAR_AE_READY:
-            A[0] = ae_pending
-        elif op["wait_a"] in (BAR_AH0_READY, BAR_AH1_READY):
-            buf = op["wait_a"] - BAR_AH0_READY
-            cw = state["h_width"][buf]
-            A[1 + buf] = f16(np.maximum(tmem[:, hcol[buf]:hcol[buf] + cw], 0))
-        slab = bytes_view[base + op["w_off"]: base + op["w_off"] + op["w_bytes"]].view(np.float16).astype(np.float32)
-        nn, kk = int(op["n"]), int(op["k"])
-        W = slab.reshape(kk // 8, nn, 8).transpose(1, 0, 2).reshape(nn, kk)
-        a = A[int(op["a_buf"])][:, int(op["a_kc"]) * 8: int(op["a_kc"]) * 8 + kk]
-        prod = a @ W.T
+            state["AE"] = state["ae_pending"]
+        elif op["wait_a"] == BAR_AH_READY:
+            state["AH"] = f16(np.maximum(tmem[:, hcol:hcol + state["hw"]], 0))   # in-place packed fp16 operand
+        nn, ks, kt = int(op["n"]), int(op["ks"]), int(op["k_total"])
+        assert op["slab_bytes"] == nn * ks * 2 <= plan["slot_bytes"]
+        assert op["n_slab"] == -(-kt // ks) and op["last_bytes"] == nn * (kt - (int(op["n_slab"]) - 1) * ks) * 2
         c0 = int(op["d_col"])
-        if op["accumulate"]:
-            tmem[:, c0:c0 + nn] += prod
-        else:
-            tmem[:, c0:c0 + nn] = prod
-        if op["commit"] in (BAR_HACC0_FULL, BAR_HACC1_FULL):
-            state["h_width"][op["commit"] - BAR_HACC0_FULL] = nn
+        acc = bool(op["accumulate"])
+        for s in range(int(op["n_slab"])):
+            kk = min(ks, kt - s * ks)
+            off = base + int(op["w_off"]) + s * int(op["slab_bytes"])
+            slab = bytes_view[off: off + nn * kk * 2].view(np.float16).astype(np.float32)
+            W = slab.reshape(kk // 8, nn, 8).transpose(1, 0, 2).reshape(nn, kk)
+            if op["a_src"] == A_E:
+                k0 = int(op["a_off"]) * 8 + s * ks
+                a = state["AE"][:, k0:k0 + kk]
+            else:
+                k0 = (int(op["a_off"]) - hcol) * 2 + s * ks
+                a = state["AH"][:, k0:k0 + kk]
+            assert a.shape[1] == kk
+            prod = a @ W.T
+            if acc:
+                tmem[:, c0:c0 + nn] += prod
+            else:
+                tmem[:, c0:c0 + nn] = prod
+            acc = True
+        if op["commit"] == BAR_HACC_FULL:
+            state["hw"] = nn
+            if out_phase:
+                q = state["oq"]
+                out[:, q * plan["oc"]: q * plan["oc"] + nn] = tmem[:, hcol:hcol + nn]
+                state["oq"] += 1
 
-    state = {"h_width": [0, 0]}
     for l in range(L):
         for op in ops[:plan["n_ops_block"]]:
-            run(op, l * plan["block_w_bytes"], state)
+            run(op, l * plan["block_w_bytes"], False)
         assert ops[plan["n_ops_block"] - 1]["commit"] == BAR_EACC_FULL
-        ae_pending = f16(tmem[:, :De])
+        state["ae_pending"] = f16(tmem[:, :De])
+    for op in ops[plan["n_ops_block"]:]:
+        run(op, 0, True)
     if plan["has_proj"]:
-        o = np.zeros((n, D), np.float32)
-        q = 0
-        for op in ops[plan["n_ops_block"]:]:
-            run(op, 0, state)
-            if op["commit"] in (BAR_HACC0_FULL, BAR_HACC1_FULL):
-                buf = op["commit"] - BAR_HACC0_FULL
-                cw = min(plan["oc"], D - q * plan["oc"])
-                o[:, q * plan["oc"]: q * plan["oc"] + cw] = tmem[:, hcol[buf]:hcol[buf] + cw]
-                q += 1
-        assert q == plan["n_ochunk"]
+        assert state["oq"] == plan["n_ochunk"]
+        o = out
     else:
         o = tmem[:, :D].copy()
     if plan["skip"]:
@@ -182,17 +192,18 @@ SHAPES = {
 
 
 @pytest.mark.parametrize("name", list(SHAPES))
-@pytest.mark.parametrize("opts", [None, [64, 1, 8192, 3, 64]])
+@pytest.mark.parametrize("opts", [None, [64, 1 | (1 << 8), 8192, 3, 32], [0, 0, 32768, 0, 0]])
 def test_op_list_replay_matches_oracle(lib, name, opts):
     cfg = synth.make_cfg(None, **SHAPES[name])
     w = synth.make_weights(cfg, seed=3, n_train=512, kmeans_iters=1, fp16_exact=True)
     plan, ops = export_plan(lib, cfg, opts)
     # structural invariants of the plan
-    assert plan["smem_total"] <= 227 * 1024 and plan["n_stage"] >= 2
-    assert plan["tmem_h_col0"] + plan["n_hbuf"] * ((plan["hc"] + 31) // 32 * 32) <= 512
+    assert plan["n_stage"] >= 2 and plan["ctas_per_sm"] in (1, 2)
+    assert plan["smem_total"] + 2048 <= (227 * 1024 if plan["ctas_per_sm"] == 1 else 113 * 1024)
+    assert plan["tmem_tile_cols"] <= plan["tmem_alloc_cols"] <= 512 // plan["ctas_per_sm"]
+    assert plan["tmem_alloc_cols"] & (plan["tmem_alloc_cols"] - 1) == 0
     for op in ops:
-        assert op["w_bytes"] == int(op["n"]) * int(op["k"]) * 2 <= plan["slot_bytes"]
-        assert op["n"] % 16 == 0 and 16 <= op["n"] <= 256 and op["k"] % 16 == 0 and op["w_off"] % 16 == 0
+        assert op["n"] % 16 == 0 and 16 <= op["n"] <= 256 and op["ks"] % 16 == 0 and op["w_off"] % 16 == 0
     blob = pack(lib, cfg, w, 1, plan, opts)
     T, CB, WxT = tables(lib, cfg, w, 1)
     rng = np.random.default_rng(0)

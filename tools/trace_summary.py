@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Print a phase timeline from a QB_MLP_TRACE dump (CTA 0): usage trace_summary.py file [n_events]"""
+import sys
+ev = {0: [], 1: [], 2: []}
+for line in open(sys.argv[1]):
+    if line.startswith("#"):
+        print(line.strip()); continue
+    r, t, i = line.split()
+    ev[int(r)].append((int(t), int(i, 16)))
+t0 = min(e[0][0] for e in ev.values() if e)
+names = {1: "init start", 2: "init done (AE_READY)", 3: "HACC_FULL seen", 4: "H-epi done (AH_READY)", 5: "EACC_FULL seen", 6: "E-epi done (AE_READY)", 8: "tile done"}
+allev = []
+for t, i in ev[0]: allev.append((t - t0, "EPI ", names.get(i, ("init batch %d" % (i - 0x10)) if 0x10 <= i < 0x20 else ("final batch %d" % (i - 0x20)) if 0x20 <= i < 0x40 else hex(i))))
+for t, i in ev[1]:
+    kind = {0x200: "ops ready, wait slab", 0x300: "slab ready, issue", 0x400: "issued"}[i & 0xf00]
+    allev.append((t - t0, "MMA ", f"op {i & 0xff:2d} {kind}"))
+for t, i in ev[2]: allev.append((t - t0, "PROD", f"slab for op {i & 0xff:2d} slot free -> copy issued"))
+allev.sort()
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 150
+prev = 0
+for t, who, what in allev[:n]:
+    print(f"{t:9d} (+{t - prev:6d}) {who} {what}")
+    prev = t
+# per-tile duration
+starts = [t for t, i in ev[0] if i == 1]
+if len(starts) > 2:
+    d = [b - a for a, b in zip(starts, starts[1:])]
+    print("tile period (cycles): min", min(d), "median", sorted(d)[len(d) // 2], "max", max(d), "n", len(d))
