@@ -213,7 +213,6 @@ qb::MlpParams base_mlp(const qb_model* m, int step) {
     p.cb_blk = s.cb_blk;
     p.out_scale = 1.f;
     p.err_flag = m->err_dev;
-    p.stagger_cycles = m->stagger;
     return p;
 }
 
@@ -651,7 +650,7 @@ int qb_model_info(const qb_model* m, int step, int32_t* out, int n_out) {
     if (step < 1 || step >= m->M) return fail(QB_ERR_INVALID, "step out of range (MLP steps are 1..M-1)");
     const QbStepPlan& p = m->steps[step].plan;
     const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk,
-                         p.ctas_per_sm, p.oc, p.n_ochunk, p.slot_bytes, p.n_stage, p.smem_total, (int32_t)p.block_w_bytes,
+                         p.n_tiles, p.oc, p.n_ochunk, p.slot_bytes, p.n_stage, p.smem_total, (int32_t)p.block_w_bytes,
                          (int32_t)p.w_blob_bytes, m->n_sm, (int32_t)default_chunk(m)};
     const int nv = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < n_out && i < nv; i++) out[i] = v[i];

@@ -40,8 +40,6 @@ struct MlpParams {
     float* xhat_out;          // apply: [n_rows, D]
     float out_scale;          // apply
     const float* out_shift;   // apply: [D] or NULL
-    int32_t exp_flags;        // timing experiments (QB_EXP env): skip parts of the epilogue; results are wrong when != 0
-    int32_t stagger_cycles;   // experiment: start delay of one of two co-resident CTAs (0 = none)
     uint32_t* err_flag;       // device word set non-zero when a barrier wait timed out
     unsigned long long* trace;   // debug: per-role event log of CTA 0 ([3][QB_TRACE_EVENTS] of clock<<16 | id), or NULL
 };

@@ -29,6 +29,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "qb_dev.h"
@@ -37,8 +38,10 @@ namespace qb {
 
 namespace {
 
-constexpr int kEpiThreads = 128;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 16;             // four warps per TMEM lane quarter: warp w owns lanes 32*(w%4).., column quarter w/4
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = kEpiThreads + 64;   // + producer warp + MMA warp
+constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 constexpr int kAkcBytes = QB_TILE_M * 16;   // bytes of one 8-element k-chunk of an A operand tile
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -216,59 +219,60 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, int nc, uint32_t (&
     }
 }
 
-// fp32 accumulator columns [0, cw) at `taddr` -> fp16 -> A_E k-chunks starting at `sdst` (shared memory).
-// One tcgen05.ld stays in flight while the previous 32 columns are converted and stored.
-__device__ __forceinline__ void acc_to_smem_operand(uint32_t taddr, int cw, uint32_t sdst /* + tid*16 already added */) {
-    uint32_t va[32], vb[32];
-    auto emit = [&](const uint32_t (&v)[32], int c, int nc) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (i * 8 < nc) {
-                uint32_t w[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    w[j] = pack_h2(__uint_as_float(v[i * 8 + 2 * j]), __uint_as_float(v[i * 8 + 2 * j + 1]));
-                st_shared_v4(sdst + (uint32_t)((c / 8 + i) * kAkcBytes), w[0], w[1], w[2], w[3]);
-            }
-        }
-    };
-    tmem_ld_cols(taddr, cw, va);
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// Column range [c0, c1) of a width-W block (W a multiple of 16) owned by column quarter cq: 16-column units are dealt
+// out as evenly as possible.
+__device__ __forceinline__ void quarter_range(int W, int cq, int& c0, int& c1) {
+    const int units = W >> 4, base = units >> 2, rem = units & 3;
+    const int u0 = cq * base + (cq < rem ? cq : rem);
+    c0 = u0 << 4;
+    c1 = (u0 + base + (cq < rem ? 1 : 0)) << 4;
+}
+
+// fp32 accumulator columns [c0, c1) at `taddr` -> fp16 -> A_E k-chunks (shared memory, `sdst` already includes the row)
+__device__ __forceinline__ void acc_to_smem_operand(uint32_t taddr, int c0, int c1, uint32_t sdst) {
 #pragma unroll 1
-    for (int c = 0; c < cw; c += 64) {
+    for (int c = c0; c < c1; c += 32) {
+        uint32_t v[32];
+        const int n = c1 - c;
+        tmem_ld_cols(taddr + c, n, v);
         tmem_wait_ld();
-        if (c + 32 < cw) tmem_ld_cols(taddr + c + 32, cw - c - 32, vb);
-        emit(va, c, cw - c);
-        if (c + 32 < cw) {
-            tmem_wait_ld();
-            if (c + 64 < cw) tmem_ld_cols(taddr + c + 64, cw - c - 64, va);
-            emit(vb, c + 32, cw - c - 32);
-        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (i * 8 < n)
+                st_shared_v4(sdst + (uint32_t)((c / 8 + i) * kAkcBytes),
+                             pack_h2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
+                             pack_h2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
+                             pack_h2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
+                             pack_h2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
     }
 }
 
-// fp32 Hacc columns [0, cw) at `taddr` -> relu -> packed fp16 pairs written back in place at columns [0, cw/2).
-// Packed column c/2 + j is written only after fp32 columns [c, c+32) were read, and the load kept in flight reads
-// columns >= c + 32 >= c/2 + 16, so the in-place compaction never overwrites unread data.
-__device__ __forceinline__ void acc_to_tmem_operand(uint32_t taddr, int cw) {
+// fp32 Hacc columns [c0, c1) (c1 - c0 <= 64) at `taddr` -> relu -> packed fp16 pairs written back IN PLACE at columns
+// [c0/2, c1/2).  The packed block of a higher column quarter lands on fp32 columns a lower quarter's thread still has
+// to read, so the four warps sharing a lane quarter first pull their whole range into registers, meet at a named
+// barrier and only then write.
+__device__ __forceinline__ void acc_to_tmem_operand(uint32_t taddr, int c0, int c1, int quarter_bar) {
     uint32_t va[32], vb[32];
-    auto emit = [&](const uint32_t (&v)[32], int c, int nc) {
+    const int n = c1 - c0;
+    if (n > 0) tmem_ld_cols(taddr + c0, n, va);
+    if (n > 32) tmem_ld_cols(taddr + c0 + 32, n - 32, vb);
+    tmem_wait_ld();
+    named_bar_sync(quarter_bar, 128);
+    if (n > 0) {
         uint32_t w[16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) w[j] = pack_h2_relu(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        for (int j = 0; j < 16; j++) w[j] = pack_h2_relu(__uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
         __syncwarp();
-        if (nc >= 32) tmem_st16(taddr + (c >> 1), w); else tmem_st8(taddr + (c >> 1), w);
-    };
-    tmem_ld_cols(taddr, cw, va);
-#pragma unroll 1
-    for (int c = 0; c < cw; c += 64) {
-        tmem_wait_ld();
-        if (c + 32 < cw) tmem_ld_cols(taddr + c + 32, cw - c - 32, vb);
-        emit(va, c, cw - c);
-        if (c + 32 < cw) {
-            tmem_wait_ld();
-            if (c + 64 < cw) tmem_ld_cols(taddr + c + 64, cw - c - 64, va);
-            emit(vb, c + 32, cw - c - 32);
-        }
+        if (n >= 32) tmem_st16(taddr + (c0 >> 1), w); else tmem_st8(taddr + (c0 >> 1), w);
+    }
+    if (n > 32) {
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) w[j] = pack_h2_relu(__uint_as_float(vb[2 * j]), __uint_as_float(vb[2 * j + 1]));
+        __syncwarp();
+        if (n >= 64) tmem_st16(taddr + ((c0 + 32) >> 1), w); else tmem_st8(taddr + ((c0 + 32) >> 1), w);
     }
     tmem_wait_st();
 }
@@ -286,124 +290,42 @@ struct Tracer {
     }
 };
 
-struct RowCtx {
-    bool valid;
-    int64_t row;    // global row
-    int64_t beam;   // (vector, beam) index b
-    int code;
-};
-
-// 32 columns of the skip codeword C_m[code][d0 .. d0+32) (blocked table [D/8][K][8]); all loads issued together
-__device__ __forceinline__ void load_cb64(const MlpParams& p, const RowCtx& rc, int d0, int cols, float4 (&cb)[8]) {
-    const int K = p.plan.K;
-    const float* base = p.cb_blk + ((size_t)(d0 >> 3) * K + rc.code) * 8 + (d0 & 7);   // d0 is a multiple of 16
-#pragma unroll
-    for (int i = 0; i < 4; i++) cb[i] = ldg4(base + (size_t)(i >> 1) * K * 8 + (i & 1) * 4);
-    if (cols > 16) {
-#pragma unroll
-        for (int i = 4; i < 8; i++) cb[i] = ldg4(base + (size_t)(i >> 1) * K * 8 + (i & 1) * 4);
-    }
-}
-
-// Final epilogue over accumulator columns [0, cw) at taddr that hold o[d0 .. d0+cw).  `cb` holds the prefetched skip
-// codeword of the first 32 columns (when plan.skip); every 16-column slot of it is refilled with the columns 32 further
-// on as soon as it has been used, and the accumulator is read 16 columns at a time with the next read in flight.
-template <bool kScore>
-__device__ __forceinline__ void consume_out(const MlpParams& p, const RowCtx& rc, uint32_t taddr, int cw, int d0,
-                                            float4 (&cb)[8], float& acc) {
-    const int D = p.plan.D;
-    const float* src = (kScore ? p.r : p.xhat_in) + rc.beam * D + d0;
-    uint32_t va[32], vb[32];
-    auto emit = [&](const uint32_t (&v)[32], int cc, int h /* 16-column slot (0/1) of the skip-codeword buffer */) {
-        float4 t[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) t[i] = (p.exp_flags & 8) ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4_jit(src + cc + i * 4);
-        float o[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) o[i] = __uint_as_float(v[i]);
-        if (p.plan.skip) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const float4 cv = cb[4 * h + i];
-                o[4 * i] += cv.x; o[4 * i + 1] += cv.y; o[4 * i + 2] += cv.z; o[4 * i + 3] += cv.w;
-            }
-        }
-        if (kScore) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const float e0 = t[i].x - o[4 * i], e1 = t[i].y - o[4 * i + 1], e2 = t[i].z - o[4 * i + 2], e3 = t[i].w - o[4 * i + 3];
-                acc = fmaf(e0, e0, acc); acc = fmaf(e1, e1, acc); acc = fmaf(e2, e2, acc); acc = fmaf(e3, e3, acc);
-            }
-        } else if (rc.valid) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int d = d0 + cc + i * 4;
-                float4 out = make_float4(t[i].x + o[4 * i], t[i].y + o[4 * i + 1], t[i].z + o[4 * i + 2], t[i].w + o[4 * i + 3]);
-                if (p.out_shift) {
-                    const float4 sh = ldg4(p.out_shift + d);
-                    out.x = fmaf(out.x, p.out_scale, sh.x); out.y = fmaf(out.y, p.out_scale, sh.y);
-                    out.z = fmaf(out.z, p.out_scale, sh.z); out.w = fmaf(out.w, p.out_scale, sh.w);
-                } else if (p.out_scale != 1.0f) {
-                    out.x *= p.out_scale; out.y *= p.out_scale; out.z *= p.out_scale; out.w *= p.out_scale;
-                }
-                *reinterpret_cast<float4*>(p.xhat_out + rc.row * D + d) = out;
-            }
-        }
-        if (p.plan.skip && cc + 32 < cw && !(p.exp_flags & 4)) {   // this slot's registers are free: fetch the same slot of the next 32 columns
-            const int K = p.plan.K;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int d = d0 + cc + 32 + i * 4;
-                cb[4 * h + i] = ldg4(p.cb_blk + ((size_t)(d >> 3) * K + rc.code) * 8 + (d & 7));
-            }
-        }
-    };
-    __syncwarp();
-    tmem_ld16(taddr, va);
-#pragma unroll 1
-    for (int cc = 0; cc < cw; cc += 32) {
-        tmem_wait_ld();
-        if (cc + 16 < cw) { __syncwarp(); tmem_ld16(taddr + cc + 16, vb); }
-        emit(va, cc, 0);
-        if (cc + 16 < cw) {
-            tmem_wait_ld();
-            if (cc + 32 < cw) { __syncwarp(); tmem_ld16(taddr + cc + 32, va); }
-            emit(vb, cc + 16, 1);
-        }
-    }
-}
-
 }  // namespace
 
 template <bool kScore>
-__global__ void __launch_bounds__(kThreads, 2) qb_mlp_kernel(const __grid_constant__ MlpParams p) {
+__global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_constant__ MlpParams p) {
     extern __shared__ __align__(1024) uint8_t dyn_smem[];
-    __shared__ __align__(8) uint64_t bars[QB_BAR_COUNT];
+    __shared__ __align__(8) uint64_t bars[2][QB_BAR_COUNT];     // one barrier set per tile slot
     __shared__ __align__(8) uint64_t w_full[QB_MAX_STAGE];
     __shared__ __align__(8) uint64_t w_empty[QB_MAX_STAGE];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float dist_part[2][3][QB_TILE_M];
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (uniform datapath)
     const QbStepPlan& pl = p.plan;
     const int n_ops = pl.n_ops_block + pl.n_ops_out;
+    const int NT = pl.n_tiles;
     const int64_t n_tiles = (p.n_rows + QB_TILE_M - 1) / QB_TILE_M;
+    const int64_t n_sets = (n_tiles + NT - 1) / NT;           // a CTA works on NT consecutive tiles at a time
 
     // ---- one-time setup ------------------------------------------------------------------------------------------
     if (tid == 0) {
-        mbar_init(smem_u32(&bars[QB_BAR_NONE]), 1);
-        mbar_init(smem_u32(&bars[QB_BAR_AE_READY]), kEpiThreads);
-        mbar_init(smem_u32(&bars[QB_BAR_AH_READY]), kEpiThreads);
-        mbar_init(smem_u32(&bars[QB_BAR_HACC_FREE]), kEpiThreads);
-        mbar_init(smem_u32(&bars[QB_BAR_HACC_FULL]), 1);
-        mbar_init(smem_u32(&bars[QB_BAR_EACC_FULL]), 1);
+        for (int t = 0; t < 2; t++) {
+            mbar_init(smem_u32(&bars[t][QB_BAR_NONE]), 1);
+            mbar_init(smem_u32(&bars[t][QB_BAR_AE_READY]), kEpiThreads);
+            mbar_init(smem_u32(&bars[t][QB_BAR_AH_READY]), kEpiThreads);
+            mbar_init(smem_u32(&bars[t][QB_BAR_HACC_FREE]), kEpiThreads);
+            mbar_init(smem_u32(&bars[t][QB_BAR_HACC_FULL]), 1);
+            mbar_init(smem_u32(&bars[t][QB_BAR_EACC_FULL]), 1);
+        }
         for (int s = 0; s < QB_MAX_STAGE; s++) {
             mbar_init(smem_u32(&w_full[s]), 1);
             mbar_init(smem_u32(&w_empty[s]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                      "r"((uint32_t)pl.tmem_alloc_cols)
                      : "memory");
@@ -412,26 +334,14 @@ __global__ void __launch_bounds__(kThreads, 2) qb_mlp_kernel(const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
     const uint32_t smem_base = smem_u32(dyn_smem);
-    if (p.trace && tid == 0) {   // debug: which SM does this CTA run on (co-residency map)
-        uint32_t smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        if (blockIdx.x < 512) p.trace[3 * QB_TRACE_EVENTS + blockIdx.x] = smid + 1;
-    }
-    if (p.stagger_cycles > 0) {
-        // experiment: delay one of the two co-resident CTAs (stagger_cycles < 2^24: upper half of the grid; else odd CTAs)
-        const bool late = (p.stagger_cycles >> 24) ? (blockIdx.x & 1) : (blockIdx.x >= (gridDim.x + 1) / 2);
-        if (late) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < (p.stagger_cycles & 0xffffff)) { }
-        }
-    }
+    const uint32_t tile_cols = (uint32_t)pl.tmem_tile_cols;
 
-    if (warp == 4) {
+    if (warp == kProducerWarp) {
         // ======================================================================================= weight producer
         uint32_t stage = 0, phase = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int64_t set = blockIdx.x; set < n_sets; set += gridDim.x) {
             for (int l = 0; l <= pl.L; l++) {
                 const int i0 = (l < pl.L) ? 0 : pl.n_ops_block;
                 const int i1 = (l < pl.L) ? pl.n_ops_block : n_ops;
@@ -453,220 +363,294 @@ __global__ void __launch_bounds__(kThreads, 2) qb_mlp_kernel(const __grid_consta
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kMmaWarp) {
         // ======================================================================================= MMA issuer
-        // Kept lean on purpose: a lone warp retires a dependent instruction every ~4-6 cycles, so everything per slab
-        // beyond "wait, 4 MMAs, commit" shows up as tensor-pipe idle time.
+        // Every GEMM of the op list is issued for tile slot 0 (which acquires the weight slabs) and then for tile slot 1
+        // on the same ring slots (which releases them).  Kept lean and warp-uniform on purpose: a lone warp retires a
+        // dependent instruction every ~4-6 cycles and a vector->uniform register move costs far more, so everything
+        // per MMA beyond "descriptor add, UTCHMMA" shows up as tensor-pipe idle time.
         uint32_t stage = 0, phase = 0;
-        uint32_t par = 0;
+        uint32_t par0 = 0, par1 = 0;
         Tracer tr;
         tr.init(p, 1, (tid & 31) == 0);
-        const uint32_t ae_lo = (smem_base + pl.smem_ae) >> 4;
         const uint32_t ring_lo = (smem_base + pl.smem_ring) >> 4;
         const uint32_t slot_lo = (uint32_t)pl.slot_bytes >> 4;
         const uint64_t a_hi = umma_desc(0, kAkcBytes, 128);
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int64_t set = blockIdx.x; set < n_sets; set += gridDim.x) {
             for (int l = 0; l <= pl.L; l++) {
                 const int i0 = (l < pl.L) ? 0 : pl.n_ops_block;
                 const int i1 = (l < pl.L) ? pl.n_ops_block : n_ops;
                 for (int i = i0; i < i1; i++) {
                     const QbOp& op = p.ops[i];
-                    if (op.wait_a) {
-                        mbar_wait(smem_u32(&bars[op.wait_a]), (par >> op.wait_a) & 1, p.err_flag, 0x200 + op.wait_a);
-                        par ^= 1u << op.wait_a;
-                    }
-                    if (op.wait_d) {
-                        mbar_wait(smem_u32(&bars[op.wait_d]), (par >> op.wait_d) & 1, p.err_flag, 0x200 + op.wait_d);
-                        par ^= 1u << op.wait_d;
-                    }
-                    tr.ev(0x200 + i);
                     const uint32_t n = op.n;
                     const uint64_t b_hi = umma_desc(0, n * 16u, 128);
                     const uint32_t b_step = 2u * n;                 // descriptor address units (16 B) per K=16
                     const uint32_t idesc = umma_idesc(n);
-                    const uint32_t d_tmem = tmem_base + op.d_col;
                     const bool from_smem = op.a_src == QB_A_E;
-                    uint32_t a_cur = from_smem ? ae_lo + (uint32_t)op.a_off * (kAkcBytes >> 4) : tmem_base + op.a_off;
-                    uint32_t acc = op.accumulate;
-                    int k_left = op.k_total;
                     const int ks = op.ks;
                     const uint32_t n_slab = op.n_slab;
-                    for (uint32_t s = 0; s < n_slab; s++) {
-                        const int nk = (k_left < ks ? k_left : ks) >> 4;
-                        k_left -= ks;
-                        mbar_wait(smem_u32(&w_full[stage]), phase, p.err_flag, 0x300 + stage);
-                        tc_fence_after();
-                        const uint32_t b_lo = ring_lo + stage * slot_lo;
-                        if (elect_one()) {
-                            if (from_smem) {
+                    const uint32_t stage0 = stage, phase0 = phase;
 #pragma unroll 1
-                                for (int t = 0; t < nk; t++) {
-                                    tc_mma_ss(d_tmem, a_hi | (uint64_t)(a_cur + (uint32_t)t * ((2 * kAkcBytes) >> 4)),
-                                              b_hi | (uint64_t)(b_lo + (uint32_t)t * b_step), idesc, acc);
-                                    acc = 1;
-                                }
-                            } else {
-#pragma unroll 1
-                                for (int t = 0; t < nk; t++) {
-                                    tc_mma_ts(d_tmem, a_cur + (uint32_t)t * 8u, b_hi | (uint64_t)(b_lo + (uint32_t)t * b_step), idesc, acc);
-                                    acc = 1;
-                                }
-                            }
-                            tc_commit(smem_u32(&w_empty[stage]));
-                            if (s + 1 == n_slab && op.commit) tc_commit(smem_u32(&bars[op.commit]));
+                    for (int t = 0; t < NT; t++) {
+                        uint32_t& par = t ? par1 : par0;
+                        if (op.wait_a) {
+                            mbar_wait(smem_u32(&bars[t][op.wait_a]), (par >> op.wait_a) & 1, p.err_flag, 0x200 + op.wait_a);
+                            par ^= 1u << op.wait_a;
                         }
-                        __syncwarp();
-                        acc = 1;
-                        a_cur += (uint32_t)nk * (from_smem ? ((2 * kAkcBytes) >> 4) : 8u);
-                        if (++stage == (uint32_t)pl.n_stage) { stage = 0; phase ^= 1; }
+                        if (op.wait_d) {
+                            mbar_wait(smem_u32(&bars[t][op.wait_d]), (par >> op.wait_d) & 1, p.err_flag, 0x200 + op.wait_d);
+                            par ^= 1u << op.wait_d;
+                        }
+                        tr.ev(0x200 + i + 0x80 * t);
+                        const uint32_t tcol = tmem_base + (uint32_t)t * tile_cols;
+                        const uint32_t d_tmem = tcol + op.d_col;
+                        uint32_t a_cur = from_smem ? ((smem_base + pl.smem_ae[t]) >> 4) + (uint32_t)op.a_off * (kAkcBytes >> 4)
+                                                   : tcol + op.a_off;
+                        uint32_t acc = op.accumulate;
+                        int k_left = op.k_total;
+                        stage = stage0;
+                        phase = phase0;
+                        const bool acquire = t == 0, release = t == NT - 1;
+                        for (uint32_t s = 0; s < n_slab; s++) {
+                            const int nk = (k_left < ks ? k_left : ks) >> 4;
+                            k_left -= ks;
+                            if (acquire) mbar_wait(smem_u32(&w_full[stage]), phase, p.err_flag, 0x300 + stage);
+                            tc_fence_after();
+                            const uint32_t b_lo = ring_lo + stage * slot_lo;
+                            if (elect_one()) {
+                                if (from_smem) {
+#pragma unroll 4
+                                    for (int k = 0; k < nk; k++) {
+                                        tc_mma_ss(d_tmem, a_hi | (uint64_t)(a_cur + (uint32_t)k * ((2 * kAkcBytes) >> 4)),
+                                                  b_hi | (uint64_t)(b_lo + (uint32_t)k * b_step), idesc, acc);
+                                        acc = 1;
+                                    }
+                                } else {
+#pragma unroll 4
+                                    for (int k = 0; k < nk; k++) {
+                                        tc_mma_ts(d_tmem, a_cur + (uint32_t)k * 8u, b_hi | (uint64_t)(b_lo + (uint32_t)k * b_step), idesc, acc);
+                                        acc = 1;
+                                    }
+                                }
+                                if (release) tc_commit(smem_u32(&w_empty[stage]));
+                                if (s + 1 == n_slab && op.commit) tc_commit(smem_u32(&bars[t][op.commit]));
+                            }
+                            __syncwarp();
+                            acc = 1;
+                            a_cur += (uint32_t)nk * (from_smem ? ((2 * kAkcBytes) >> 4) : 8u);
+                            if (++stage == (uint32_t)pl.n_stage) { stage = 0; phase ^= 1; }
+                        }
+                        tr.ev(0x400 + i + 0x80 * t);
                     }
-                    tr.ev(0x400 + i);
                 }
             }
         }
     } else {
         // ======================================================================================= epilogue warps
-        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const uint32_t ae_dst = smem_base + pl.smem_ae + (uint32_t)tid * 16u;
-        uint32_t par = 0;
+        // Thread (lane quarter q = warp % 4, lane) owns row r = 32 q + lane of BOTH tiles in flight and alternates
+        // between them; the four warps of a lane quarter split every column range in quarters (cq = warp / 4), so a
+        // phase is one 32-column block per thread for the 128-wide shapes and latency is hidden by warp count, not by
+        // registers.
+        const int q = warp & 3, cq = warp >> 2;
+        const int r = q * 32 + (tid & 31);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t par0 = 0, par1 = 0;
         Tracer tr;
         tr.init(p, 0, tid == 0);
-        const int De = pl.De, K = pl.K, nkc = De >> 3;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            RowCtx rc;
-            rc.row = tile * QB_TILE_M + tid;
-            rc.valid = rc.row < p.n_rows;
-            rc.beam = 0;
-            rc.code = 0;
-            if (rc.valid) {
-                if (kScore) {
-                    rc.beam = rc.row / p.C;
-                    const int a = (int)(rc.row - rc.beam * p.C);
-                    rc.code = p.A > 0 ? (int)__ldg(p.idx + rc.beam * p.A + a) : a;
-                } else {
-                    const int64_t v = rc.row / p.F_out;
-                    const int parent = p.sel_parent ? (int)__ldg(p.sel_parent + rc.row) : 0;
-                    rc.beam = v * p.F_in + parent;
-                    rc.code = (int)__ldg(p.sel_code + rc.row * p.code_stride + p.code_off);
-                }
-                if (rc.code >= K) rc.code = K - 1;   // never read outside the tables (bad codes are rejected on the host)
-            }
-            tr.ev(1);
-            // ---- init: e0 = T_m[code] + u_b; 64 columns per batch, all table loads of a batch issued up front ----------
-            {
-                const float* tp = p.t_blk + (size_t)rc.code * 8;
-                const size_t tstride = (p.exp_flags & 2) ? 0 : (size_t)K * 8;
-                const float* up = p.u + rc.beam * De;
-                // the per-beam rows are shared by many rows of the tile: pull them into L1 (one 128 B line per thread)
-                if (tid * 32 < De) prefetch_l1(up + tid * 32);
-                auto emit_chunk = [&](int kc, const float4 t0, const float4 t1) {
-                    float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
-                    if (!(p.exp_flags & 1)) { u0 = ldg4_jit(up + kc * 8); u1 = ldg4_jit(up + kc * 8 + 4); }
-                    uint32_t e[8];
-                    const float f0 = t0.x + u0.x, f1 = t0.y + u0.y, f2 = t0.z + u0.z, f3 = t0.w + u0.w;
-                    const float f4 = t1.x + u1.x, f5 = t1.y + u1.y, f6 = t1.z + u1.z, f7 = t1.w + u1.w;
-                    e[0] = __float_as_uint(f0); e[1] = __float_as_uint(f1); e[2] = __float_as_uint(f2);
-                    e[3] = __float_as_uint(f3); e[4] = __float_as_uint(f4); e[5] = __float_as_uint(f5);
-                    e[6] = __float_as_uint(f6); e[7] = __float_as_uint(f7);
-                    __syncwarp();
-                    if (!(p.exp_flags & 32)) tmem_st8(lane_base + pl.tmem_e_col + kc * 8, e);
-                    st_shared_v4(ae_dst + (uint32_t)kc * kAkcBytes, pack_h2(f0, f1), pack_h2(f2, f3), pack_h2(f4, f5),
-                                 pack_h2(f6, f7));
-                };
-                int kc0 = 0;
-                if (nkc >= 4) {                          // 32 columns per batch; the next batch's table rows in flight
-                    float4 ta[8], tb[8];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) { ta[2 * q] = ldg4(tp + (size_t)q * tstride); ta[2 * q + 1] = ldg4(tp + (size_t)q * tstride + 4); }
-#pragma unroll 1
-                    for (; kc0 + 4 <= nkc; kc0 += 8) {
-                        const bool more1 = kc0 + 8 <= nkc;
-                        if (more1) {
-#pragma unroll
-                            for (int q = 0; q < 4; q++) { tb[2 * q] = ldg4(tp + (size_t)(kc0 + 4 + q) * tstride); tb[2 * q + 1] = ldg4(tp + (size_t)(kc0 + 4 + q) * tstride + 4); }
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; q++) emit_chunk(kc0 + q, ta[2 * q], ta[2 * q + 1]);
-                        if (more1) {
-                            if (kc0 + 12 <= nkc) {
-#pragma unroll
-                                for (int q = 0; q < 4; q++) { ta[2 * q] = ldg4(tp + (size_t)(kc0 + 8 + q) * tstride); ta[2 * q + 1] = ldg4(tp + (size_t)(kc0 + 8 + q) * tstride + 4); }
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; q++) emit_chunk(kc0 + 4 + q, tb[2 * q], tb[2 * q + 1]);
-                        }
+        const int De = pl.De, K = pl.K, D = pl.D;
+        int e0c, e1c, o0c, o1c;             // this thread's columns of e / of the output (no out_proj)
+        quarter_range(De, cq, e0c, e1c);
+        quarter_range(D, cq, o0c, o1c);
+        for (int64_t set = blockIdx.x; set < n_sets; set += gridDim.x) {
+            // per-tile row context, kept in scalars (no runtime-indexed arrays)
+            int code0 = 0, code1 = 0;
+            int64_t beam0 = 0, beam1 = 0, row0 = 0, row1 = 0;
+            bool valid0 = false, valid1 = false;
+            auto row_ctx = [&](int t, int64_t& row, int64_t& beam, int& code, bool& valid) {
+                row = (set * NT + t) * QB_TILE_M + r;
+                valid = t < NT && row < p.n_rows;
+                if (valid) {
+                    if (kScore) {
+                        beam = (int64_t)((uint32_t)row / (uint32_t)p.C);      // rows per launch < 2^31 (launch_mlp checks)
+                        const int a = (int)((uint32_t)row - (uint32_t)beam * (uint32_t)p.C);
+                        code = p.A > 0 ? (int)__ldg(p.idx + beam * p.A + a) : a;
+                    } else {
+                        const int64_t v = (int64_t)((uint32_t)row / (uint32_t)p.F_out);
+                        const int parent = p.sel_parent ? (int)__ldg(p.sel_parent + row) : 0;
+                        beam = v * p.F_in + parent;
+                        code = (int)__ldg(p.sel_code + row * p.code_stride + p.code_off);
                     }
-                    kc0 = nkc & ~3;
+                    if (code >= K) code = K - 1;   // never read outside the tables (bad codes are rejected on the host)
                 }
+            };
+            row_ctx(0, row0, beam0, code0, valid0);
+            row_ctx(1, row1, beam1, code1, valid1);
+            tr.ev(1);
+            // ---- init: e0 = T_m[code] + u_b over this thread's columns ------------------------------------------------
+            auto init_tile = [&](int t, int code, int64_t beam) {
+                const uint32_t tl = lane_base + (uint32_t)t * tile_cols;
+                const uint32_t ae_dst = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
+                const float* tp = p.t_blk + (size_t)code * 8;
+                const float* up = p.u + beam * De;
+                if (cq == 0 && r * 32 < De) prefetch_l1(up + r * 32);    // the per-beam row is shared by many rows: pull it into L1
 #pragma unroll 1
-                for (; kc0 + 2 <= nkc; kc0 += 2) {      // tail (de is a multiple of 16): 16 columns at a time
-                    const float4 a0 = ldg4(tp + (size_t)kc0 * K * 8), a1 = ldg4(tp + (size_t)kc0 * K * 8 + 4);
-                    const float4 b0 = ldg4(tp + (size_t)(kc0 + 1) * K * 8), b1 = ldg4(tp + (size_t)(kc0 + 1) * K * 8 + 4);
-                    emit_chunk(kc0, a0, a1);
-                    emit_chunk(kc0 + 1, b0, b1);
+                for (int kc = e0c >> 3; kc < (e1c >> 3); kc += 2) {   // 16 columns per step, a step's loads issued together
+                    const float4 a0 = ldg4(tp + (size_t)kc * K * 8), a1 = ldg4(tp + (size_t)kc * K * 8 + 4);
+                    const float4 b0 = ldg4(tp + (size_t)(kc + 1) * K * 8), b1 = ldg4(tp + (size_t)(kc + 1) * K * 8 + 4);
+                    const float4 u0 = ldg4(up + kc * 8), u1 = ldg4(up + kc * 8 + 4), u2 = ldg4(up + kc * 8 + 8), u3 = ldg4(up + kc * 8 + 12);
+                    uint32_t e[8];
+                    float f0 = a0.x + u0.x, f1 = a0.y + u0.y, f2 = a0.z + u0.z, f3 = a0.w + u0.w;
+                    float f4 = a1.x + u1.x, f5 = a1.y + u1.y, f6 = a1.z + u1.z, f7 = a1.w + u1.w;
+                    e[0] = __float_as_uint(f0); e[1] = __float_as_uint(f1); e[2] = __float_as_uint(f2); e[3] = __float_as_uint(f3);
+                    e[4] = __float_as_uint(f4); e[5] = __float_as_uint(f5); e[6] = __float_as_uint(f6); e[7] = __float_as_uint(f7);
+                    __syncwarp();
+                    tmem_st8(tl + pl.tmem_e_col + kc * 8, e);
+                    st_shared_v4(ae_dst + (uint32_t)kc * kAkcBytes, pack_h2(f0, f1), pack_h2(f2, f3), pack_h2(f4, f5), pack_h2(f6, f7));
+                    f0 = b0.x + u2.x; f1 = b0.y + u2.y; f2 = b0.z + u2.z; f3 = b0.w + u2.w;
+                    f4 = b1.x + u3.x; f5 = b1.y + u3.y; f6 = b1.z + u3.z; f7 = b1.w + u3.w;
+                    e[0] = __float_as_uint(f0); e[1] = __float_as_uint(f1); e[2] = __float_as_uint(f2); e[3] = __float_as_uint(f3);
+                    e[4] = __float_as_uint(f4); e[5] = __float_as_uint(f5); e[6] = __float_as_uint(f6); e[7] = __float_as_uint(f7);
+                    __syncwarp();
+                    tmem_st8(tl + pl.tmem_e_col + (kc + 1) * 8, e);
+                    st_shared_v4(ae_dst + (uint32_t)(kc + 1) * kAkcBytes, pack_h2(f0, f1), pack_h2(f2, f3), pack_h2(f4, f5), pack_h2(f6, f7));
                 }
                 tmem_wait_st();
                 tc_fence_before();
-                if (!(p.exp_flags & 16)) proxy_fence_async();
-                mbar_arrive(smem_u32(&bars[QB_BAR_AE_READY]));
-                tr.ev(2);
-            }
+                proxy_fence_async();
+                mbar_arrive(smem_u32(&bars[t][QB_BAR_AE_READY]));
+                tr.ev(2 + 0x80 * t);
+            };
+#pragma unroll 1
+            for (int t = 0; t < NT; t++) init_tile(t, t ? code1 : code0, t ? beam1 : beam0);
             // ---- residual blocks -----------------------------------------------------------------------------------
-            float4 cb[8];
+            float acc0 = 0.f, acc1 = 0.f;
+            auto wait_bar = [&](int t, int bar, uint32_t code) {
+                uint32_t& par = t ? par1 : par0;
+                mbar_wait(smem_u32(&bars[t][bar]), (par >> bar) & 1, p.err_flag, code);
+                par ^= 1u << bar;
+                tc_fence_after();
+            };
+            // final epilogue of columns [c0, c1) at accumulator address taddr (o[d0 + c0 ..]); cb = prefetched skip codeword
+            auto final_cols = [&](uint32_t taddr, int c0, int c1, int d0, int code, int64_t beam, int64_t row, bool valid,
+                                  float& acc) {
+                const float* src = (kScore ? p.r : p.xhat_in) + beam * D + d0;
+#pragma unroll 1
+                for (int cc = c0; cc < c1; cc += 16) {
+                    float4 cv[4];
+                    if (pl.skip) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) cb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int i = 0; i < 4; i++) {
+                            const int d = d0 + cc + i * 4;
+                            cv[i] = ldg4(p.cb_blk + ((size_t)(d >> 3) * K + code) * 8 + (d & 7));
+                        }
+                    }
+                    float4 t4[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) t4[i] = ldg4(src + cc + i * 4);
+                    uint32_t v[32];
+                    __syncwarp();
+                    tmem_ld16(taddr + cc, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        float o0 = __uint_as_float(v[4 * i]), o1 = __uint_as_float(v[4 * i + 1]), o2 = __uint_as_float(v[4 * i + 2]),
+                              o3 = __uint_as_float(v[4 * i + 3]);
+                        if (pl.skip) { o0 += cv[i].x; o1 += cv[i].y; o2 += cv[i].z; o3 += cv[i].w; }
+                        if (kScore) {
+                            const float e0 = t4[i].x - o0, e1 = t4[i].y - o1, e2 = t4[i].z - o2, e3 = t4[i].w - o3;
+                            acc = fmaf(e0, e0, acc); acc = fmaf(e1, e1, acc); acc = fmaf(e2, e2, acc); acc = fmaf(e3, e3, acc);
+                        } else if (valid) {
+                            const int d = d0 + cc + i * 4;
+                            float4 out = make_float4(t4[i].x + o0, t4[i].y + o1, t4[i].z + o2, t4[i].w + o3);
+                            if (p.out_shift) {
+                                const float4 sh = ldg4(p.out_shift + d);
+                                out.x = fmaf(out.x, p.out_scale, sh.x); out.y = fmaf(out.y, p.out_scale, sh.y);
+                                out.z = fmaf(out.z, p.out_scale, sh.z); out.w = fmaf(out.w, p.out_scale, sh.w);
+                            } else if (p.out_scale != 1.0f) {
+                                out.x *= p.out_scale; out.y *= p.out_scale; out.z *= p.out_scale; out.w *= p.out_scale;
+                            }
+                            *reinterpret_cast<float4*>(p.xhat_out + row * D + d) = out;
+                        }
+                    }
+                }
+            };
 #pragma unroll 1
             for (int l = 0; l < pl.L; l++) {
 #pragma unroll 1
                 for (int j = 0; j < pl.n_hchunk; j++) {
                     const int cw = min(pl.hc, pl.Dh - j * pl.hc);
-                    mbar_wait(smem_u32(&bars[QB_BAR_HACC_FULL]), (par >> QB_BAR_HACC_FULL) & 1, p.err_flag, 0x404);
-                    par ^= 1u << QB_BAR_HACC_FULL;
-                    tc_fence_after();
-                    tr.ev(3);
-                    acc_to_tmem_operand(lane_base + pl.tmem_h_col, cw);
-                    tc_fence_before();
-                    mbar_arrive(smem_u32(&bars[QB_BAR_AH_READY]));
-                    tr.ev(4);
+                    int c0, c1;
+                    quarter_range(cw, cq, c0, c1);
+#pragma unroll 1
+                    for (int t = 0; t < NT; t++) {
+                        wait_bar(t, QB_BAR_HACC_FULL, 0x404);
+                        tr.ev(3 + 0x80 * t);
+                        acc_to_tmem_operand(lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col, c0, c1, 1 + q);
+                        tc_fence_before();
+                        mbar_arrive(smem_u32(&bars[t][QB_BAR_AH_READY]));
+                        tr.ev(4 + 0x80 * t);
+                    }
                 }
                 const bool last = (l + 1 == pl.L);
-                if (last) {
-                    // inputs of the final epilogue travel while the last down-projection runs
-                    const float* src = (kScore ? p.r : p.xhat_in) + rc.beam * pl.D;
-                    if (tid * 32 < pl.D) prefetch_l1(src + tid * 32);
-                    if (!pl.has_proj && pl.skip && !(p.exp_flags & 4)) load_cb64(p, rc, 0, pl.D, cb);
-                }
-                mbar_wait(smem_u32(&bars[QB_BAR_EACC_FULL]), (par >> QB_BAR_EACC_FULL) & 1, p.err_flag, 0x405);
-                par ^= 1u << QB_BAR_EACC_FULL;
-                tc_fence_after();
-                tr.ev(5);
-                if (!last || pl.has_proj) {
-                    acc_to_smem_operand(lane_base + pl.tmem_e_col, De, ae_dst);
-                    tc_fence_before();
-                    if (!(p.exp_flags & 16)) proxy_fence_async();
-                    mbar_arrive(smem_u32(&bars[QB_BAR_AE_READY]));
-                    tr.ev(6);
+#pragma unroll 1
+                for (int t = 0; t < NT; t++) {
+                    const uint32_t tl = lane_base + (uint32_t)t * tile_cols;
+                    if (last && cq == 0 && r * 32 < D)   // the per-beam operand of the final epilogue travels to L1 meanwhile
+                        prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
+                    wait_bar(t, QB_BAR_EACC_FULL, 0x405);
+                    tr.ev(5 + 0x80 * t);
+                    if (!last || pl.has_proj) {
+                        acc_to_smem_operand(tl + pl.tmem_e_col, e0c, e1c, smem_base + pl.smem_ae[t] + (uint32_t)r * 16u);
+                        tc_fence_before();
+                        proxy_fence_async();
+                        mbar_arrive(smem_u32(&bars[t][QB_BAR_AE_READY]));
+                        tr.ev(6 + 0x80 * t);
+                    } else {
+                        float a = 0.f;
+                        final_cols(tl + pl.tmem_e_col, o0c, o1c, 0, t ? code1 : code0, t ? beam1 : beam0, t ? row1 : row0,
+                                   t ? valid1 : valid0, a);
+                        if (t) acc1 = a; else acc0 = a;
+                        tc_fence_before();
+                        tr.ev(7 + 0x80 * t);
+                    }
                 }
             }
-            // ---- final epilogue --------------------------------------------------------------------------------------
-            float acc = 0.f;
+            // ---- out_proj chunks / models without residual blocks ------------------------------------------------------
             if (pl.has_proj) {
-                for (int q = 0; q < pl.n_ochunk; q++) {
-                    const int cw = min(pl.oc, pl.D - q * pl.oc);
-                    if (pl.skip) load_cb64(p, rc, q * pl.oc, cw, cb);
-                    mbar_wait(smem_u32(&bars[QB_BAR_HACC_FULL]), (par >> QB_BAR_HACC_FULL) & 1, p.err_flag, 0x414);
-                    par ^= 1u << QB_BAR_HACC_FULL;
-                    tc_fence_after();
-                    consume_out<kScore>(p, rc, lane_base + pl.tmem_h_col, cw, q * pl.oc, cb, acc);
-                    tc_fence_before();
-                    if (q + 1 < pl.n_ochunk) mbar_arrive(smem_u32(&bars[QB_BAR_HACC_FREE]));
+                for (int qq = 0; qq < pl.n_ochunk; qq++) {
+                    const int cw = min(pl.oc, D - qq * pl.oc);
+                    int c0, c1;
+                    quarter_range(cw, cq, c0, c1);
+#pragma unroll 1
+                    for (int t = 0; t < NT; t++) {
+                        wait_bar(t, QB_BAR_HACC_FULL, 0x414);
+                        const uint32_t ta = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
+                        float a = t ? acc1 : acc0;
+                        final_cols(ta, c0, c1, qq * pl.oc, t ? code1 : code0, t ? beam1 : beam0, t ? row1 : row0, t ? valid1 : valid0, a);
+                        if (t) acc1 = a; else acc0 = a;
+                        tc_fence_before();
+                        if (qq + 1 < pl.n_ochunk) mbar_arrive(smem_u32(&bars[t][QB_BAR_HACC_FREE]));
+                    }
                 }
-            } else {
-                if (pl.L == 0 && pl.skip) load_cb64(p, rc, 0, pl.D, cb);
-                consume_out<kScore>(p, rc, lane_base + pl.tmem_e_col, pl.D, 0, cb, acc);
+            } else if (pl.L == 0) {
+#pragma unroll 1
+                for (int t = 0; t < NT; t++) {
+                    float a = 0.f;
+                    final_cols(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, o0c, o1c, 0, t ? code1 : code0, t ? beam1 : beam0,
+                               t ? row1 : row0, t ? valid1 : valid0, a);
+                    if (t) acc1 = a; else acc0 = a;
+                }
                 tc_fence_before();
             }
-            if (kScore && rc.valid) p.dist[rc.row] = acc;
+            if (kScore) {   // the four column quarters of a row meet in shared memory
+                if (cq > 0) { dist_part[0][cq - 1][r] = acc0; dist_part[1][cq - 1][r] = acc1; }
+                named_bar_sync(5, kEpiThreads);
+                if (cq == 0) {
+                    if (valid0) p.dist[row0] = ((acc0 + dist_part[0][0][r]) + dist_part[0][1][r]) + dist_part[0][2][r];
+                    if (valid1) p.dist[row1] = ((acc1 + dist_part[1][0][r]) + dist_part[1][1][r]) + dist_part[1][2][r];
+                }
+                named_bar_sync(5, kEpiThreads);
+            }
             tr.ev(8);
         }
     }
@@ -675,7 +659,7 @@ __global__ void __launch_bounds__(kThreads, 2) qb_mlp_kernel(const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)pl.tmem_alloc_cols)
                      : "memory");
@@ -698,13 +682,12 @@ cudaError_t mlp_set_smem_attr(int smem_bytes) {
 
 cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
     if (p.n_rows <= 0) return cudaSuccess;
+    if (p.n_rows >= (1ll << 31) - 256) return cudaErrorInvalidValue;   // 32-bit row arithmetic in the kernel
     const int64_t n_tiles = (p.n_rows + QB_TILE_M - 1) / QB_TILE_M;
-    const int64_t slots = (int64_t)n_sm * p.plan.ctas_per_sm;
-    const int grid = (int)(n_tiles < slots ? n_tiles : slots);
+    const int64_t n_sets = (n_tiles + p.plan.n_tiles - 1) / p.plan.n_tiles;
+    const int grid = (int)(n_sets < n_sm ? n_sets : n_sm);
     // Debug: QB_MLP_TRACE=<file>[:<launch index>] dumps the event log of CTA 0 for one launch (synchronises).
     static const char* trace_env = getenv("QB_MLP_TRACE");
-    static const int exp_flags = getenv("QB_EXP") ? atoi(getenv("QB_EXP")) : 0;
-    if (exp_flags) const_cast<MlpParams&>(p).exp_flags = exp_flags;
     static int trace_at = -1, launch_no = 0;
     if (trace_env && trace_at < 0) {
         const char* c = strrchr(trace_env, ':');

@@ -80,21 +80,20 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     if (e_cols + h_cols > 512) { *err = "de too large for TMEM: round32(de) + round32(hc) must be <= 512 columns"; return -1; }
     const int a_kc_bytes = QB_TILE_M * 16;  // one 8-element k-chunk of a 128-row A operand
     const int ae_bytes = (De / 8) * a_kc_bytes;
-    p->slot_bytes = opt.slot_bytes > 0 ? opt.slot_bytes : 16384;
+    p->slot_bytes = opt.slot_bytes > 0 ? opt.slot_bytes : 32768;
     if (p->slot_bytes % 1024) { *err = "slot_bytes must be a multiple of 1024"; return -1; }
-    if (opt.n_tiles > 1) { *err = "n_tiles > 1 is not supported by this kernel generation"; return -1; }
-    // two CTAs per SM: each gets half of TMEM and of the shared memory (228 KB per SM, 1 KB reserved per CTA)
-    int ctas = opt.ctas_per_sm > 0 ? opt.ctas_per_sm : 2;
-    if (ctas == 2 && (e_cols + h_cols > 256 || 110 * 1024 - ae_bytes < 3 * p->slot_bytes)) {
-        if (opt.ctas_per_sm == 2) { *err = "two CTAs per SM do not fit (TMEM columns or shared memory)"; return -1; }
-        ctas = 1;
+    // two tiles in flight share every weight slab: they need 2x the TMEM columns and 2x the A_E tile
+    int n_tiles = opt.n_tiles > 0 ? opt.n_tiles : 2;
+    if (n_tiles > 2) { *err = "n_tiles must be 1 or 2"; return -1; }
+    const int budget = opt.smem_budget > 0 ? opt.smem_budget : 216 * 1024;
+    if (n_tiles == 2 && (2 * (e_cols + h_cols) > 512 || budget - 2 * ae_bytes < 4 * p->slot_bytes)) {
+        if (opt.n_tiles == 2) { *err = "two tiles in flight do not fit (TMEM columns or shared memory)"; return -1; }
+        n_tiles = 1;
     }
-    if (ctas > 2) { *err = "ctas_per_sm must be 1 or 2"; return -1; }
-    const int budget = opt.smem_budget > 0 ? opt.smem_budget : (ctas == 2 ? 110 * 1024 : 220 * 1024);
-    p->ctas_per_sm = ctas;
+    p->n_tiles = n_tiles;
     {
         int c = 32;
-        while (c < e_cols + h_cols) c *= 2;
+        while (c < n_tiles * (e_cols + h_cols)) c *= 2;
         p->tmem_alloc_cols = c;
     }
     p->hc = hc;
@@ -107,7 +106,7 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
 
     // ---- shared memory ------------------------------------------------------------------------------------------
     int off = 0;
-    p->smem_ae = off; off += ae_bytes;
+    for (int t = 0; t < 2; t++) { p->smem_ae[t] = off; if (t < n_tiles) off += ae_bytes; }
     p->smem_ring = off;
     int n_stage = (budget - off) / p->slot_bytes;
     n_stage = std::min(n_stage, opt.max_stage > 0 ? std::min(opt.max_stage, QB_MAX_STAGE) : QB_MAX_STAGE);
@@ -164,6 +163,8 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     }
     p->n_ops_out = (int)ops->size() - p->n_ops_block;
     if (ops->size() > QB_MAX_OPS) { *err = "op list too long"; return -1; }
+    for (const QbOp& op : *ops)
+        if (n_tiles == 2 && op.n_slab + 1 > n_stage) { *err = "weight ring too shallow for two tiles (raise slot_bytes)"; return -1; }
     for (const QbOp& op : *ops)
         if ((int)op.slab_bytes > p->slot_bytes || op.n_slab < 1) { *err = "internal: slab larger than ring slot"; return -1; }
     p->w_blob_bytes = std::max<int64_t>(w_off, 16);
@@ -257,9 +258,9 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
     std::vector<QbOp> ops;
     std::string err;
     if (qb::make_step_plan(D, De, Dh, L, K, qinco1_mode, opt, &p, &ops, &err)) return -1;
-    const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.ctas_per_sm, p.tmem_alloc_cols,
+    const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_tiles, p.tmem_alloc_cols,
                          p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk, p.oc, p.n_ochunk, p.tmem_e_col, p.tmem_h_col,
-                         p.tmem_tile_cols, p.smem_ae, p.smem_ring, p.slot_bytes, p.n_stage, p.smem_total,
+                         p.tmem_tile_cols, p.smem_ae[0], p.smem_ring, p.slot_bytes, p.n_stage, p.smem_total,
                          (int32_t)p.block_w_bytes, (int32_t)p.w_blob_bytes};
     const int nv = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < nv && i < n_plan_out; i++) plan_out[i] = v[i];

@@ -7,11 +7,13 @@
 //     e  += Wdn_l . relu(Wup_l . e)   l < L      fp16 operands, fp32 accumulate, fp32 residual stream in TMEM
 //     o   = Pout . e (+ C_m[code])               Pout absent when De == D; skip absent in qinco1_mode
 //
-// A CTA works on one 128-row tile at a time; when a tile needs <= 256 TMEM columns and <= ~110 KB of shared memory
-// TWO CTAs are co-resident per SM (plan.ctas_per_sm), so one CTA's table gathers / epilogues overlap the other's MMAs.
-// Per tile, TMEM holds the fp32 residual accumulator Eacc (De columns) and one hidden-chunk accumulator Hacc
-// (hc columns); relu(h) is written back IN PLACE as packed fp16 and read by the down-projection MMA as a TMEM A
-// operand, so only e (fp16, [De/8][128][16 B] K-major core-matrix layout) lives in shared memory next to the weight ring.
+// One CTA per SM works on n_tiles (2 when TMEM allows, else 1) 128-row tiles at a time, in lockstep: every GEMM of
+// the op list is issued for tile X and then for tile Y on the SAME weight slabs (fetched once per two tiles), while the
+// single group of epilogue warps alternates X, Y, X, Y ... — so the TMEM->relu->fp16 epilogue of one tile always
+// overlaps the MMAs of the other.  Per tile, TMEM holds the fp32 residual accumulator Eacc (De columns) and one
+// hidden-chunk accumulator Hacc (hc columns); relu(h) is written back IN PLACE as packed fp16 and read by the
+// down-projection MMA as a TMEM A operand, so only e (fp16, [De/8][128][16 B] K-major core-matrix layout, one tile per
+// slot) lives in shared memory next to the weight ring.
 //
 // The MMA warp walks a static list of "ops" (kept in the kernel-parameter constant bank).  An op is one GEMM
 //     D[128, n] (+)= A[128, k_total] . W[n, k_total]^T
@@ -62,8 +64,8 @@ struct QbStepPlan {
     int32_t D, De, Dh, L, K;
     int32_t has_proj;        // De != D: out_proj runs on the tensor core
     int32_t skip;            // QINCo2: o += C_m[code]
-    int32_t ctas_per_sm;     // co-resident CTAs per SM (2 when a tile needs <= 256 TMEM columns and <= ~110 KB smem)
-    int32_t tmem_alloc_cols; // power of two >= tmem_tile_cols
+    int32_t n_tiles;         // tiles in flight per CTA (1 or 2); tile slot t uses TMEM columns [t*tmem_tile_cols, ...)
+    int32_t tmem_alloc_cols; // power of two >= n_tiles * tmem_tile_cols
     int32_t n_ops_block;     // ops[0 .. n_ops_block) run once per residual block l (weights at l*block_w_bytes + w_off)
     int32_t n_ops_out;       // ops[n_ops_block .. n_ops_block+n_ops_out) run once per tile set for out_proj
     int32_t hc;              // H chunk width (columns of Hacc per chunk; the last chunk may be narrower)
@@ -72,9 +74,9 @@ struct QbStepPlan {
     int32_t n_ochunk;
     int32_t tmem_e_col;      // per-tile column offsets
     int32_t tmem_h_col;
-    int32_t tmem_tile_cols;  // columns used
+    int32_t tmem_tile_cols;  // columns per tile slot
     // shared memory carve-up (byte offsets from the 1024-aligned dynamic smem base)
-    int32_t smem_ae;         // A_E: [De/8][128][16B]
+    int32_t smem_ae[2];      // A_E per tile slot: [De/8][128][16B]
     int32_t smem_ring;       // ring of n_stage slots of slot_bytes
     int32_t slot_bytes;
     int32_t n_stage;

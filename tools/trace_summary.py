@@ -10,10 +10,11 @@ for line in open(sys.argv[1]):
 t0 = min(e[0][0] for e in ev.values() if e)
 names = {1: "init start", 2: "init done (AE_READY)", 3: "HACC_FULL seen", 4: "H-epi done (AH_READY)", 5: "EACC_FULL seen", 6: "E-epi done (AE_READY)", 8: "tile done"}
 allev = []
-for t, i in ev[0]: allev.append((t - t0, "EPI ", names.get(i, ("init batch %d" % (i - 0x10)) if 0x10 <= i < 0x20 else ("final batch %d" % (i - 0x20)) if 0x20 <= i < 0x40 else hex(i))))
+names[7] = "final done"
+for t, i in ev[0]: allev.append((t - t0, "EPI ", ("Y " if i & 0x80 else "X ") + names.get(i & 0x7f, hex(i))))
 for t, i in ev[1]:
     kind = {0x200: "ops ready, wait slab", 0x300: "slab ready, issue", 0x400: "issued"}[i & 0xf00]
-    allev.append((t - t0, "MMA ", f"op {i & 0xff:2d} {kind}"))
+    allev.append((t - t0, "MMA ", f"{'Y' if i & 0x80 else 'X'} op {i & 0x7f:2d} {kind}"))
 for t, i in ev[2]: allev.append((t - t0, "PROD", f"slab for op {i & 0xff:2d} slot free -> copy issued"))
 allev.sort()
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 150
