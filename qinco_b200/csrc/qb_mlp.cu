@@ -40,8 +40,8 @@ namespace {
 
 constexpr int kEpiWarps = 16;             // four warps per TMEM lane quarter: warp w owns lanes 32*(w%4).., column quarter w/4
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = kEpiThreads + 64;   // + producer warp + MMA warp
-constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+constexpr int kThreads = kEpiThreads + 96;   // + producer warp + one MMA warp per tile slot
+constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;   // MMA warps: kMmaWarp + tile slot
 constexpr int kAkcBytes = QB_TILE_M * 16;   // bytes of one 8-element k-chunk of an A operand tile
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         }
         for (int s = 0; s < QB_MAX_STAGE; s++) {
             mbar_init(smem_u32(&w_full[s]), 1);
-            mbar_init(smem_u32(&w_empty[s]), 1);
+            mbar_init(smem_u32(&w_empty[s]), (uint32_t)pl.n_tiles);   // released by every tile slot's MMA warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -363,36 +363,36 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 }
             }
         }
-    } else if (warp == kMmaWarp) {
-        // ======================================================================================= MMA issuer
-        // Every GEMM of the op list is issued for tile slot 0 (which acquires the weight slabs) and then for tile slot 1
-        // on the same ring slots (which releases them).  Kept lean and warp-uniform on purpose: a lone warp retires a
-        // dependent instruction every ~4-6 cycles and a vector->uniform register move costs far more, so everything
-        // per MMA beyond "descriptor add, UTCHMMA" shows up as tensor-pipe idle time.
-        uint32_t stage = 0, phase = 0;
-        uint32_t par0 = 0, par1 = 0;
-        Tracer tr;
-        tr.init(p, 1, (tid & 31) == 0);
-        const uint32_t ring_lo = (smem_base + pl.smem_ring) >> 4;
-        const uint32_t slot_lo = (uint32_t)pl.slot_bytes >> 4;
-        const uint64_t a_hi = umma_desc(0, kAkcBytes, 128);
-        for (int64_t set = blockIdx.x; set < n_sets; set += gridDim.x) {
-            for (int l = 0; l <= pl.L; l++) {
-                const int i0 = (l < pl.L) ? 0 : pl.n_ops_block;
-                const int i1 = (l < pl.L) ? pl.n_ops_block : n_ops;
-                for (int i = i0; i < i1; i++) {
-                    const QbOp& op = p.ops[i];
-                    const uint32_t n = op.n;
-                    const uint64_t b_hi = umma_desc(0, n * 16u, 128);
-                    const uint32_t b_step = 2u * n;                 // descriptor address units (16 B) per K=16
-                    const uint32_t idesc = umma_idesc(n);
-                    const bool from_smem = op.a_src == QB_A_E;
-                    const int ks = op.ks;
-                    const uint32_t n_slab = op.n_slab;
-                    const uint32_t stage0 = stage, phase0 = phase;
-#pragma unroll 1
-                    for (int t = 0; t < NT; t++) {
-                        uint32_t& par = t ? par1 : par0;
+    } else if (warp >= kMmaWarp) {
+        // ======================================================================================= MMA issuers
+        // One warp per tile slot walks the op list for its own tile; both wait on the same "slab landed" barriers and a
+        // ring slot is recycled once every slot's warp has committed it (w_empty counts n_tiles arrivals), so the
+        // weights are fetched once per two tiles while the two issue streams overlap each other's bookkeeping.
+        // Kept lean and warp-uniform on purpose: a lone warp retires a dependent instruction every ~4-6 cycles.
+        const int t = warp - kMmaWarp;
+        if (t < NT) {
+            uint32_t stage = 0, phase = 0;
+            uint32_t par = 0;
+            Tracer tr;
+            tr.init(p, 1 + t, (tid & 31) == 0);      // trace roles 1 / 2: MMA warps of tile slots 0 / 1
+            const uint32_t ring_lo = (smem_base + pl.smem_ring) >> 4;
+            const uint32_t slot_lo = (uint32_t)pl.slot_bytes >> 4;
+            const uint64_t a_hi = umma_desc(0, kAkcBytes, 128);
+            const uint32_t tcol = tmem_base + (uint32_t)t * tile_cols;
+            const uint32_t ae_lo = (smem_base + pl.smem_ae[t]) >> 4;
+            for (int64_t set = blockIdx.x; set < n_sets; set += gridDim.x) {
+                for (int l = 0; l <= pl.L; l++) {
+                    const int i0 = (l < pl.L) ? 0 : pl.n_ops_block;
+                    const int i1 = (l < pl.L) ? pl.n_ops_block : n_ops;
+                    for (int i = i0; i < i1; i++) {
+                        const QbOp& op = p.ops[i];
+                        const uint32_t n = op.n;
+                        const uint64_t b_hi = umma_desc(0, n * 16u, 128);
+                        const uint32_t b_step = 2u * n;                 // descriptor address units (16 B) per K=16
+                        const uint32_t idesc = umma_idesc(n);
+                        const bool from_smem = op.a_src == QB_A_E;
+                        const int ks = op.ks;
+                        const uint32_t n_slab = op.n_slab;
                         if (op.wait_a) {
                             mbar_wait(smem_u32(&bars[t][op.wait_a]), (par >> op.wait_a) & 1, p.err_flag, 0x200 + op.wait_a);
                             par ^= 1u << op.wait_a;
@@ -401,20 +401,15 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                             mbar_wait(smem_u32(&bars[t][op.wait_d]), (par >> op.wait_d) & 1, p.err_flag, 0x200 + op.wait_d);
                             par ^= 1u << op.wait_d;
                         }
-                        tr.ev(0x200 + i + 0x80 * t);
-                        const uint32_t tcol = tmem_base + (uint32_t)t * tile_cols;
+                        tr.ev(0x200 + i);
                         const uint32_t d_tmem = tcol + op.d_col;
-                        uint32_t a_cur = from_smem ? ((smem_base + pl.smem_ae[t]) >> 4) + (uint32_t)op.a_off * (kAkcBytes >> 4)
-                                                   : tcol + op.a_off;
+                        uint32_t a_cur = from_smem ? ae_lo + (uint32_t)op.a_off * (kAkcBytes >> 4) : tcol + op.a_off;
                         uint32_t acc = op.accumulate;
                         int k_left = op.k_total;
-                        stage = stage0;
-                        phase = phase0;
-                        const bool acquire = t == 0, release = t == NT - 1;
                         for (uint32_t s = 0; s < n_slab; s++) {
                             const int nk = (k_left < ks ? k_left : ks) >> 4;
                             k_left -= ks;
-                            if (acquire) mbar_wait(smem_u32(&w_full[stage]), phase, p.err_flag, 0x300 + stage);
+                            mbar_wait(smem_u32(&w_full[stage]), phase, p.err_flag, 0x300 + stage);
                             tc_fence_after();
                             const uint32_t b_lo = ring_lo + stage * slot_lo;
                             if (elect_one()) {
@@ -432,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                                         acc = 1;
                                     }
                                 }
-                                if (release) tc_commit(smem_u32(&w_empty[stage]));
+                                tc_commit(smem_u32(&w_empty[stage]));
                                 if (s + 1 == n_slab && op.commit) tc_commit(smem_u32(&bars[t][op.commit]));
                             }
                             __syncwarp();
@@ -440,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                             a_cur += (uint32_t)nk * (from_smem ? ((2 * kAkcBytes) >> 4) : 8u);
                             if (++stage == (uint32_t)pl.n_stage) { stage = 0; phase ^= 1; }
                         }
-                        tr.ev(0x400 + i + 0x80 * t);
+                        tr.ev(0x400 + i);
                     }
                 }
             }
@@ -493,26 +488,33 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 const float* tp = p.t_blk + (size_t)code * 8;
                 const float* up = p.u + beam * De;
                 if (cq == 0 && r * 32 < De) prefetch_l1(up + r * 32);    // the per-beam row is shared by many rows: pull it into L1
-#pragma unroll 1
-                for (int kc = e0c >> 3; kc < (e1c >> 3); kc += 2) {   // 16 columns per step, a step's loads issued together
-                    const float4 a0 = ldg4(tp + (size_t)kc * K * 8), a1 = ldg4(tp + (size_t)kc * K * 8 + 4);
-                    const float4 b0 = ldg4(tp + (size_t)(kc + 1) * K * 8), b1 = ldg4(tp + (size_t)(kc + 1) * K * 8 + 4);
-                    const float4 u0 = ldg4(up + kc * 8), u1 = ldg4(up + kc * 8 + 4), u2 = ldg4(up + kc * 8 + 8), u3 = ldg4(up + kc * 8 + 12);
+                auto emit_chunk = [&](int kc, const float4 t0, const float4 t1) {
+                    const float4 u0 = ldg4(up + kc * 8), u1 = ldg4(up + kc * 8 + 4);
                     uint32_t e[8];
-                    float f0 = a0.x + u0.x, f1 = a0.y + u0.y, f2 = a0.z + u0.z, f3 = a0.w + u0.w;
-                    float f4 = a1.x + u1.x, f5 = a1.y + u1.y, f6 = a1.z + u1.z, f7 = a1.w + u1.w;
+                    const float f0 = t0.x + u0.x, f1 = t0.y + u0.y, f2 = t0.z + u0.z, f3 = t0.w + u0.w;
+                    const float f4 = t1.x + u1.x, f5 = t1.y + u1.y, f6 = t1.z + u1.z, f7 = t1.w + u1.w;
                     e[0] = __float_as_uint(f0); e[1] = __float_as_uint(f1); e[2] = __float_as_uint(f2); e[3] = __float_as_uint(f3);
                     e[4] = __float_as_uint(f4); e[5] = __float_as_uint(f5); e[6] = __float_as_uint(f6); e[7] = __float_as_uint(f7);
                     __syncwarp();
                     tmem_st8(tl + pl.tmem_e_col + kc * 8, e);
                     st_shared_v4(ae_dst + (uint32_t)kc * kAkcBytes, pack_h2(f0, f1), pack_h2(f2, f3), pack_h2(f4, f5), pack_h2(f6, f7));
-                    f0 = b0.x + u2.x; f1 = b0.y + u2.y; f2 = b0.z + u2.z; f3 = b0.w + u2.w;
-                    f4 = b1.x + u3.x; f5 = b1.y + u3.y; f6 = b1.z + u3.z; f7 = b1.w + u3.w;
-                    e[0] = __float_as_uint(f0); e[1] = __float_as_uint(f1); e[2] = __float_as_uint(f2); e[3] = __float_as_uint(f3);
-                    e[4] = __float_as_uint(f4); e[5] = __float_as_uint(f5); e[6] = __float_as_uint(f6); e[7] = __float_as_uint(f7);
-                    __syncwarp();
-                    tmem_st8(tl + pl.tmem_e_col + (kc + 1) * 8, e);
-                    st_shared_v4(ae_dst + (uint32_t)(kc + 1) * kAkcBytes, pack_h2(f0, f1), pack_h2(f2, f3), pack_h2(f4, f5), pack_h2(f6, f7));
+                };
+                int kc = e0c >> 3;
+                const int kc_end = e1c >> 3;
+#pragma unroll 1
+                for (; kc + 4 <= kc_end; kc += 4) {      // 32 columns: 8 table loads in flight
+                    float4 tb[8];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { tb[2 * j] = ldg4(tp + (size_t)(kc + j) * K * 8); tb[2 * j + 1] = ldg4(tp + (size_t)(kc + j) * K * 8 + 4); }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) emit_chunk(kc + j, tb[2 * j], tb[2 * j + 1]);
+                }
+#pragma unroll 1
+                for (; kc + 2 <= kc_end; kc += 2) {      // tail: 16 columns
+                    const float4 a0 = ldg4(tp + (size_t)kc * K * 8), a1 = ldg4(tp + (size_t)kc * K * 8 + 4);
+                    const float4 b0 = ldg4(tp + (size_t)(kc + 1) * K * 8), b1 = ldg4(tp + (size_t)(kc + 1) * K * 8 + 4);
+                    emit_chunk(kc, a0, a1);
+                    emit_chunk(kc + 1, b0, b1);
                 }
                 tmem_wait_st();
                 tc_fence_before();
@@ -530,50 +532,62 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 par ^= 1u << bar;
                 tc_fence_after();
             };
-            // final epilogue of columns [c0, c1) at accumulator address taddr (o[d0 + c0 ..]); cb = prefetched skip codeword
+            // skip codeword C_m[code][d .. d+32) (blocked table [D/8][K][8]); `cols` (16 or >= 32) of them are fetched
+            auto load_cb = [&](float4 (&cb)[8], int code, int d, int cols) {
+                const float* base = p.cb_blk + ((size_t)(d >> 3) * K + code) * 8;
+#pragma unroll
+                for (int i = 0; i < 4; i++) cb[i] = ldg4(base + (size_t)(i >> 1) * K * 8 + (i & 1) * 4);
+                if (cols > 16) {
+#pragma unroll
+                    for (int i = 4; i < 8; i++) cb[i] = ldg4(base + (size_t)(i >> 1) * K * 8 + (i & 1) * 4);
+                }
+            };
+            // final epilogue of columns [c0, c1) at accumulator address taddr (o[d0 + c0 ..]); cb = skip codeword of the
+            // first 32 columns, fetched by the caller BEFORE it waited for the accumulator
             auto final_cols = [&](uint32_t taddr, int c0, int c1, int d0, int code, int64_t beam, int64_t row, bool valid,
-                                  float& acc) {
+                                  float4 (&cb)[8], float& acc) {
                 const float* src = (kScore ? p.r : p.xhat_in) + beam * D + d0;
 #pragma unroll 1
-                for (int cc = c0; cc < c1; cc += 16) {
-                    float4 cv[4];
-                    if (pl.skip) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const int d = d0 + cc + i * 4;
-                            cv[i] = ldg4(p.cb_blk + ((size_t)(d >> 3) * K + code) * 8 + (d & 7));
-                        }
-                    }
-                    float4 t4[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) t4[i] = ldg4(src + cc + i * 4);
+                for (int cb0 = c0; cb0 < c1; cb0 += 32) {
+                    if (cb0 > c0 && pl.skip) load_cb(cb, code, d0 + cb0, c1 - cb0);
                     uint32_t v[32];
-                    __syncwarp();
-                    tmem_ld16(taddr + cc, v);
+                    tmem_ld_cols(taddr + cb0, c1 - cb0, v);
+                    float4 t4[8];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) t4[i] = ldg4(src + cb0 + i * 4);
+                    if (c1 - cb0 > 16) {
+#pragma unroll
+                        for (int i = 4; i < 8; i++) t4[i] = ldg4(src + cb0 + i * 4);
+                    }
                     tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        float o0 = __uint_as_float(v[4 * i]), o1 = __uint_as_float(v[4 * i + 1]), o2 = __uint_as_float(v[4 * i + 2]),
-                              o3 = __uint_as_float(v[4 * i + 3]);
-                        if (pl.skip) { o0 += cv[i].x; o1 += cv[i].y; o2 += cv[i].z; o3 += cv[i].w; }
-                        if (kScore) {
-                            const float e0 = t4[i].x - o0, e1 = t4[i].y - o1, e2 = t4[i].z - o2, e3 = t4[i].w - o3;
-                            acc = fmaf(e0, e0, acc); acc = fmaf(e1, e1, acc); acc = fmaf(e2, e2, acc); acc = fmaf(e3, e3, acc);
-                        } else if (valid) {
-                            const int d = d0 + cc + i * 4;
-                            float4 out = make_float4(t4[i].x + o0, t4[i].y + o1, t4[i].z + o2, t4[i].w + o3);
-                            if (p.out_shift) {
-                                const float4 sh = ldg4(p.out_shift + d);
-                                out.x = fmaf(out.x, p.out_scale, sh.x); out.y = fmaf(out.y, p.out_scale, sh.y);
-                                out.z = fmaf(out.z, p.out_scale, sh.z); out.w = fmaf(out.w, p.out_scale, sh.w);
-                            } else if (p.out_scale != 1.0f) {
-                                out.x *= p.out_scale; out.y *= p.out_scale; out.z *= p.out_scale; out.w *= p.out_scale;
+                    for (int i = 0; i < 8; i++) {
+                        if (i < 4 || c1 - cb0 > 16) {
+                            float o0 = __uint_as_float(v[4 * i]), o1 = __uint_as_float(v[4 * i + 1]), o2 = __uint_as_float(v[4 * i + 2]),
+                                  o3 = __uint_as_float(v[4 * i + 3]);
+                            if (pl.skip) { o0 += cb[i].x; o1 += cb[i].y; o2 += cb[i].z; o3 += cb[i].w; }
+                            if (kScore) {
+                                const float e0 = t4[i].x - o0, e1 = t4[i].y - o1, e2 = t4[i].z - o2, e3 = t4[i].w - o3;
+                                acc = fmaf(e0, e0, acc); acc = fmaf(e1, e1, acc); acc = fmaf(e2, e2, acc); acc = fmaf(e3, e3, acc);
+                            } else if (valid) {
+                                const int d = d0 + cb0 + i * 4;
+                                float4 out = make_float4(t4[i].x + o0, t4[i].y + o1, t4[i].z + o2, t4[i].w + o3);
+                                if (p.out_shift) {
+                                    const float4 sh = ldg4(p.out_shift + d);
+                                    out.x = fmaf(out.x, p.out_scale, sh.x); out.y = fmaf(out.y, p.out_scale, sh.y);
+                                    out.z = fmaf(out.z, p.out_scale, sh.z); out.w = fmaf(out.w, p.out_scale, sh.w);
+                                } else if (p.out_scale != 1.0f) {
+                                    out.x *= p.out_scale; out.y *= p.out_scale; out.z *= p.out_scale; out.w *= p.out_scale;
+                                }
+                                *reinterpret_cast<float4*>(p.xhat_out + row * D + d) = out;
                             }
-                            *reinterpret_cast<float4*>(p.xhat_out + row * D + d) = out;
                         }
                     }
                 }
             };
+            float4 cb[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) cb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
             for (int l = 0; l < pl.L; l++) {
 #pragma unroll 1
@@ -595,8 +609,13 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
 #pragma unroll 1
                 for (int t = 0; t < NT; t++) {
                     const uint32_t tl = lane_base + (uint32_t)t * tile_cols;
-                    if (last && cq == 0 && r * 32 < D)   // the per-beam operand of the final epilogue travels to L1 meanwhile
-                        prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
+                    tr.ev(9 + 0x80 * t);
+                    if (last && !pl.has_proj) {   // inputs of the final epilogue travel while the last down-projection runs
+                        if (cq == 0 && r * 32 < D) prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
+                        tr.ev(10 + 0x80 * t);
+                        if (pl.skip && o0c < o1c) load_cb(cb, t ? code1 : code0, o0c, o1c - o0c);
+                    }
+                    tr.ev(11 + 0x80 * t);
                     wait_bar(t, QB_BAR_EACC_FULL, 0x405);
                     tr.ev(5 + 0x80 * t);
                     if (!last || pl.has_proj) {
@@ -608,7 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     } else {
                         float a = 0.f;
                         final_cols(tl + pl.tmem_e_col, o0c, o1c, 0, t ? code1 : code0, t ? beam1 : beam0, t ? row1 : row0,
-                                   t ? valid1 : valid0, a);
+                                   t ? valid1 : valid0, cb, a);
                         if (t) acc1 = a; else acc0 = a;
                         tc_fence_before();
                         tr.ev(7 + 0x80 * t);
@@ -623,10 +642,12 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     quarter_range(cw, cq, c0, c1);
 #pragma unroll 1
                     for (int t = 0; t < NT; t++) {
+                        if (pl.skip && c0 < c1) load_cb(cb, t ? code1 : code0, qq * pl.oc + c0, c1 - c0);
+                        if (qq == 0 && cq == 0 && r * 32 < D) prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
                         wait_bar(t, QB_BAR_HACC_FULL, 0x414);
                         const uint32_t ta = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
                         float a = t ? acc1 : acc0;
-                        final_cols(ta, c0, c1, qq * pl.oc, t ? code1 : code0, t ? beam1 : beam0, t ? row1 : row0, t ? valid1 : valid0, a);
+                        final_cols(ta, c0, c1, qq * pl.oc, t ? code1 : code0, t ? beam1 : beam0, t ? row1 : row0, t ? valid1 : valid0, cb, a);
                         if (t) acc1 = a; else acc0 = a;
                         tc_fence_before();
                         if (qq + 1 < pl.n_ochunk) mbar_arrive(smem_u32(&bars[t][QB_BAR_HACC_FREE]));
@@ -636,8 +657,9 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
 #pragma unroll 1
                 for (int t = 0; t < NT; t++) {
                     float a = 0.f;
+                    if (pl.skip && o0c < o1c) load_cb(cb, t ? code1 : code0, o0c, o1c - o0c);
                     final_cols(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, o0c, o1c, 0, t ? code1 : code0, t ? beam1 : beam0,
-                               t ? row1 : row0, t ? valid1 : valid0, a);
+                               t ? row1 : row0, t ? valid1 : valid0, cb, a);
                     if (t) acc1 = a; else acc0 = a;
                 }
                 tc_fence_before();
