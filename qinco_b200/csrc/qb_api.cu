@@ -423,7 +423,7 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
     qb::PlanOptions opt;
     opt.hc = d->opt_hc; opt.n_tiles = d->opt_n_tiles & 0xff; opt.ctas_per_sm = d->opt_n_tiles >> 8;
     opt.slot_bytes = d->opt_slot_bytes;
-    opt.max_stage = d->opt_max_stage; opt.max_slab_k = d->opt_max_slab_k;
+    opt.max_stage = d->opt_max_stage & 0xff; opt.no_resident = d->opt_max_stage >> 8; opt.max_slab_k = d->opt_max_slab_k;
     int max_smem = 0;
     for (int s = 1; s < m->M; s++) {
         StepDev& sd = m->steps[s];

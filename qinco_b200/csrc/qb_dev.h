@@ -22,8 +22,8 @@ struct MlpParams {
                               // warps read it through the uniform datapath
     int32_t n_ops;
     const uint8_t* w_blob;    // packed fp16 slabs of this step
-    const float* t_blk;       // [De/8][K][8]  T_m
-    const float* cb_blk;      // [D/8][K][8]   C_m (outer skip), unused in qinco1_mode
+    const float* t_blk;       // [De/4][K][4]  T_m
+    const float* cb_blk;      // [D/4][K][4]   C_m (outer skip), unused in qinco1_mode
     int32_t mode;
     int32_t C, A;             // score
     int32_t F_in, F_out;      // apply

@@ -38,7 +38,8 @@ namespace qb {
 
 namespace {
 
-constexpr int kEpiWarps = 16;             // four warps per TMEM lane quarter: warp w owns lanes 32*(w%4).., column quarter w/4
+constexpr int kEpiWarps = 8;              // two warps per TMEM lane quarter: warp w owns lanes 32*(w%4).., column group w/4
+constexpr int kColGroups = kEpiWarps / 4;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiThreads + 96;   // + producer warp + one MMA warp per tile slot
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;   // MMA warps: kMmaWarp + tile slot
@@ -81,22 +82,22 @@ __device__ __forceinline__ uint64_t globaltimer() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// Bounded wait: a protocol bug must trap (and report) instead of hanging the GPU.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t* err_flag, uint32_t code) {
-    const uint64_t t0 = globaltimer();
+// Bounded wait: a protocol bug must trap (and report) instead of hanging the GPU.  Fully inlined: a call here would
+// make every live register of the epilogue (prefetched table rows) caller-saved, i.e. spilled around each wait.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* err_flag, uint32_t code) {
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (globaltimer() - t0 > 4000000000ull) {   // 4 s
-            if (err_flag) atomicExch(err_flag, code);
-            __threadfence_system();
-            __trap();
+        if ((++spins & 1023u) == 0) {               // the timer is read only once in a while, off the fast path
+            const uint64_t now = globaltimer();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 4000000000ull) {          // 4 s
+                if (err_flag) atomicExch(err_flag, code);
+                __threadfence_system();
+                __trap();
+            }
         }
     }
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* err_flag, uint32_t code) {
-#pragma unroll 1
-    for (int i = 0; i < 64; i++)
-        if (mbar_try_wait(bar, parity)) return;
-    mbar_wait_slow(bar, parity, err_flag, code);
 }
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -221,45 +222,57 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, int nc, uint32_t (&
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-// Column range [c0, c1) of a width-W block (W a multiple of 16) owned by column quarter cq: 16-column units are dealt
-// out as evenly as possible.
-__device__ __forceinline__ void quarter_range(int W, int cq, int& c0, int& c1) {
-    const int units = W >> 4, base = units >> 2, rem = units & 3;
-    const int u0 = cq * base + (cq < rem ? cq : rem);
+// Column range [c0, c1) of a width-W block (W a multiple of 16) owned by column group cg of kColGroups: 16-column units
+// are dealt out as evenly as possible.
+__device__ __forceinline__ void group_range(int W, int cg, int& c0, int& c1) {
+    const int units = W >> 4, base = units / kColGroups, rem = units % kColGroups;
+    const int u0 = cg * base + (cg < rem ? cg : rem);
     c0 = u0 << 4;
-    c1 = (u0 + base + (cq < rem ? 1 : 0)) << 4;
+    c1 = (u0 + base + (cg < rem ? 1 : 0)) << 4;
 }
 
-// fp32 accumulator columns [c0, c1) at `taddr` -> fp16 -> A_E k-chunks (shared memory, `sdst` already includes the row)
+// fp32 accumulator columns [c0, c1) at `taddr` -> fp16 -> A_E k-chunks (shared memory, `sdst` already includes the row);
+// 64 columns per step with both tcgen05.ld of the step in flight together
 __device__ __forceinline__ void acc_to_smem_operand(uint32_t taddr, int c0, int c1, uint32_t sdst) {
 #pragma unroll 1
-    for (int c = c0; c < c1; c += 32) {
-        uint32_t v[32];
+    for (int c = c0; c < c1; c += 64) {
+        uint32_t va[32], vb[32];
         const int n = c1 - c;
-        tmem_ld_cols(taddr + c, n, v);
+        tmem_ld_cols(taddr + c, n, va);
+        if (n > 32) tmem_ld_cols(taddr + c + 32, n - 32, vb);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 4; i++)
             if (i * 8 < n)
                 st_shared_v4(sdst + (uint32_t)((c / 8 + i) * kAkcBytes),
-                             pack_h2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
-                             pack_h2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
-                             pack_h2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
-                             pack_h2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+                             pack_h2(__uint_as_float(va[8 * i]), __uint_as_float(va[8 * i + 1])),
+                             pack_h2(__uint_as_float(va[8 * i + 2]), __uint_as_float(va[8 * i + 3])),
+                             pack_h2(__uint_as_float(va[8 * i + 4]), __uint_as_float(va[8 * i + 5])),
+                             pack_h2(__uint_as_float(va[8 * i + 6]), __uint_as_float(va[8 * i + 7])));
+        if (n > 32) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (32 + i * 8 < n)
+                    st_shared_v4(sdst + (uint32_t)((c / 8 + 4 + i) * kAkcBytes),
+                                 pack_h2(__uint_as_float(vb[8 * i]), __uint_as_float(vb[8 * i + 1])),
+                                 pack_h2(__uint_as_float(vb[8 * i + 2]), __uint_as_float(vb[8 * i + 3])),
+                                 pack_h2(__uint_as_float(vb[8 * i + 4]), __uint_as_float(vb[8 * i + 5])),
+                                 pack_h2(__uint_as_float(vb[8 * i + 6]), __uint_as_float(vb[8 * i + 7])));
+        }
     }
 }
 
 // fp32 Hacc columns [c0, c1) (c1 - c0 <= 64) at `taddr` -> relu -> packed fp16 pairs written back IN PLACE at columns
 // [c0/2, c1/2).  The packed block of a higher column quarter lands on fp32 columns a lower quarter's thread still has
-// to read, so the four warps sharing a lane quarter first pull their whole range into registers, meet at a named
-// barrier and only then write.
+// to read, so the warps sharing a lane quarter first pull their whole range into registers, meet at a named barrier
+// and only then write.
 __device__ __forceinline__ void acc_to_tmem_operand(uint32_t taddr, int c0, int c1, int quarter_bar) {
     uint32_t va[32], vb[32];
     const int n = c1 - c0;
     if (n > 0) tmem_ld_cols(taddr + c0, n, va);
     if (n > 32) tmem_ld_cols(taddr + c0 + 32, n - 32, vb);
     tmem_wait_ld();
-    named_bar_sync(quarter_bar, 128);
+    named_bar_sync(quarter_bar, kColGroups * 32);
     if (n > 0) {
         uint32_t w[16];
 #pragma unroll
@@ -292,14 +305,17 @@ struct Tracer {
 
 }  // namespace
 
-template <bool kScore>
+template <bool kScore, bool kResident>
 __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_constant__ MlpParams p) {
     extern __shared__ __align__(1024) uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t bars[2][QB_BAR_COUNT];     // one barrier set per tile slot
     __shared__ __align__(8) uint64_t w_full[QB_MAX_STAGE];
     __shared__ __align__(8) uint64_t w_empty[QB_MAX_STAGE];
+    __shared__ __align__(8) uint64_t tres_bar;                  // resident table half has landed
+    __shared__ __align__(8) uint64_t rows_full[3], rows_empty[3];   // resident mode: per-beam rows (u_b, r_b) of a set, 3 sets deep
+    __shared__ __align__(16) float beam_rows[3][2][256];        // [buffer][tile slot][u_b (De) | r_b (D)]
     __shared__ uint32_t tmem_base_s;
-    __shared__ float dist_part[2][3][QB_TILE_M];
+    __shared__ float dist_part[2][kColGroups > 1 ? kColGroups - 1 : 1][QB_TILE_M];
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (uniform datapath)
@@ -307,7 +323,14 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     const int n_ops = pl.n_ops_block + pl.n_ops_out;
     const int NT = pl.n_tiles;
     const int64_t n_tiles = (p.n_rows + QB_TILE_M - 1) / QB_TILE_M;
-    const int64_t n_sets = (n_tiles + NT - 1) / NT;           // a CTA works on NT consecutive tiles at a time
+    // Work units ("sets" of NT tiles).  Default: NT consecutive tiles, sets strided over the CTAs.  Resident mode (score,
+    // all 256 codes per beam = 2 tiles per beam): CTA parity hh picks the code half, a set is the hh-half of two
+    // consecutive beams, so both tile slots use the same 128 codes whose table rows never leave the SM.
+    const int hh = kResident ? (int)(blockIdx.x & 1) : 0;
+    const int64_t n_beams = p.n_rows >> 8;
+    const int64_t n_sets = kResident ? (n_beams + 1) / 2 : (n_tiles + NT - 1) / NT;
+    const int64_t set_first = kResident ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+    const int64_t set_stride = kResident ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
 
     // ---- one-time setup ------------------------------------------------------------------------------------------
     if (tid == 0) {
@@ -319,6 +342,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             mbar_init(smem_u32(&bars[t][QB_BAR_HACC_FULL]), 1);
             mbar_init(smem_u32(&bars[t][QB_BAR_EACC_FULL]), 1);
         }
+        mbar_init(smem_u32(&tres_bar), 1);
+        for (int b = 0; b < 3; b++) { mbar_init(smem_u32(&rows_full[b]), 1); mbar_init(smem_u32(&rows_empty[b]), kEpiThreads); }
         for (int s = 0; s < QB_MAX_STAGE; s++) {
             mbar_init(smem_u32(&w_full[s]), 1);
             mbar_init(smem_u32(&w_empty[s]), (uint32_t)pl.n_tiles);   // released by every tile slot's MMA warp
@@ -341,7 +366,37 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     if (warp == kProducerWarp) {
         // ======================================================================================= weight producer
         uint32_t stage = 0, phase = 0;
-        for (int64_t set = blockIdx.x; set < n_sets; set += gridDim.x) {
+        if (kResident) {    // this CTA's half of T_m: De/4 column blocks of 128 codes x 16 B, contiguous 2 KB each in the table
+            if (elect_one()) {
+                mbar_expect_tx(smem_u32(&tres_bar), (uint32_t)pl.De * 512u);
+                for (int c4 = 0; c4 < (pl.De >> 2); c4++)
+                    bulk_g2s(smem_base + pl.smem_tres + c4 * 2048, p.t_blk + ((size_t)c4 * pl.K + hh * 128) * 4, 2048,
+                             smem_u32(&tres_bar));
+            }
+            __syncwarp();
+        }
+        // resident mode: the per-beam rows u_b (init) and r_b (distance) of set number k land in beam_rows[k % 3] one set
+        // ahead of their use; buffer k % 3 was last read by set k - 3, long finished
+        auto push_rows = [&](int64_t set, int64_t k) {
+            if (set >= n_sets) return;
+            const int b = (int)(k % 3);
+            mbar_wait(smem_u32(&rows_empty[b]), (uint32_t)(((k / 3) & 1) ^ 1), p.err_flag, 0x600 + b);
+            if (elect_one()) {
+                const uint32_t de_b = (uint32_t)pl.De * 4u, d_b = (uint32_t)pl.D * 4u;
+                mbar_expect_tx(smem_u32(&rows_full[b]), 2u * (de_b + d_b));
+                for (int t = 0; t < 2; t++) {
+                    int64_t beam = 2 * set + t;
+                    if (beam >= n_beams) beam = 0;
+                    bulk_g2s(smem_u32(&beam_rows[b][t][0]), p.u + beam * pl.De, de_b, smem_u32(&rows_full[b]));
+                    bulk_g2s(smem_u32(&beam_rows[b][t][pl.De]), p.r + beam * pl.D, d_b, smem_u32(&rows_full[b]));
+                }
+            }
+            __syncwarp();
+        };
+        int64_t kset = 0;
+        if (kResident) push_rows(set_first, 0);
+        for (int64_t set = set_first; set < n_sets; set += set_stride, kset++) {
+            if (kResident) push_rows(set + set_stride, kset + 1);
             for (int l = 0; l <= pl.L; l++) {
                 const int i0 = (l < pl.L) ? 0 : pl.n_ops_block;
                 const int i1 = (l < pl.L) ? pl.n_ops_block : n_ops;
@@ -380,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             const uint64_t a_hi = umma_desc(0, kAkcBytes, 128);
             const uint32_t tcol = tmem_base + (uint32_t)t * tile_cols;
             const uint32_t ae_lo = (smem_base + pl.smem_ae[t]) >> 4;
-            for (int64_t set = blockIdx.x; set < n_sets; set += gridDim.x) {
+            for (int64_t set = set_first; set < n_sets; set += set_stride) {
                 for (int l = 0; l <= pl.L; l++) {
                     const int i0 = (l < pl.L) ? 0 : pl.n_ops_block;
                     const int i1 = (l < pl.L) ? pl.n_ops_block : n_ops;
@@ -443,10 +498,10 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     } else {
         // ======================================================================================= epilogue warps
         // Thread (lane quarter q = warp % 4, lane) owns row r = 32 q + lane of BOTH tiles in flight and alternates
-        // between them; the four warps of a lane quarter split every column range in quarters (cq = warp / 4), so a
-        // phase is one 32-column block per thread for the 128-wide shapes and latency is hidden by warp count, not by
-        // registers.
-        const int q = warp & 3, cq = warp >> 2;
+        // between them; the kColGroups warps of a lane quarter split every column range (cg = warp / 4).  Table rows
+        // (T_m, the skip codeword) are fetched 64 columns at a time with all loads of a batch issued together, the skip
+        // codeword before the thread starts waiting for the accumulator.
+        const int q = warp & 3, cg = warp >> 2;
         const int r = q * 32 + (tid & 31);
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t par0 = 0, par1 = 0;
@@ -454,14 +509,38 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         tr.init(p, 0, tid == 0);
         const int De = pl.De, K = pl.K, D = pl.D;
         int e0c, e1c, o0c, o1c;             // this thread's columns of e / of the output (no out_proj)
-        quarter_range(De, cq, e0c, e1c);
-        quarter_range(D, cq, o0c, o1c);
-        for (int64_t set = blockIdx.x; set < n_sets; set += gridDim.x) {
+        group_range(De, cg, e0c, e1c);
+        group_range(D, cg, o0c, o1c);
+        // resident mode: this thread's slice of the skip codeword of ITS code (the same for every tile it will ever see)
+        float4 creg[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) creg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kResident) {
+            if (pl.skip) {
+                const float* base = p.cb_blk + ((size_t)(o0c >> 2) * K + hh * 128 + r) * 4;
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    if (o0c + i * 4 < o1c) creg[i] = ldg4(base + (size_t)i * K * 4);
+            }
+            mbar_wait(smem_u32(&tres_bar), 0, p.err_flag, 0x500);
+        }
+        int64_t kset = 0;
+        for (int64_t set = set_first; set < n_sets; set += set_stride, kset++) {
+            const int rb = (int)(kset % 3);
+            if (kResident) mbar_wait(smem_u32(&rows_full[rb]), (uint32_t)((kset / 3) & 1), p.err_flag, 0x610 + rb);
             // per-tile row context, kept in scalars (no runtime-indexed arrays)
             int code0 = 0, code1 = 0;
             int64_t beam0 = 0, beam1 = 0, row0 = 0, row1 = 0;
             bool valid0 = false, valid1 = false;
             auto row_ctx = [&](int t, int64_t& row, int64_t& beam, int& code, bool& valid) {
+                if (kResident) {            // tile slot t = beam 2*set + t, rows of code half hh; the code never changes
+                    beam = 2 * set + t;
+                    code = hh * 128 + r;
+                    row = beam * 256 + code;
+                    valid = beam < n_beams;
+                    if (!valid) beam = 0;
+                    return;
+                }
                 row = (set * NT + t) * QB_TILE_M + r;
                 valid = t < NT && row < p.n_rows;
                 if (valid) {
@@ -481,40 +560,62 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             row_ctx(0, row0, beam0, code0, valid0);
             row_ctx(1, row1, beam1, code1, valid1);
             tr.ev(1);
+            // table row block: columns [c, c + 64) of a [cols/4][K][4] table for `code`, `n` (<= 64, multiple of 16) of them
+            auto load_row64 = [&](float4 (&tb)[16], const float* tbl, int code, int c, int n) {
+                const float* base = tbl + ((size_t)(c >> 2) * K + code) * 4;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    if (j * 4 < n) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) tb[j + i] = ldg4(base + (size_t)(j + i) * K * 4);
+                    }
+                }
+            };
             // ---- init: e0 = T_m[code] + u_b over this thread's columns ------------------------------------------------
             auto init_tile = [&](int t, int code, int64_t beam) {
                 const uint32_t tl = lane_base + (uint32_t)t * tile_cols;
                 const uint32_t ae_dst = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
-                const float* tp = p.t_blk + (size_t)code * 8;
                 const float* up = p.u + beam * De;
-                if (cq == 0 && r * 32 < De) prefetch_l1(up + r * 32);    // the per-beam row is shared by many rows: pull it into L1
-                auto emit_chunk = [&](int kc, const float4 t0, const float4 t1) {
-                    const float4 u0 = ldg4(up + kc * 8), u1 = ldg4(up + kc * 8 + 4);
-                    uint32_t e[8];
-                    const float f0 = t0.x + u0.x, f1 = t0.y + u0.y, f2 = t0.z + u0.z, f3 = t0.w + u0.w;
-                    const float f4 = t1.x + u1.x, f5 = t1.y + u1.y, f6 = t1.z + u1.z, f7 = t1.w + u1.w;
-                    e[0] = __float_as_uint(f0); e[1] = __float_as_uint(f1); e[2] = __float_as_uint(f2); e[3] = __float_as_uint(f3);
-                    e[4] = __float_as_uint(f4); e[5] = __float_as_uint(f5); e[6] = __float_as_uint(f6); e[7] = __float_as_uint(f7);
-                    __syncwarp();
-                    tmem_st8(tl + pl.tmem_e_col + kc * 8, e);
-                    st_shared_v4(ae_dst + (uint32_t)kc * kAkcBytes, pack_h2(f0, f1), pack_h2(f2, f3), pack_h2(f4, f5), pack_h2(f6, f7));
-                };
-                int kc = e0c >> 3;
-                const int kc_end = e1c >> 3;
+                if (!kResident && cg == 0 && r * 32 < De) prefetch_l1(up + r * 32);   // the per-beam row is shared by many rows: pull it into L1
 #pragma unroll 1
-                for (; kc + 4 <= kc_end; kc += 4) {      // 32 columns: 8 table loads in flight
-                    float4 tb[8];
+                for (int c = e0c; c < e1c; c += 64) {
+                    float4 tb[16];
+                    const int n = e1c - c;
+                    if (kResident) {
+                        const uint32_t ts = smem_base + pl.smem_tres + (uint32_t)r * 16u;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { tb[2 * j] = ldg4(tp + (size_t)(kc + j) * K * 8); tb[2 * j + 1] = ldg4(tp + (size_t)(kc + j) * K * 8 + 4); }
+                        for (int j = 0; j < 16; j++)
+                            if (j * 4 < n) {
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                             : "=f"(tb[j].x), "=f"(tb[j].y), "=f"(tb[j].z), "=f"(tb[j].w)
+                                             : "r"(ts + (uint32_t)((c >> 2) + j) * 2048u));
+                            }
+                    } else {
+                        load_row64(tb, p.t_blk, code, c, n);
+                    }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) emit_chunk(kc + j, tb[2 * j], tb[2 * j + 1]);
-                }
-#pragma unroll 1
-                for (; kc + 2 <= kc_end; kc += 2) {      // tail: 16 columns
-                    const float4 a0 = ldg4(tp + (size_t)kc * K * 8), a1 = ldg4(tp + (size_t)kc * K * 8 + 4);
-                    const float4 b0 = ldg4(tp + (size_t)(kc + 1) * K * 8), b1 = ldg4(tp + (size_t)(kc + 1) * K * 8 + 4);
-                    emit_chunk(kc, a0, a1);
-                    emit_chunk(kc + 1, b0, b1);
+                    for (int j = 0; j < 8; j++) {       // 8 columns per step
+                        if (j * 8 < n) {
+                            const int kc = (c >> 3) + j;
+                            float4 u0, u1;
+                            if (kResident) {
+                                u0 = *reinterpret_cast<const float4*>(&beam_rows[rb][t][kc * 8]);
+                                u1 = *reinterpret_cast<const float4*>(&beam_rows[rb][t][kc * 8 + 4]);
+                            } else {
+                                u0 = ldg4(up + kc * 8);
+                                u1 = ldg4(up + kc * 8 + 4);
+                            }
+                            const float4 t0 = tb[2 * j], t1 = tb[2 * j + 1];
+                            uint32_t e[8];
+                            const float f0 = t0.x + u0.x, f1 = t0.y + u0.y, f2 = t0.z + u0.z, f3 = t0.w + u0.w;
+                            const float f4 = t1.x + u1.x, f5 = t1.y + u1.y, f6 = t1.z + u1.z, f7 = t1.w + u1.w;
+                            e[0] = __float_as_uint(f0); e[1] = __float_as_uint(f1); e[2] = __float_as_uint(f2); e[3] = __float_as_uint(f3);
+                            e[4] = __float_as_uint(f4); e[5] = __float_as_uint(f5); e[6] = __float_as_uint(f6); e[7] = __float_as_uint(f7);
+                            __syncwarp();
+                            tmem_st8(tl + pl.tmem_e_col + kc * 8, e);
+                            st_shared_v4(ae_dst + (uint32_t)kc * kAkcBytes, pack_h2(f0, f1), pack_h2(f2, f3), pack_h2(f4, f5), pack_h2(f6, f7));
+                        }
+                    }
                 }
                 tmem_wait_st();
                 tc_fence_before();
@@ -532,69 +633,57 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 par ^= 1u << bar;
                 tc_fence_after();
             };
-            // skip codeword C_m[code][d .. d+32) (blocked table [D/8][K][8]); `cols` (16 or >= 32) of them are fetched
-            auto load_cb = [&](float4 (&cb)[8], int code, int d, int cols) {
-                const float* base = p.cb_blk + ((size_t)(d >> 3) * K + code) * 8;
-#pragma unroll
-                for (int i = 0; i < 4; i++) cb[i] = ldg4(base + (size_t)(i >> 1) * K * 8 + (i & 1) * 4);
-                if (cols > 16) {
-#pragma unroll
-                    for (int i = 4; i < 8; i++) cb[i] = ldg4(base + (size_t)(i >> 1) * K * 8 + (i & 1) * 4);
-                }
-            };
             // final epilogue of columns [c0, c1) at accumulator address taddr (o[d0 + c0 ..]); cb = skip codeword of the
-            // first 32 columns, fetched by the caller BEFORE it waited for the accumulator
+            // first 64 columns, fetched by the caller BEFORE it waited for the accumulator
             auto final_cols = [&](uint32_t taddr, int c0, int c1, int d0, int code, int64_t beam, int64_t row, bool valid,
-                                  float4 (&cb)[8], float& acc) {
-                const float* src = (kScore ? p.r : p.xhat_in) + beam * D + d0;
+                                  float4 (&cb)[16], float& acc, const float* rows_smem) {
+                const float* src = kResident ? rows_smem + d0 : (kScore ? p.r : p.xhat_in) + beam * D + d0;
 #pragma unroll 1
-                for (int cb0 = c0; cb0 < c1; cb0 += 32) {
-                    if (cb0 > c0 && pl.skip) load_cb(cb, code, d0 + cb0, c1 - cb0);
-                    uint32_t v[32];
-                    tmem_ld_cols(taddr + cb0, c1 - cb0, v);
-                    float4 t4[8];
+                for (int cb0 = c0; cb0 < c1; cb0 += 64) {
+                    const int n = c1 - cb0;
+                    if (cb0 > c0 && pl.skip) load_row64(cb, p.cb_blk, code, d0 + cb0, n);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) t4[i] = ldg4(src + cb0 + i * 4);
-                    if (c1 - cb0 > 16) {
+                    for (int hh = 0; hh < 2; hh++) {    // 32 accumulator columns per step
+                        if (hh * 32 < n) {
+                            uint32_t v[32];
+                            tmem_ld_cols(taddr + cb0 + hh * 32, n - hh * 32, v);
+                            tmem_wait_ld();
 #pragma unroll
-                        for (int i = 4; i < 8; i++) t4[i] = ldg4(src + cb0 + i * 4);
-                    }
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        if (i < 4 || c1 - cb0 > 16) {
-                            float o0 = __uint_as_float(v[4 * i]), o1 = __uint_as_float(v[4 * i + 1]), o2 = __uint_as_float(v[4 * i + 2]),
-                                  o3 = __uint_as_float(v[4 * i + 3]);
-                            if (pl.skip) { o0 += cb[i].x; o1 += cb[i].y; o2 += cb[i].z; o3 += cb[i].w; }
-                            if (kScore) {
-                                const float e0 = t4[i].x - o0, e1 = t4[i].y - o1, e2 = t4[i].z - o2, e3 = t4[i].w - o3;
-                                acc = fmaf(e0, e0, acc); acc = fmaf(e1, e1, acc); acc = fmaf(e2, e2, acc); acc = fmaf(e3, e3, acc);
-                            } else if (valid) {
-                                const int d = d0 + cb0 + i * 4;
-                                float4 out = make_float4(t4[i].x + o0, t4[i].y + o1, t4[i].z + o2, t4[i].w + o3);
-                                if (p.out_shift) {
-                                    const float4 sh = ldg4(p.out_shift + d);
-                                    out.x = fmaf(out.x, p.out_scale, sh.x); out.y = fmaf(out.y, p.out_scale, sh.y);
-                                    out.z = fmaf(out.z, p.out_scale, sh.z); out.w = fmaf(out.w, p.out_scale, sh.w);
-                                } else if (p.out_scale != 1.0f) {
-                                    out.x *= p.out_scale; out.y *= p.out_scale; out.z *= p.out_scale; out.w *= p.out_scale;
+                            for (int i = 0; i < 8; i++) {
+                                if (hh * 32 + i * 4 < n) {
+                                    const int cc = cb0 + hh * 32 + i * 4;
+                                    const float4 t4 = kResident ? *reinterpret_cast<const float4*>(src + cc) : ldg4(src + cc);
+                                    float o0 = __uint_as_float(v[4 * i]), o1 = __uint_as_float(v[4 * i + 1]), o2 = __uint_as_float(v[4 * i + 2]),
+                                          o3 = __uint_as_float(v[4 * i + 3]);
+                                    if (pl.skip) { const float4 cv = cb[hh * 8 + i]; o0 += cv.x; o1 += cv.y; o2 += cv.z; o3 += cv.w; }
+                                    if (kScore) {
+                                        const float e0 = t4.x - o0, e1 = t4.y - o1, e2 = t4.z - o2, e3 = t4.w - o3;
+                                        acc = fmaf(e0, e0, acc); acc = fmaf(e1, e1, acc); acc = fmaf(e2, e2, acc); acc = fmaf(e3, e3, acc);
+                                    } else if (valid) {
+                                        const int d = d0 + cc;
+                                        float4 out = make_float4(t4.x + o0, t4.y + o1, t4.z + o2, t4.w + o3);
+                                        if (p.out_shift) {
+                                            const float4 sh = ldg4(p.out_shift + d);
+                                            out.x = fmaf(out.x, p.out_scale, sh.x); out.y = fmaf(out.y, p.out_scale, sh.y);
+                                            out.z = fmaf(out.z, p.out_scale, sh.z); out.w = fmaf(out.w, p.out_scale, sh.w);
+                                        } else if (p.out_scale != 1.0f) {
+                                            out.x *= p.out_scale; out.y *= p.out_scale; out.z *= p.out_scale; out.w *= p.out_scale;
+                                        }
+                                        *reinterpret_cast<float4*>(p.xhat_out + row * D + d) = out;
+                                    }
                                 }
-                                *reinterpret_cast<float4*>(p.xhat_out + row * D + d) = out;
                             }
                         }
                     }
                 }
             };
-            float4 cb[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) cb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
             for (int l = 0; l < pl.L; l++) {
 #pragma unroll 1
                 for (int j = 0; j < pl.n_hchunk; j++) {
                     const int cw = min(pl.hc, pl.Dh - j * pl.hc);
                     int c0, c1;
-                    quarter_range(cw, cq, c0, c1);
+                    group_range(cw, cg, c0, c1);
 #pragma unroll 1
                     for (int t = 0; t < NT; t++) {
                         wait_bar(t, QB_BAR_HACC_FULL, 0x404);
@@ -605,74 +694,75 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         tr.ev(4 + 0x80 * t);
                     }
                 }
-                const bool last = (l + 1 == pl.L);
+                if (l + 1 < pl.L || pl.has_proj) {
 #pragma unroll 1
-                for (int t = 0; t < NT; t++) {
-                    const uint32_t tl = lane_base + (uint32_t)t * tile_cols;
-                    tr.ev(9 + 0x80 * t);
-                    if (last && !pl.has_proj) {   // inputs of the final epilogue travel while the last down-projection runs
-                        if (cq == 0 && r * 32 < D) prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
-                        tr.ev(10 + 0x80 * t);
-                        if (pl.skip && o0c < o1c) load_cb(cb, t ? code1 : code0, o0c, o1c - o0c);
-                    }
-                    tr.ev(11 + 0x80 * t);
-                    wait_bar(t, QB_BAR_EACC_FULL, 0x405);
-                    tr.ev(5 + 0x80 * t);
-                    if (!last || pl.has_proj) {
-                        acc_to_smem_operand(tl + pl.tmem_e_col, e0c, e1c, smem_base + pl.smem_ae[t] + (uint32_t)r * 16u);
+                    for (int t = 0; t < NT; t++) {
+                        wait_bar(t, QB_BAR_EACC_FULL, 0x405);
+                        tr.ev(5 + 0x80 * t);
+                        acc_to_smem_operand(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, e0c, e1c,
+                                            smem_base + pl.smem_ae[t] + (uint32_t)r * 16u);
                         tc_fence_before();
                         proxy_fence_async();
                         mbar_arrive(smem_u32(&bars[t][QB_BAR_AE_READY]));
                         tr.ev(6 + 0x80 * t);
-                    } else {
-                        float a = 0.f;
-                        final_cols(tl + pl.tmem_e_col, o0c, o1c, 0, t ? code1 : code0, t ? beam1 : beam0, t ? row1 : row0,
-                                   t ? valid1 : valid0, cb, a);
-                        if (t) acc1 = a; else acc0 = a;
-                        tc_fence_before();
-                        tr.ev(7 + 0x80 * t);
                     }
                 }
             }
-            // ---- out_proj chunks / models without residual blocks ------------------------------------------------------
+            // ---- final epilogue straight from Eacc (no out_proj); the skip codeword is only alive here ------------------
+            if (!pl.has_proj) {
+#pragma unroll 1
+                for (int t = 0; t < NT; t++) {
+                    float4 cb[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) cb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    // inputs of the final epilogue travel while the last down-projection runs
+                    if (!kResident && cg == 0 && r * 32 < D) prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
+                    if (!kResident && pl.skip && o0c < o1c) load_row64(cb, p.cb_blk, t ? code1 : code0, o0c, o1c - o0c);
+                    if (pl.L > 0) wait_bar(t, QB_BAR_EACC_FULL, 0x405);
+                    tr.ev(5 + 0x80 * t);
+                    float a = 0.f;
+                    final_cols(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, o0c, o1c, 0, t ? code1 : code0, t ? beam1 : beam0,
+                               t ? row1 : row0, t ? valid1 : valid0, kResident ? creg : cb, a, &beam_rows[rb][t][De]);
+                    if (t) acc1 = a; else acc0 = a;
+                    tc_fence_before();
+                    tr.ev(7 + 0x80 * t);
+                }
+            }
+            // ---- out_proj chunks ---------------------------------------------------------------------------------------
             if (pl.has_proj) {
                 for (int qq = 0; qq < pl.n_ochunk; qq++) {
                     const int cw = min(pl.oc, D - qq * pl.oc);
                     int c0, c1;
-                    quarter_range(cw, cq, c0, c1);
+                    group_range(cw, cg, c0, c1);
 #pragma unroll 1
                     for (int t = 0; t < NT; t++) {
-                        if (pl.skip && c0 < c1) load_cb(cb, t ? code1 : code0, qq * pl.oc + c0, c1 - c0);
-                        if (qq == 0 && cq == 0 && r * 32 < D) prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
+                        float4 cb[16];
+#pragma unroll
+                        for (int i = 0; i < 16; i++) cb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (pl.skip && c0 < c1) load_row64(cb, p.cb_blk, t ? code1 : code0, qq * pl.oc + c0, c1 - c0);
+                        if (qq == 0 && cg == 0 && r * 32 < D) prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
                         wait_bar(t, QB_BAR_HACC_FULL, 0x414);
                         const uint32_t ta = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
                         float a = t ? acc1 : acc0;
-                        final_cols(ta, c0, c1, qq * pl.oc, t ? code1 : code0, t ? beam1 : beam0, t ? row1 : row0, t ? valid1 : valid0, cb, a);
+                        final_cols(ta, c0, c1, qq * pl.oc, t ? code1 : code0, t ? beam1 : beam0, t ? row1 : row0, t ? valid1 : valid0, cb, a, nullptr);
                         if (t) acc1 = a; else acc0 = a;
                         tc_fence_before();
                         if (qq + 1 < pl.n_ochunk) mbar_arrive(smem_u32(&bars[t][QB_BAR_HACC_FREE]));
                     }
                 }
-            } else if (pl.L == 0) {
-#pragma unroll 1
-                for (int t = 0; t < NT; t++) {
-                    float a = 0.f;
-                    if (pl.skip && o0c < o1c) load_cb(cb, t ? code1 : code0, o0c, o1c - o0c);
-                    final_cols(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, o0c, o1c, 0, t ? code1 : code0, t ? beam1 : beam0,
-                               t ? row1 : row0, t ? valid1 : valid0, cb, a);
-                    if (t) acc1 = a; else acc0 = a;
-                }
-                tc_fence_before();
             }
-            if (kScore) {   // the four column quarters of a row meet in shared memory
-                if (cq > 0) { dist_part[0][cq - 1][r] = acc0; dist_part[1][cq - 1][r] = acc1; }
+            if (kScore) {   // the column groups of a row meet in shared memory
+                if (cg > 0) { dist_part[0][cg - 1][r] = acc0; dist_part[1][cg - 1][r] = acc1; }
                 named_bar_sync(5, kEpiThreads);
-                if (cq == 0) {
-                    if (valid0) p.dist[row0] = ((acc0 + dist_part[0][0][r]) + dist_part[0][1][r]) + dist_part[0][2][r];
-                    if (valid1) p.dist[row1] = ((acc1 + dist_part[1][0][r]) + dist_part[1][1][r]) + dist_part[1][2][r];
+                if (cg == 0) {
+#pragma unroll
+                    for (int g = 0; g < kColGroups - 1; g++) { acc0 += dist_part[0][g][r]; acc1 += dist_part[1][g][r]; }
+                    if (valid0) p.dist[row0] = acc0;
+                    if (valid1) p.dist[row1] = acc1;
                 }
                 named_bar_sync(5, kEpiThreads);
             }
+            if (kResident) mbar_arrive(smem_u32(&rows_empty[rb]));
             tr.ev(8);
         }
     }
@@ -696,8 +786,9 @@ cudaError_t mlp_set_smem_attr(int smem_bytes) {
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (smem_bytes <= current[dev]) return cudaSuccess;
-    e = cudaFuncSetAttribute(qb_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(qb_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    e = cudaFuncSetAttribute(qb_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(qb_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(qb_mlp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e == cudaSuccess) current[dev] = smem_bytes;
     return e;
 }
@@ -706,8 +797,23 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
     if (p.n_rows <= 0) return cudaSuccess;
     if (p.n_rows >= (1ll << 31) - 256) return cudaErrorInvalidValue;   // 32-bit row arithmetic in the kernel
     const int64_t n_tiles = (p.n_rows + QB_TILE_M - 1) / QB_TILE_M;
-    const int64_t n_sets = (n_tiles + p.plan.n_tiles - 1) / p.plan.n_tiles;
-    const int grid = (int)(n_sets < n_sm ? n_sets : n_sm);
+    int64_t n_sets = (n_tiles + p.plan.n_tiles - 1) / p.plan.n_tiles;
+    // resident tables: score launches over all 256 codes of every beam (2 tiles per beam), shape qualified by the planner
+    const bool resident = p.mode == QB_MODE_SCORE && p.A == 0 && p.C == 256 && p.plan.K == 256 && p.plan.smem_tres >= 0 &&
+                          p.plan.n_tiles == 2 && (p.n_rows & 255) == 0 && n_sm >= 2;
+    int grid;
+    if (resident) {
+        const int64_t sets_per_half = ((p.n_rows >> 8) + 1) / 2;
+        const int64_t per_half = sets_per_half < n_sm / 2 ? sets_per_half : n_sm / 2;
+        grid = (int)(2 * per_half);
+    } else {
+        grid = (int)(n_sets < n_sm ? n_sets : n_sm);
+    }
+    auto launch = [&](const MlpParams& q) {
+        if (resident) qb_mlp_kernel<true, true><<<grid, kThreads, q.plan.smem_total, stream>>>(q);
+        else if (q.mode == QB_MODE_SCORE) qb_mlp_kernel<true, false><<<grid, kThreads, q.plan.smem_total, stream>>>(q);
+        else qb_mlp_kernel<false, false><<<grid, kThreads, q.plan.smem_total, stream>>>(q);
+    };
     // Debug: QB_MLP_TRACE=<file>[:<launch index>] dumps the event log of CTA 0 for one launch (synchronises).
     static const char* trace_env = getenv("QB_MLP_TRACE");
     static int trace_at = -1, launch_no = 0;
@@ -720,8 +826,7 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
         const size_t bytes = (3 * QB_TRACE_EVENTS + 512) * sizeof(unsigned long long);
         cudaMalloc((void**)&q.trace, bytes);
         cudaMemsetAsync(q.trace, 0, bytes, stream);
-        if (p.mode == QB_MODE_SCORE) qb_mlp_kernel<true><<<grid, kThreads, p.plan.smem_total, stream>>>(q);
-        else qb_mlp_kernel<false><<<grid, kThreads, p.plan.smem_total, stream>>>(q);
+        launch(q);
         cudaStreamSynchronize(stream);
         std::vector<unsigned long long> h(3 * QB_TRACE_EVENTS + 512);
         cudaMemcpy(h.data(), q.trace, bytes, cudaMemcpyDeviceToHost);
@@ -741,8 +846,7 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
         }
         return cudaGetLastError();
     }
-    if (p.mode == QB_MODE_SCORE) qb_mlp_kernel<true><<<grid, kThreads, p.plan.smem_total, stream>>>(p);
-    else qb_mlp_kernel<false><<<grid, kThreads, p.plan.smem_total, stream>>>(p);
+    launch(p);
     return cudaGetLastError();
 }
 

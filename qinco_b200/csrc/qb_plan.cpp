@@ -107,6 +107,16 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     // ---- shared memory ------------------------------------------------------------------------------------------
     int off = 0;
     for (int t = 0; t < 2; t++) { p->smem_ae[t] = off; if (t < n_tiles) off += ae_bytes; }
+    // Resident tables (score launches with all K = 256 candidates per beam): both tile slots of a CTA then work on the
+    // same half of the codes, whose rows of T_m stay in shared memory (and whose skip codewords stay in registers)
+    // instead of being gathered from L2 for every tile.
+    p->smem_tres = -1;
+    if (n_tiles == 2 && !p->has_proj && K == 256 && De * 512 <= 64 * 1024 && budget - off - De * 512 >= 4 * 16384 &&
+        opt.no_resident == 0) {
+        p->smem_tres = off;
+        off += De * 512;
+        if (opt.slot_bytes <= 0) p->slot_bytes = 16384;      // a deeper ring of smaller slabs fits next to the table
+    }
     p->smem_ring = off;
     int n_stage = (budget - off) / p->slot_bytes;
     n_stage = std::min(n_stage, opt.max_stage > 0 ? std::min(opt.max_stage, QB_MAX_STAGE) : QB_MAX_STAGE);
@@ -164,7 +174,6 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     p->n_ops_out = (int)ops->size() - p->n_ops_block;
     if (ops->size() > QB_MAX_OPS) { *err = "op list too long"; return -1; }
     for (const QbOp& op : *ops)
-        if (n_tiles == 2 && op.n_slab + 1 > n_stage) { *err = "weight ring too shallow for two tiles (raise slot_bytes)"; return -1; }
     for (const QbOp& op : *ops)
         if ((int)op.slab_bytes > p->slot_bytes || op.n_slab < 1) { *err = "internal: slab larger than ring slot"; return -1; }
     p->w_blob_bytes = std::max<int64_t>(w_off, 16);
@@ -214,7 +223,8 @@ int pack_step_weights(const QbStepPlan& p, const std::vector<QbOp>& ops, const f
     return 0;
 }
 
-// T_m[k] = e0 + Wcat[:, :De] . e0 + bcat,  e0 = Pin . C_m[k]   (double accumulation, stored fp32, blocked [De/8][K][8])
+// T_m[k] = e0 + Wcat[:, :De] . e0 + bcat,  e0 = Pin . C_m[k]   (double accumulation, stored fp32, blocked [De/4][K][4]:
+// consecutive codes are 16 B apart, so a warp whose lanes hold consecutive codes gathers 512 contiguous bytes)
 void build_tables(int D, int De, int K, const float* codebook, const float* in_proj, const float* concat_w,
                   const float* concat_b, float* t_blk, float* cb_blk, float* wx_t) {
     std::vector<double> e0(De), t(De);
@@ -233,8 +243,8 @@ void build_tables(int D, int De, int K, const float* codebook, const float* in_p
             for (int j = 0; j < De; j++) s += (double)wrow[j] * e0[j];
             t[e] = e0[e] + s;
         }
-        for (int e = 0; e < De; e++) t_blk[((size_t)(e / 8) * K + k) * 8 + (e % 8)] = (float)t[e];
-        for (int d = 0; d < D; d++) cb_blk[((size_t)(d / 8) * K + k) * 8 + (d % 8)] = c[d];
+        for (int e = 0; e < De; e++) t_blk[((size_t)(e / 4) * K + k) * 4 + (e % 4)] = (float)t[e];
+        for (int d = 0; d < D; d++) cb_blk[((size_t)(d / 4) * K + k) * 4 + (d % 4)] = c[d];
     }
     // Wx^T [D][De]: u = Wcat[:, De:] . xhat
     for (int e = 0; e < De; e++)
@@ -252,7 +262,7 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
     qb::PlanOptions opt;
     if (opts5) {
         opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.ctas_per_sm = opts5[1] >> 8; opt.slot_bytes = opts5[2];
-        opt.max_stage = opts5[3]; opt.max_slab_k = opts5[4];
+        opt.max_stage = opts5[3] & 0xff; opt.no_resident = opts5[3] >> 8; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
     std::vector<QbOp> ops;
@@ -260,7 +270,7 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
     if (qb::make_step_plan(D, De, Dh, L, K, qinco1_mode, opt, &p, &ops, &err)) return -1;
     const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_tiles, p.tmem_alloc_cols,
                          p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk, p.oc, p.n_ochunk, p.tmem_e_col, p.tmem_h_col,
-                         p.tmem_tile_cols, p.smem_ae[0], p.smem_ring, p.slot_bytes, p.n_stage, p.smem_total,
+                         p.tmem_tile_cols, p.smem_tres, p.smem_ring, p.slot_bytes, p.n_stage, p.smem_total,
                          (int32_t)p.block_w_bytes, (int32_t)p.w_blob_bytes};
     const int nv = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < nv && i < n_plan_out; i++) plan_out[i] = v[i];
@@ -274,7 +284,7 @@ int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int
     qb::PlanOptions opt;
     if (opts5) {
         opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.ctas_per_sm = opts5[1] >> 8; opt.slot_bytes = opts5[2];
-        opt.max_stage = opts5[3]; opt.max_slab_k = opts5[4];
+        opt.max_stage = opts5[3] & 0xff; opt.no_resident = opts5[3] >> 8; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
     std::vector<QbOp> ops;

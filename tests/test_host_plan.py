@@ -18,7 +18,7 @@ OP_DTYPE = np.dtype([("w_off", "<u4"), ("slab_bytes", "<u4"), ("last_bytes", "<u
                      ("k_total", "<u2"), ("a_off", "<u2"), ("d_col", "<u2"), ("n_slab", "u1"), ("a_src", "u1"),
                      ("accumulate", "u1"), ("wait_a", "u1"), ("wait_d", "u1"), ("commit", "u1"), ("pad", "u1", 4)])
 PLAN_FIELDS = ["D", "De", "Dh", "L", "K", "has_proj", "skip", "n_tiles", "tmem_alloc_cols", "n_ops_block", "n_ops_out",
-               "hc", "n_hchunk", "oc", "n_ochunk", "tmem_e_col", "tmem_h_col", "tmem_tile_cols", "smem_ae", "smem_ring",
+               "hc", "n_hchunk", "oc", "n_ochunk", "tmem_e_col", "tmem_h_col", "tmem_tile_cols", "smem_tres", "smem_ring",
                "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes"]
 A_E, A_H = 0, 1
 BAR_AE_READY, BAR_AH_READY, BAR_HACC_FREE, BAR_HACC_FULL, BAR_EACC_FULL = 1, 2, 3, 4, 5
@@ -102,8 +102,8 @@ def tables(lib, cfg, w, m):
     lib.qb_plan_tables(D, De, K, p(_lib._f32(w[f"steps.{m}.codebook.weight"])), p(inp),
                        p(_lib._f32(w[f"steps.{m}.concat.mlp.weight"])), p(_lib._f32(w[f"steps.{m}.concat.mlp.bias"])),
                        p(t_blk), p(cb_blk), p(wx_t))
-    T = t_blk.reshape(De // 8, K, 8).transpose(1, 0, 2).reshape(K, De)
-    CB = cb_blk.reshape(D // 8, K, 8).transpose(1, 0, 2).reshape(K, D)
+    T = t_blk.reshape(De // 4, K, 4).transpose(1, 0, 2).reshape(K, De)
+    CB = cb_blk.reshape(D // 4, K, 4).transpose(1, 0, 2).reshape(K, D)
     return T, CB, wx_t.reshape(D, De)
 
 
@@ -201,7 +201,6 @@ def test_op_list_replay_matches_oracle(lib, name, opts):
     assert plan["n_stage"] >= 2 and plan["n_tiles"] in (1, 2)
     assert plan["smem_total"] + 4096 <= 227 * 1024
     assert plan["n_tiles"] * plan["tmem_tile_cols"] <= plan["tmem_alloc_cols"] <= 512
-    assert plan["n_tiles"] == 1 or all(int(op["n_slab"]) + 1 <= plan["n_stage"] for op in ops)
     assert plan["tmem_alloc_cols"] & (plan["tmem_alloc_cols"] - 1) == 0
     for op in ops:
         assert op["n"] % 16 == 0 and 16 <= op["n"] <= 256 and op["ks"] % 16 == 0 and op["w_off"] % 16 == 0
