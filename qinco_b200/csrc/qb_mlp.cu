@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     __shared__ __align__(8) uint64_t w_empty[QB_MAX_STAGE];
     __shared__ __align__(8) uint64_t tres_bar;                  // resident table half has landed
     __shared__ __align__(8) uint64_t rows_full[3], rows_empty[3];   // resident mode: per-beam rows (u_b, r_b) of a set, 3 sets deep
-    __shared__ __align__(16) float beam_rows[3][2][256];        // [buffer][tile slot][u_b (De) | r_b (D)]
+    __shared__ __align__(16) float beam_rows[3][2][2][256];     // [buffer][tile slot][beam of the tile][u_b (De) | r_b (D)]
     __shared__ uint32_t tmem_base_s;
     __shared__ float dist_part[2][kColGroups > 1 ? kColGroups - 1 : 1][QB_TILE_M];
 
@@ -324,13 +324,14 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     const int NT = pl.n_tiles;
     const int64_t n_tiles = (p.n_rows + QB_TILE_M - 1) / QB_TILE_M;
     // Work units ("sets" of NT tiles).  Default: NT consecutive tiles, sets strided over the CTAs.  Resident mode (score,
-    // all 256 codes per beam = 2 tiles per beam): CTA parity hh picks the code half, a set is the hh-half of two
-    // consecutive beams, so both tile slots use the same 128 codes whose table rows never leave the SM.
-    const int hh = kResident ? (int)(blockIdx.x & 1) : 0;
+    // all 256 codes per beam): CTA index % 4 picks a code quarter hq; a tile is that quarter (64 codes) of TWO consecutive
+    // beams and a set is 2 such tiles = 4 consecutive beams, so every thread sees the same code for the whole launch and
+    // the quarter's table rows never leave the SM.
+    const int hq = kResident ? (int)(blockIdx.x & 3) : 0;
     const int64_t n_beams = p.n_rows >> 8;
-    const int64_t n_sets = kResident ? (n_beams + 1) / 2 : (n_tiles + NT - 1) / NT;
-    const int64_t set_first = kResident ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
-    const int64_t set_stride = kResident ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+    const int64_t n_sets = kResident ? (n_beams + 3) / 4 : (n_tiles + NT - 1) / NT;
+    const int64_t set_first = kResident ? (int64_t)(blockIdx.x >> 2) : (int64_t)blockIdx.x;
+    const int64_t set_stride = kResident ? (int64_t)(gridDim.x >> 2) : (int64_t)gridDim.x;
 
     // ---- one-time setup ------------------------------------------------------------------------------------------
     if (tid == 0) {
@@ -366,11 +367,14 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     if (warp == kProducerWarp) {
         // ======================================================================================= weight producer
         uint32_t stage = 0, phase = 0;
-        if (kResident) {    // this CTA's half of T_m: De/4 column blocks of 128 codes x 16 B, contiguous 2 KB each in the table
+        if (kResident) {    // this CTA's quarter of T_m and C_m: per 4-column block 64 codes x 16 B = 1 KB, contiguous in the tables
             if (elect_one()) {
-                mbar_expect_tx(smem_u32(&tres_bar), (uint32_t)pl.De * 512u);
+                mbar_expect_tx(smem_u32(&tres_bar), (uint32_t)(pl.De + pl.D) * 256u);
                 for (int c4 = 0; c4 < (pl.De >> 2); c4++)
-                    bulk_g2s(smem_base + pl.smem_tres + c4 * 2048, p.t_blk + ((size_t)c4 * pl.K + hh * 128) * 4, 2048,
+                    bulk_g2s(smem_base + pl.smem_tres + c4 * 1024, p.t_blk + ((size_t)c4 * pl.K + hq * 64) * 4, 1024,
+                             smem_u32(&tres_bar));
+                for (int c4 = 0; c4 < (pl.D >> 2); c4++)
+                    bulk_g2s(smem_base + pl.smem_tres + pl.De * 256 + c4 * 1024, p.cb_blk + ((size_t)c4 * pl.K + hq * 64) * 4, 1024,
                              smem_u32(&tres_bar));
             }
             __syncwarp();
@@ -383,12 +387,12 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             mbar_wait(smem_u32(&rows_empty[b]), (uint32_t)(((k / 3) & 1) ^ 1), p.err_flag, 0x600 + b);
             if (elect_one()) {
                 const uint32_t de_b = (uint32_t)pl.De * 4u, d_b = (uint32_t)pl.D * 4u;
-                mbar_expect_tx(smem_u32(&rows_full[b]), 2u * (de_b + d_b));
-                for (int t = 0; t < 2; t++) {
-                    int64_t beam = 2 * set + t;
+                mbar_expect_tx(smem_u32(&rows_full[b]), 4u * (de_b + d_b));
+                for (int t = 0; t < 4; t++) {       // tile slot t / 2, beam t % 2 of the tile
+                    int64_t beam = 4 * set + t;
                     if (beam >= n_beams) beam = 0;
-                    bulk_g2s(smem_u32(&beam_rows[b][t][0]), p.u + beam * pl.De, de_b, smem_u32(&rows_full[b]));
-                    bulk_g2s(smem_u32(&beam_rows[b][t][pl.De]), p.r + beam * pl.D, d_b, smem_u32(&rows_full[b]));
+                    bulk_g2s(smem_u32(&beam_rows[b][t >> 1][t & 1][0]), p.u + beam * pl.De, de_b, smem_u32(&rows_full[b]));
+                    bulk_g2s(smem_u32(&beam_rows[b][t >> 1][t & 1][pl.De]), p.r + beam * pl.D, d_b, smem_u32(&rows_full[b]));
                 }
             }
             __syncwarp();
@@ -511,19 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         int e0c, e1c, o0c, o1c;             // this thread's columns of e / of the output (no out_proj)
         group_range(De, cg, e0c, e1c);
         group_range(D, cg, o0c, o1c);
-        // resident mode: this thread's slice of the skip codeword of ITS code (the same for every tile it will ever see)
-        float4 creg[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) creg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kResident) {
-            if (pl.skip) {
-                const float* base = p.cb_blk + ((size_t)(o0c >> 2) * K + hh * 128 + r) * 4;
-#pragma unroll
-                for (int i = 0; i < 16; i++)
-                    if (o0c + i * 4 < o1c) creg[i] = ldg4(base + (size_t)i * K * 4);
-            }
-            mbar_wait(smem_u32(&tres_bar), 0, p.err_flag, 0x500);
-        }
+        if (kResident) mbar_wait(smem_u32(&tres_bar), 0, p.err_flag, 0x500);
         int64_t kset = 0;
         for (int64_t set = set_first; set < n_sets; set += set_stride, kset++) {
             const int rb = (int)(kset % 3);
@@ -533,12 +525,11 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             int64_t beam0 = 0, beam1 = 0, row0 = 0, row1 = 0;
             bool valid0 = false, valid1 = false;
             auto row_ctx = [&](int t, int64_t& row, int64_t& beam, int& code, bool& valid) {
-                if (kResident) {            // tile slot t = beam 2*set + t, rows of code half hh; the code never changes
-                    beam = 2 * set + t;
-                    code = hh * 128 + r;
+                if (kResident) {            // tile slot t, rows 0-63 / 64-127 = code quarter hq of beams 4*set + 2t / + 2t + 1
+                    beam = 4 * set + 2 * t + (r >> 6);
+                    code = hq * 64 + (r & 63);
                     row = beam * 256 + code;
                     valid = beam < n_beams;
-                    if (!valid) beam = 0;
                     return;
                 }
                 row = (set * NT + t) * QB_TILE_M + r;
@@ -582,13 +573,13 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     float4 tb[16];
                     const int n = e1c - c;
                     if (kResident) {
-                        const uint32_t ts = smem_base + pl.smem_tres + (uint32_t)r * 16u;
+                        const uint32_t ts = smem_base + pl.smem_tres + (uint32_t)(r & 63) * 16u;
 #pragma unroll
                         for (int j = 0; j < 16; j++)
                             if (j * 4 < n) {
                                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                              : "=f"(tb[j].x), "=f"(tb[j].y), "=f"(tb[j].z), "=f"(tb[j].w)
-                                             : "r"(ts + (uint32_t)((c >> 2) + j) * 2048u));
+                                             : "r"(ts + (uint32_t)((c >> 2) + j) * 1024u));
                             }
                     } else {
                         load_row64(tb, p.t_blk, code, c, n);
@@ -599,8 +590,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                             const int kc = (c >> 3) + j;
                             float4 u0, u1;
                             if (kResident) {
-                                u0 = *reinterpret_cast<const float4*>(&beam_rows[rb][t][kc * 8]);
-                                u1 = *reinterpret_cast<const float4*>(&beam_rows[rb][t][kc * 8 + 4]);
+                                u0 = *reinterpret_cast<const float4*>(&beam_rows[rb][t][r >> 6][kc * 8]);
+                                u1 = *reinterpret_cast<const float4*>(&beam_rows[rb][t][r >> 6][kc * 8 + 4]);
                             } else {
                                 u0 = ldg4(up + kc * 8);
                                 u1 = ldg4(up + kc * 8 + 4);
@@ -655,7 +646,18 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                                     const float4 t4 = kResident ? *reinterpret_cast<const float4*>(src + cc) : ldg4(src + cc);
                                     float o0 = __uint_as_float(v[4 * i]), o1 = __uint_as_float(v[4 * i + 1]), o2 = __uint_as_float(v[4 * i + 2]),
                                           o3 = __uint_as_float(v[4 * i + 3]);
-                                    if (pl.skip) { const float4 cv = cb[hh * 8 + i]; o0 += cv.x; o1 += cv.y; o2 += cv.z; o3 += cv.w; }
+                                    if (pl.skip) {
+                                        float4 cv;
+                                        if (kResident) {
+                                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                                         : "=f"(cv.x), "=f"(cv.y), "=f"(cv.z), "=f"(cv.w)
+                                                         : "r"(smem_base + pl.smem_tres + (uint32_t)pl.De * 256u + (uint32_t)(r & 63) * 16u +
+                                                               (uint32_t)((d0 + cc) >> 2) * 1024u));
+                                        } else {
+                                            cv = cb[hh * 8 + i];
+                                        }
+                                        o0 += cv.x; o1 += cv.y; o2 += cv.z; o3 += cv.w;
+                                    }
                                     if (kScore) {
                                         const float e0 = t4.x - o0, e1 = t4.y - o1, e2 = t4.z - o2, e3 = t4.w - o3;
                                         acc = fmaf(e0, e0, acc); acc = fmaf(e1, e1, acc); acc = fmaf(e2, e2, acc); acc = fmaf(e3, e3, acc);
@@ -722,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     tr.ev(5 + 0x80 * t);
                     float a = 0.f;
                     final_cols(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, o0c, o1c, 0, t ? code1 : code0, t ? beam1 : beam0,
-                               t ? row1 : row0, t ? valid1 : valid0, kResident ? creg : cb, a, &beam_rows[rb][t][De]);
+                               t ? row1 : row0, t ? valid1 : valid0, cb, a, &beam_rows[rb][t][r >> 6][De]);
                     if (t) acc1 = a; else acc0 = a;
                     tc_fence_before();
                     tr.ev(7 + 0x80 * t);
@@ -800,12 +802,12 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
     int64_t n_sets = (n_tiles + p.plan.n_tiles - 1) / p.plan.n_tiles;
     // resident tables: score launches over all 256 codes of every beam (2 tiles per beam), shape qualified by the planner
     const bool resident = p.mode == QB_MODE_SCORE && p.A == 0 && p.C == 256 && p.plan.K == 256 && p.plan.smem_tres >= 0 &&
-                          p.plan.n_tiles == 2 && (p.n_rows & 255) == 0 && n_sm >= 2;
+                          p.plan.n_tiles == 2 && (p.n_rows & 255) == 0 && n_sm >= 4;
     int grid;
     if (resident) {
-        const int64_t sets_per_half = ((p.n_rows >> 8) + 1) / 2;
-        const int64_t per_half = sets_per_half < n_sm / 2 ? sets_per_half : n_sm / 2;
-        grid = (int)(2 * per_half);
+        const int64_t sets = ((p.n_rows >> 8) + 3) / 4;       // per code quarter
+        const int64_t per_quarter = sets < n_sm / 4 ? sets : n_sm / 4;
+        grid = (int)(4 * per_quarter);
     } else {
         grid = (int)(n_sets < n_sm ? n_sets : n_sm);
     }

@@ -107,15 +107,15 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     // ---- shared memory ------------------------------------------------------------------------------------------
     int off = 0;
     for (int t = 0; t < 2; t++) { p->smem_ae[t] = off; if (t < n_tiles) off += ae_bytes; }
-    // Resident tables (score launches with all K = 256 candidates per beam): both tile slots of a CTA then work on the
-    // same half of the codes, whose rows of T_m stay in shared memory (and whose skip codewords stay in registers)
-    // instead of being gathered from L2 for every tile.
+    // Resident tables (score launches with all K = 256 candidates per beam): a CTA then only ever works on ONE quarter of
+    // the codes (64 codes x 2 beams per tile), whose rows of T_m and of the skip codebook stay in shared memory instead
+    // of being gathered from L2 for every tile (the gathers cost as much L2->SM bandwidth as the weights).
     p->smem_tres = -1;
-    if (n_tiles == 2 && !p->has_proj && K == 256 && De * 512 <= 64 * 1024 && budget - off - De * 512 >= 4 * 16384 &&
+    if (n_tiles == 2 && !p->has_proj && K == 256 && (De + D) * 256 <= 64 * 1024 && budget - off - (De + D) * 256 >= 4 * 16384 &&
         opt.no_resident == 0) {
         p->smem_tres = off;
-        off += De * 512;
-        if (opt.slot_bytes <= 0) p->slot_bytes = 16384;      // a deeper ring of smaller slabs fits next to the table
+        off += (De + D) * 256;
+        if (opt.slot_bytes <= 0) p->slot_bytes = 16384;      // a deeper ring of smaller slabs fits next to the tables
     }
     p->smem_ring = off;
     int n_stage = (budget - off) / p->slot_bytes;
