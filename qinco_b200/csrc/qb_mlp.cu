@@ -568,43 +568,45 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 const uint32_t ae_dst = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
                 const float* up = p.u + beam * De;
                 if (!kResident && cg == 0 && r * 32 < De) prefetch_l1(up + r * 32);   // the per-beam row is shared by many rows: pull it into L1
+                auto emit_chunk = [&](int kc, const float4 t0, const float4 t1, const float4 u0, const float4 u1) {
+                    uint32_t e[8];
+                    const float f0 = t0.x + u0.x, f1 = t0.y + u0.y, f2 = t0.z + u0.z, f3 = t0.w + u0.w;
+                    const float f4 = t1.x + u1.x, f5 = t1.y + u1.y, f6 = t1.z + u1.z, f7 = t1.w + u1.w;
+                    e[0] = __float_as_uint(f0); e[1] = __float_as_uint(f1); e[2] = __float_as_uint(f2); e[3] = __float_as_uint(f3);
+                    e[4] = __float_as_uint(f4); e[5] = __float_as_uint(f5); e[6] = __float_as_uint(f6); e[7] = __float_as_uint(f7);
+                    __syncwarp();
+                    tmem_st8(tl + pl.tmem_e_col + kc * 8, e);
+                    st_shared_v4(ae_dst + (uint32_t)kc * kAkcBytes, pack_h2(f0, f1), pack_h2(f2, f3), pack_h2(f4, f5), pack_h2(f6, f7));
+                };
+                if (kResident) {
+                    // everything is in shared memory: no register staging, a small rolled loop (16 columns per iteration)
+                    const uint32_t ts = smem_base + pl.smem_tres + (uint32_t)(r & 63) * 16u;
+                    const float* us = &beam_rows[rb][t][r >> 6][0];
 #pragma unroll 1
-                for (int c = e0c; c < e1c; c += 64) {
-                    float4 tb[16];
-                    const int n = e1c - c;
-                    if (kResident) {
-                        const uint32_t ts = smem_base + pl.smem_tres + (uint32_t)(r & 63) * 16u;
+                    for (int kc = e0c >> 3; kc < (e1c >> 3); kc += 2) {
+                        float4 tv[4];
 #pragma unroll
-                        for (int j = 0; j < 16; j++)
-                            if (j * 4 < n) {
-                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                             : "=f"(tb[j].x), "=f"(tb[j].y), "=f"(tb[j].z), "=f"(tb[j].w)
-                                             : "r"(ts + (uint32_t)((c >> 2) + j) * 1024u));
-                            }
-                    } else {
-                        load_row64(tb, p.t_blk, code, c, n);
+                        for (int j = 0; j < 4; j++)
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(tv[j].x), "=f"(tv[j].y), "=f"(tv[j].z), "=f"(tv[j].w)
+                                         : "r"(ts + (uint32_t)(2 * kc + j) * 1024u));
+                        const float4 u0 = *reinterpret_cast<const float4*>(us + kc * 8), u1 = *reinterpret_cast<const float4*>(us + kc * 8 + 4);
+                        const float4 u2 = *reinterpret_cast<const float4*>(us + kc * 8 + 8), u3 = *reinterpret_cast<const float4*>(us + kc * 8 + 12);
+                        emit_chunk(kc, tv[0], tv[1], u0, u1);
+                        emit_chunk(kc + 1, tv[2], tv[3], u2, u3);
                     }
+                } else {
+#pragma unroll 1
+                    for (int c = e0c; c < e1c; c += 64) {
+                        float4 tb[16];
+                        const int n = e1c - c;
+                        load_row64(tb, p.t_blk, code, c, n);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {       // 8 columns per step
-                        if (j * 8 < n) {
-                            const int kc = (c >> 3) + j;
-                            float4 u0, u1;
-                            if (kResident) {
-                                u0 = *reinterpret_cast<const float4*>(&beam_rows[rb][t][r >> 6][kc * 8]);
-                                u1 = *reinterpret_cast<const float4*>(&beam_rows[rb][t][r >> 6][kc * 8 + 4]);
-                            } else {
-                                u0 = ldg4(up + kc * 8);
-                                u1 = ldg4(up + kc * 8 + 4);
+                        for (int j = 0; j < 8; j++) {       // 8 columns per step
+                            if (j * 8 < n) {
+                                const int kc = (c >> 3) + j;
+                                emit_chunk(kc, tb[2 * j], tb[2 * j + 1], ldg4(up + kc * 8), ldg4(up + kc * 8 + 4));
                             }
-                            const float4 t0 = tb[2 * j], t1 = tb[2 * j + 1];
-                            uint32_t e[8];
-                            const float f0 = t0.x + u0.x, f1 = t0.y + u0.y, f2 = t0.z + u0.z, f3 = t0.w + u0.w;
-                            const float f4 = t1.x + u1.x, f5 = t1.y + u1.y, f6 = t1.z + u1.z, f7 = t1.w + u1.w;
-                            e[0] = __float_as_uint(f0); e[1] = __float_as_uint(f1); e[2] = __float_as_uint(f2); e[3] = __float_as_uint(f3);
-                            e[4] = __float_as_uint(f4); e[5] = __float_as_uint(f5); e[6] = __float_as_uint(f6); e[7] = __float_as_uint(f7);
-                            __syncwarp();
-                            tmem_st8(tl + pl.tmem_e_col + kc * 8, e);
-                            st_shared_v4(ae_dst + (uint32_t)kc * kAkcBytes, pack_h2(f0, f1), pack_h2(f2, f3), pack_h2(f4, f5), pack_h2(f6, f7));
                         }
                     }
                 }
