@@ -551,15 +551,15 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             row_ctx(0, row0, beam0, code0, valid0);
             row_ctx(1, row1, beam1, code1, valid1);
             tr.ev(1);
-            // table row block: columns [c, c + 64) of a [cols/4][K][4] table for `code`, `n` (<= 64, multiple of 16) of them
-            auto load_row64 = [&](float4 (&tb)[16], const float* tbl, int code, int c, int n) {
+            // table row block: columns [c, c + 32) of a [cols/4][K][4] table for `code`, `n` (16 or >= 32) of them.  Kept to
+            // 32 columns (32 registers): anything that spills is re-read from L2, which costs more than a second batch.
+            auto load_row32 = [&](float4 (&tb)[8], const float* tbl, int code, int c, int n) {
                 const float* base = tbl + ((size_t)(c >> 2) * K + code) * 4;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    if (j * 4 < n) {
+                for (int i = 0; i < 4; i++) tb[i] = ldg4(base + (size_t)i * K * 4);
+                if (n > 16) {
 #pragma unroll
-                        for (int i = 0; i < 4; i++) tb[j + i] = ldg4(base + (size_t)(j + i) * K * 4);
-                    }
+                    for (int i = 4; i < 8; i++) tb[i] = ldg4(base + (size_t)i * K * 4);
                 }
             };
             // ---- init: e0 = T_m[code] + u_b over this thread's columns ------------------------------------------------
@@ -597,15 +597,15 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     }
                 } else {
 #pragma unroll 1
-                    for (int c = e0c; c < e1c; c += 64) {
-                        float4 tb[16];
+                    for (int c = e0c; c < e1c; c += 32) {
+                        float4 tb[8];
                         const int n = e1c - c;
-                        load_row64(tb, p.t_blk, code, c, n);
+                        load_row32(tb, p.t_blk, code, c, n);
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {       // 8 columns per step
+                        for (int j = 0; j < 4; j++) {       // 8 columns per step
                             if (j * 8 < n) {
                                 const int kc = (c >> 3) + j;
-                                emit_chunk(kc, tb[2 * j], tb[2 * j + 1], ldg4(up + kc * 8), ldg4(up + kc * 8 + 4));
+                                emit_chunk(kc, tb[2 * j], tb[2 * j + 1], ldg4_jit(up + kc * 8), ldg4_jit(up + kc * 8 + 4));
                             }
                         }
                     }
@@ -627,17 +627,17 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 tc_fence_after();
             };
             // final epilogue of columns [c0, c1) at accumulator address taddr (o[d0 + c0 ..]); cb = skip codeword of the
-            // first 64 columns, fetched by the caller BEFORE it waited for the accumulator
+            // first 32 columns, fetched by the caller BEFORE it waited for the accumulator
             auto final_cols = [&](uint32_t taddr, int c0, int c1, int d0, int code, int64_t beam, int64_t row, bool valid,
-                                  float4 (&cb)[16], float& acc, const float* rows_smem) {
+                                  float4 (&cb)[8], float& acc, const float* rows_smem) {
                 const float* src = kResident ? rows_smem + d0 : (kScore ? p.r : p.xhat_in) + beam * D + d0;
 #pragma unroll 1
-                for (int cb0 = c0; cb0 < c1; cb0 += 64) {
+                for (int cb0 = c0; cb0 < c1; cb0 += 32) {
                     const int n = c1 - cb0;
-                    if (cb0 > c0 && pl.skip) load_row64(cb, p.cb_blk, code, d0 + cb0, n);
-#pragma unroll
-                    for (int hh = 0; hh < 2; hh++) {    // 32 accumulator columns per step
-                        if (hh * 32 < n) {
+                    if (!kResident && cb0 > c0 && pl.skip) load_row32(cb, p.cb_blk, code, d0 + cb0, n);
+                    {
+                        constexpr int hh = 0;           // 32 accumulator columns per step
+                        {
                             uint32_t v[32];
                             tmem_ld_cols(taddr + cb0 + hh * 32, n - hh * 32, v);
                             tmem_wait_ld();
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                             for (int i = 0; i < 8; i++) {
                                 if (hh * 32 + i * 4 < n) {
                                     const int cc = cb0 + hh * 32 + i * 4;
-                                    const float4 t4 = kResident ? *reinterpret_cast<const float4*>(src + cc) : ldg4(src + cc);
+                                    const float4 t4 = kResident ? *reinterpret_cast<const float4*>(src + cc) : ldg4_jit(src + cc);
                                     float o0 = __uint_as_float(v[4 * i]), o1 = __uint_as_float(v[4 * i + 1]), o2 = __uint_as_float(v[4 * i + 2]),
                                           o3 = __uint_as_float(v[4 * i + 3]);
                                     if (pl.skip) {
@@ -716,12 +716,12 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             if (!pl.has_proj) {
 #pragma unroll 1
                 for (int t = 0; t < NT; t++) {
-                    float4 cb[16];
+                    float4 cb[8];
 #pragma unroll
-                    for (int i = 0; i < 16; i++) cb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < 8; i++) cb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     // inputs of the final epilogue travel while the last down-projection runs
                     if (!kResident && cg == 0 && r * 32 < D) prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
-                    if (!kResident && pl.skip && o0c < o1c) load_row64(cb, p.cb_blk, t ? code1 : code0, o0c, o1c - o0c);
+                    if (!kResident && pl.skip && o0c < o1c) load_row32(cb, p.cb_blk, t ? code1 : code0, o0c, o1c - o0c);
                     if (pl.L > 0) wait_bar(t, QB_BAR_EACC_FULL, 0x405);
                     tr.ev(5 + 0x80 * t);
                     float a = 0.f;
@@ -740,10 +740,10 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     group_range(cw, cg, c0, c1);
 #pragma unroll 1
                     for (int t = 0; t < NT; t++) {
-                        float4 cb[16];
+                        float4 cb[8];
 #pragma unroll
-                        for (int i = 0; i < 16; i++) cb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (pl.skip && c0 < c1) load_row64(cb, p.cb_blk, t ? code1 : code0, qq * pl.oc + c0, c1 - c0);
+                        for (int i = 0; i < 8; i++) cb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (pl.skip && c0 < c1) load_row32(cb, p.cb_blk, t ? code1 : code0, qq * pl.oc + c0, c1 - c0);
                         if (qq == 0 && cg == 0 && r * 32 < D) prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
                         wait_bar(t, QB_BAR_HACC_FULL, 0x414);
                         const uint32_t ta = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
