@@ -41,6 +41,7 @@ struct MlpParams {
     float out_scale;          // apply
     const float* out_shift;   // apply: [D] or NULL
     uint32_t* err_flag;       // device word set non-zero when a barrier wait timed out
+    int32_t exp;              // debug: experiment bits from the QB_EXP environment variable (0 in production)
     unsigned long long* trace;   // debug: per-role event log of CTA 0 ([3][QB_TRACE_EVENTS] of clock<<16 | id), or NULL
 };
 

@@ -41,7 +41,10 @@ namespace {
 constexpr int kEpiWarps = 8;              // two warps per TMEM lane quarter: warp w owns lanes 32*(w%4).., column group w/4
 constexpr int kColGroups = kEpiWarps / 4;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = kEpiThreads + 96;   // + producer warp + one MMA warp per tile slot
+constexpr int kThreads = kEpiThreads + 128;  // + one warpgroup: producer warp, one MMA warp per tile slot, one idle warp
+// Registers are a per-scheduler pool (16 K per SM sub-partition = 3 warps x 168 at launch).  The service warpgroup
+// hands most of its share back (setmaxnreg.dec) and the epilogue warpgroups take it (setmaxnreg.inc): 2 x 216 + 56 <= 512.
+constexpr int kEpiRegs = 216, kSvcRegs = 56;
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;   // MMA warps: kMmaWarp + tile slot
 constexpr int kAkcBytes = QB_TILE_M * 16;   // bytes of one 8-element k-chunk of an A operand tile
 
@@ -179,6 +182,21 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         QB_W8(v, 0), QB_W8(v, 8)
         : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        QB_W8(v, 0), QB_W8(v, 8), QB_W8(v, 16), QB_W8(v, 24)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16p(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        QB_W8(v, 0), QB_W8(v, 8)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
                  "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -273,19 +291,30 @@ __device__ __forceinline__ void acc_to_tmem_operand(uint32_t taddr, int c0, int 
     if (n > 32) tmem_ld_cols(taddr + c0 + 32, n - 32, vb);
     tmem_wait_ld();
     named_bar_sync(quarter_bar, kColGroups * 32);
-    if (n > 0) {
-        uint32_t w[16];
+    if (n >= 64) {          // common case: one 32-column store of the 64 packed values
+        uint32_t w[32];
 #pragma unroll
-        for (int j = 0; j < 16; j++) w[j] = pack_h2_relu(__uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
+        for (int j = 0; j < 16; j++) {
+            w[j] = pack_h2_relu(__uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
+            w[16 + j] = pack_h2_relu(__uint_as_float(vb[2 * j]), __uint_as_float(vb[2 * j + 1]));
+        }
         __syncwarp();
-        if (n >= 32) tmem_st16(taddr + (c0 >> 1), w); else tmem_st8(taddr + (c0 >> 1), w);
-    }
-    if (n > 32) {
-        uint32_t w[16];
+        tmem_st32(taddr + (c0 >> 1), w);
+    } else {
+        if (n > 0) {
+            uint32_t w[16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) w[j] = pack_h2_relu(__uint_as_float(vb[2 * j]), __uint_as_float(vb[2 * j + 1]));
-        __syncwarp();
-        if (n >= 64) tmem_st16(taddr + ((c0 + 32) >> 1), w); else tmem_st8(taddr + ((c0 + 32) >> 1), w);
+            for (int j = 0; j < 16; j++) w[j] = pack_h2_relu(__uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
+            __syncwarp();
+            if (n >= 32) tmem_st16(taddr + (c0 >> 1), w); else tmem_st8(taddr + (c0 >> 1), w);
+        }
+        if (n > 32) {
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) w[j] = pack_h2_relu(__uint_as_float(vb[2 * j]), __uint_as_float(vb[2 * j + 1]));
+            __syncwarp();
+            tmem_st8(taddr + ((c0 + 32) >> 1), w);
+        }
     }
     tmem_wait_st();
 }
@@ -364,6 +393,9 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     const uint32_t smem_base = smem_u32(dyn_smem);
     const uint32_t tile_cols = (uint32_t)pl.tmem_tile_cols;
 
+    // (unconditional on purpose: ptxas only budgets registers per region when every path executes the setmaxnreg)
+    if (warp >= kEpiWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSvcRegs));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     if (warp == kProducerWarp) {
         // ======================================================================================= weight producer
         uint32_t stage = 0, phase = 0;
@@ -499,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 }
             }
         }
-    } else {
+    } else if (warp < kEpiWarps) {
         // ======================================================================================= epilogue warps
         // Thread (lane quarter q = warp % 4, lane) owns row r = 32 q + lane of BOTH tiles in flight and alternates
         // between them; the kColGroups warps of a lane quarter split every column range (cg = warp / 4).  Table rows
@@ -568,48 +600,49 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 const uint32_t ae_dst = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
                 const float* up = p.u + beam * De;
                 if (!kResident && cg == 0 && r * 32 < De) prefetch_l1(up + r * 32);   // the per-beam row is shared by many rows: pull it into L1
-                auto emit_chunk = [&](int kc, const float4 t0, const float4 t1, const float4 u0, const float4 u1) {
-                    uint32_t e[8];
-                    const float f0 = t0.x + u0.x, f1 = t0.y + u0.y, f2 = t0.z + u0.z, f3 = t0.w + u0.w;
-                    const float f4 = t1.x + u1.x, f5 = t1.y + u1.y, f6 = t1.z + u1.z, f7 = t1.w + u1.w;
-                    e[0] = __float_as_uint(f0); e[1] = __float_as_uint(f1); e[2] = __float_as_uint(f2); e[3] = __float_as_uint(f3);
-                    e[4] = __float_as_uint(f4); e[5] = __float_as_uint(f5); e[6] = __float_as_uint(f6); e[7] = __float_as_uint(f7);
-                    __syncwarp();
-                    tmem_st8(tl + pl.tmem_e_col + kc * 8, e);
-                    st_shared_v4(ae_dst + (uint32_t)kc * kAkcBytes, pack_h2(f0, f1), pack_h2(f2, f3), pack_h2(f4, f5), pack_h2(f6, f7));
-                };
-                if (kResident) {
-                    // everything is in shared memory: no register staging, a small rolled loop (16 columns per iteration)
-                    const uint32_t ts = smem_base + pl.smem_tres + (uint32_t)(r & 63) * 16u;
-                    const float* us = &beam_rows[rb][t][r >> 6][0];
+                // 32 columns per iteration: all 16 operand loads are issued before the first use, one wide TMEM store
+                const float4* ts4 = reinterpret_cast<const float4*>(dyn_smem + pl.smem_tres) + (r & 63);   // resident: [col/4][64][4]
+                const float4* us4 = reinterpret_cast<const float4*>(&beam_rows[rb][t][r >> 6][0]);
 #pragma unroll 1
-                    for (int kc = e0c >> 3; kc < (e1c >> 3); kc += 2) {
-                        float4 tv[4];
+                for (int c = e0c; c < e1c; c += 32) {
+                    const int n = e1c - c;          // 16 or >= 32
+                    uint32_t e[32];
+                    auto half16 = [&](int h) {      // columns c + 16 h .. + 16: 8 operand loads in flight, then the sums
+                        float4 tb[4], ub[4];
+                        if (kResident) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                         : "=f"(tv[j].x), "=f"(tv[j].y), "=f"(tv[j].z), "=f"(tv[j].w)
-                                         : "r"(ts + (uint32_t)(2 * kc + j) * 1024u));
-                        const float4 u0 = *reinterpret_cast<const float4*>(us + kc * 8), u1 = *reinterpret_cast<const float4*>(us + kc * 8 + 4);
-                        const float4 u2 = *reinterpret_cast<const float4*>(us + kc * 8 + 8), u3 = *reinterpret_cast<const float4*>(us + kc * 8 + 12);
-                        emit_chunk(kc, tv[0], tv[1], u0, u1);
-                        emit_chunk(kc + 1, tv[2], tv[3], u2, u3);
-                    }
-                } else {
-#pragma unroll 1
-                    for (int c = e0c; c < e1c; c += 32) {
-                        float4 tb[8];
-                        const int n = e1c - c;
-                        load_row32(tb, p.t_blk, code, c, n);
+                            for (int i = 0; i < 4; i++) { tb[i] = ts4[((c >> 2) + 4 * h + i) * 64]; ub[i] = us4[(c >> 2) + 4 * h + i]; }
+                        } else {
+                            const float* base = p.t_blk + ((size_t)((c >> 2) + 4 * h) * K + code) * 4;
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {       // 8 columns per step
-                            if (j * 8 < n) {
-                                const int kc = (c >> 3) + j;
-                                emit_chunk(kc, tb[2 * j], tb[2 * j + 1], ldg4_jit(up + kc * 8), ldg4_jit(up + kc * 8 + 4));
-                            }
+                            for (int i = 0; i < 4; i++) { tb[i] = ldg4(base + (size_t)i * K * 4); ub[i] = ldg4(up + c + 16 * h + 4 * i); }
                         }
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            e[16 * h + 4 * i + 0] = __float_as_uint(tb[i].x + ub[i].x); e[16 * h + 4 * i + 1] = __float_as_uint(tb[i].y + ub[i].y);
+                            e[16 * h + 4 * i + 2] = __float_as_uint(tb[i].z + ub[i].z); e[16 * h + 4 * i + 3] = __float_as_uint(tb[i].w + ub[i].w);
+                        }
+                    };
+                    auto to_smem = [&](int j) {     // 8 columns -> one fp16 k-chunk row of A_E
+                        st_shared_v4(ae_dst + (uint32_t)((c >> 3) + j) * kAkcBytes,
+                                     pack_h2(__uint_as_float(e[8 * j]), __uint_as_float(e[8 * j + 1])),
+                                     pack_h2(__uint_as_float(e[8 * j + 2]), __uint_as_float(e[8 * j + 3])),
+                                     pack_h2(__uint_as_float(e[8 * j + 4]), __uint_as_float(e[8 * j + 5])),
+                                     pack_h2(__uint_as_float(e[8 * j + 6]), __uint_as_float(e[8 * j + 7])));
+                    };
+                    half16(0);
+                    if (n > 16) {
+                        half16(1);
+                        __syncwarp();
+                        tmem_st32(tl + pl.tmem_e_col + c, e);
+                        to_smem(0); to_smem(1); to_smem(2); to_smem(3);
+                    } else {
+                        __syncwarp();
+                        tmem_st16p(tl + pl.tmem_e_col + c, e);
+                        to_smem(0); to_smem(1);
                     }
                 }
+                tr.ev(14);
                 tmem_wait_st();
                 tc_fence_before();
                 proxy_fence_async();
@@ -631,55 +664,56 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             auto final_cols = [&](uint32_t taddr, int c0, int c1, int d0, int code, int64_t beam, int64_t row, bool valid,
                                   float4 (&cb)[8], float& acc, const float* rows_smem) {
                 const float* src = kResident ? rows_smem + d0 : (kScore ? p.r : p.xhat_in) + beam * D + d0;
+                const float4* cs4 = reinterpret_cast<const float4*>(dyn_smem + pl.smem_tres + pl.De * 256) + (r & 63);   // resident C_m quarter
+                const bool skip = pl.skip != 0;
+                float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;       // four independent accumulation chains
 #pragma unroll 1
                 for (int cb0 = c0; cb0 < c1; cb0 += 32) {
-                    const int n = c1 - cb0;
-                    if (!kResident && cb0 > c0 && pl.skip) load_row32(cb, p.cb_blk, code, d0 + cb0, n);
-                    {
-                        constexpr int hh = 0;           // 32 accumulator columns per step
-                        {
-                            uint32_t v[32];
-                            tmem_ld_cols(taddr + cb0 + hh * 32, n - hh * 32, v);
-                            tmem_wait_ld();
+                    const int n = c1 - cb0;                          // 16 or >= 32
+                    uint32_t v[32];
+                    tr.ev(12);
+                    tmem_ld_cols(taddr + cb0, n, v);
+                    if (!kResident && cb0 > c0 && skip) load_row32(cb, p.cb_blk, code, d0 + cb0, n);
+                    auto half16 = [&](int h, bool waited) {
+                        float4 tv[4], cv[4];
 #pragma unroll
-                            for (int i = 0; i < 8; i++) {
-                                if (hh * 32 + i * 4 < n) {
-                                    const int cc = cb0 + hh * 32 + i * 4;
-                                    const float4 t4 = kResident ? *reinterpret_cast<const float4*>(src + cc) : ldg4_jit(src + cc);
-                                    float o0 = __uint_as_float(v[4 * i]), o1 = __uint_as_float(v[4 * i + 1]), o2 = __uint_as_float(v[4 * i + 2]),
-                                          o3 = __uint_as_float(v[4 * i + 3]);
-                                    if (pl.skip) {
-                                        float4 cv;
-                                        if (kResident) {
-                                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                                         : "=f"(cv.x), "=f"(cv.y), "=f"(cv.z), "=f"(cv.w)
-                                                         : "r"(smem_base + pl.smem_tres + (uint32_t)pl.De * 256u + (uint32_t)(r & 63) * 16u +
-                                                               (uint32_t)((d0 + cc) >> 2) * 1024u));
-                                        } else {
-                                            cv = cb[hh * 8 + i];
-                                        }
-                                        o0 += cv.x; o1 += cv.y; o2 += cv.z; o3 += cv.w;
-                                    }
-                                    if (kScore) {
-                                        const float e0 = t4.x - o0, e1 = t4.y - o1, e2 = t4.z - o2, e3 = t4.w - o3;
-                                        acc = fmaf(e0, e0, acc); acc = fmaf(e1, e1, acc); acc = fmaf(e2, e2, acc); acc = fmaf(e3, e3, acc);
-                                    } else if (valid) {
-                                        const int d = d0 + cc;
-                                        float4 out = make_float4(t4.x + o0, t4.y + o1, t4.z + o2, t4.w + o3);
-                                        if (p.out_shift) {
-                                            const float4 sh = ldg4(p.out_shift + d);
-                                            out.x = fmaf(out.x, p.out_scale, sh.x); out.y = fmaf(out.y, p.out_scale, sh.y);
-                                            out.z = fmaf(out.z, p.out_scale, sh.z); out.w = fmaf(out.w, p.out_scale, sh.w);
-                                        } else if (p.out_scale != 1.0f) {
-                                            out.x *= p.out_scale; out.y *= p.out_scale; out.z *= p.out_scale; out.w *= p.out_scale;
-                                        }
-                                        *reinterpret_cast<float4*>(p.xhat_out + row * D + d) = out;
-                                    }
-                                }
+                        for (int i = 0; i < 4; i++) {
+                            const int cc = cb0 + 16 * h + 4 * i;
+                            if (kResident) {
+                                tv[i] = *reinterpret_cast<const float4*>(src + cc);
+                                cv[i] = skip ? cs4[((d0 + cc) >> 2) * 64] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            } else {
+                                tv[i] = ldg4(src + cc);
+                                cv[i] = cb[4 * h + i];          // all zero when the model has no outer skip
                             }
                         }
-                    }
+                        if (!waited) { tmem_wait_ld(); tr.ev(13); }
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int vi = 16 * h + 4 * i;
+                            const float o0 = __uint_as_float(v[vi]) + cv[i].x, o1 = __uint_as_float(v[vi + 1]) + cv[i].y;
+                            const float o2 = __uint_as_float(v[vi + 2]) + cv[i].z, o3 = __uint_as_float(v[vi + 3]) + cv[i].w;
+                            if (kScore) {
+                                const float e0 = tv[i].x - o0, e1 = tv[i].y - o1, e2 = tv[i].z - o2, e3 = tv[i].w - o3;
+                                ax = fmaf(e0, e0, ax); ay = fmaf(e1, e1, ay); az = fmaf(e2, e2, az); aw = fmaf(e3, e3, aw);
+                            } else if (valid) {
+                                const int d = d0 + cb0 + 16 * h + 4 * i;
+                                float4 out = make_float4(tv[i].x + o0, tv[i].y + o1, tv[i].z + o2, tv[i].w + o3);
+                                if (p.out_shift) {
+                                    const float4 sh = ldg4(p.out_shift + d);
+                                    out.x = fmaf(out.x, p.out_scale, sh.x); out.y = fmaf(out.y, p.out_scale, sh.y);
+                                    out.z = fmaf(out.z, p.out_scale, sh.z); out.w = fmaf(out.w, p.out_scale, sh.w);
+                                } else if (p.out_scale != 1.0f) {
+                                    out.x *= p.out_scale; out.y *= p.out_scale; out.z *= p.out_scale; out.w *= p.out_scale;
+                                }
+                                *reinterpret_cast<float4*>(p.xhat_out + row * D + d) = out;
+                            }
+                        }
+                    };
+                    half16(0, false);
+                    if (n > 16) half16(1, true);
                 }
+                if (kScore) acc += (ax + ay) + (az + aw);
             };
 #pragma unroll 1
             for (int l = 0; l < pl.L; l++) {
@@ -813,7 +847,10 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
     } else {
         grid = (int)(n_sets < n_sm ? n_sets : n_sm);
     }
-    auto launch = [&](const MlpParams& q) {
+    static const int exp_bits = getenv("QB_EXP") ? atoi(getenv("QB_EXP")) : 0;
+    auto launch = [&](const MlpParams& q0) {
+        MlpParams q = q0;
+        q.exp = exp_bits;
         if (resident) qb_mlp_kernel<true, true><<<grid, kThreads, q.plan.smem_total, stream>>>(q);
         else if (q.mode == QB_MODE_SCORE) qb_mlp_kernel<true, false><<<grid, kThreads, q.plan.smem_total, stream>>>(q);
         else qb_mlp_kernel<false, false><<<grid, kThreads, q.plan.smem_total, stream>>>(q);

@@ -10,7 +10,7 @@ for line in open(sys.argv[1]):
 t0 = min(e[0][0] for e in ev.values() if e)
 names = {1: "init start", 2: "init done (AE_READY)", 3: "HACC_FULL seen", 4: "H-epi done (AH_READY)", 5: "EACC_FULL seen", 6: "E-epi done (AE_READY)", 8: "tile done"}
 allev = []
-names[7] = "final done"; names[9] = "pre-wait start"; names[10] = "prefetch issued"; names[11] = "cb loads issued"
+names[7] = "final done"; names[9] = "pre-wait start"; names[10] = "prefetch issued"; names[11] = "cb loads issued"; names[12] = "final: ld issue"; names[13] = "final: ld landed"; names[14] = "init: stores issued"
 for t, i in ev[0]: allev.append((t - t0, "EPI ", ("Y " if i & 0x80 else "X ") + names.get(i & 0x7f, hex(i))))
 for t, i in ev[1]:
     kind = {0x200: "ops ready, wait slab", 0x300: "slab ready, issue", 0x400: "issued"}[i & 0xf00]
