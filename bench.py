@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="vectors per GPU per step (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--plan-opts", default="", help="kernel planner overrides, e.g. slot_bytes=8192,ctas=1,hc=64,max_stage=4")
+    ap.add_argument("--plan-opts", default="", help="kernel planner overrides, e.g. slot_bytes=8192,pair=1,hc=64,max_stage=4 (pair: 0 auto, 1 off, 2 on)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -207,7 +207,7 @@ def main():
     if args.plan_opts:
         kv = dict(t.split("=") for t in args.plan_opts.split(","))
         plan_opts = {k: int(v) for k, v in kv.items() if k in ("hc", "slot_bytes", "max_stage", "max_slab_k", "stagger")}
-        plan_opts["n_tiles"] = int(kv.get("n_tiles", 0)) | (int(kv.get("ctas", 0)) << 8)
+        plan_opts["n_tiles"] = int(kv.get("n_tiles", 0)) | (int(kv.get("pair", 0)) << 8)
     model = QINCo(cfg, w, device=dev, plan_opts=plan_opts)
     h = model._h
     x_pin = x_host.pin_memory()

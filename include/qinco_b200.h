@@ -58,7 +58,7 @@ typedef struct {
     const float* const* out_proj;          /* [M] or NULL when De == D */
     const float* data_mean;                /* [D] or NULL (zeros) */
     float data_std;                        /* > 0 */
-    /* kernel planner overrides, 0 = automatic; opt_n_tiles = n_tiles | ctas_per_sm << 8 */
+    /* kernel planner overrides, 0 = automatic; opt_n_tiles = n_tiles | pair << 8 (pair: 0 auto, 1 off, 2 on) */
     int32_t opt_hc, opt_n_tiles, opt_slot_bytes, opt_max_stage, opt_max_slab_k;
     int32_t opt_stagger;     /* start delay (cycles) of the second CTA per SM; 0 = automatic, < 0 = none */
 } qb_model_desc;

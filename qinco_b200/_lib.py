@@ -111,7 +111,7 @@ class _PtrArray:
 
 INFO_FIELDS = ["D", "De", "Dh", "L", "K", "has_proj", "skip", "n_ops_block", "n_ops_out", "hc", "n_hchunk", "n_tiles",
                "oc", "n_ochunk", "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes", "n_sm",
-               "default_chunk"]
+               "default_chunk", "pair"]
 
 
 class Handle:

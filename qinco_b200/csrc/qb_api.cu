@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -421,8 +422,10 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         (void)mma;
     }
     qb::PlanOptions opt;
-    opt.hc = d->opt_hc; opt.n_tiles = d->opt_n_tiles & 0xff; opt.ctas_per_sm = d->opt_n_tiles >> 8;
+    opt.hc = d->opt_hc; opt.n_tiles = d->opt_n_tiles & 0xff; opt.pair = d->opt_n_tiles >> 8;
     opt.slot_bytes = d->opt_slot_bytes;
+    if (opt.pair == 0)
+        if (const char* e = getenv("QB_PAIR")) opt.pair = atoi(e);   // debug / A-B runs: 1 = single-CTA kernel, 2 = force pairs
     opt.max_stage = d->opt_max_stage & 0xff; opt.no_resident = d->opt_max_stage >> 8; opt.max_slab_k = d->opt_max_slab_k;
     int max_smem = 0;
     for (int s = 1; s < m->M; s++) {
@@ -651,7 +654,7 @@ int qb_model_info(const qb_model* m, int step, int32_t* out, int n_out) {
     const QbStepPlan& p = m->steps[step].plan;
     const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk,
                          p.n_tiles, p.oc, p.n_ochunk, p.slot_bytes, p.n_stage, p.smem_total, (int32_t)p.block_w_bytes,
-                         (int32_t)p.w_blob_bytes, m->n_sm, (int32_t)default_chunk(m)};
+                         (int32_t)p.w_blob_bytes, m->n_sm, (int32_t)default_chunk(m), p.pair};
     const int nv = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < n_out && i < nv; i++) out[i] = v[i];
     return nv;

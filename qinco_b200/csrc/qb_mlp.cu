@@ -47,6 +47,7 @@ constexpr int kThreads = kEpiThreads + 128;  // + one warpgroup: producer warp, 
 constexpr int kEpiRegs = 216, kSvcRegs = 56;
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;   // MMA warps: kMmaWarp + tile slot
 constexpr int kAkcBytes = QB_TILE_M * 16;   // bytes of one 8-element k-chunk of an A operand tile
+constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);   // high word of every UMMA smem descriptor here: SBO = 128 B, version 1
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,6 +81,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ uint64_t globaltimer() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -95,6 +107,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
             const uint64_t now = globaltimer();
             if (t0 == 0) t0 = now;
             if (now - t0 > 4000000000ull) {          // 4 s
+                if (err_flag) atomicExch(err_flag, code);
+                __threadfence_system();
+                __trap();
+            }
+        }
+    }
+}
+
+// Busy-polling wait (mbarrier.test_wait never suspends the thread): for the single-warp roles whose wake-up latency is on
+// the critical path.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, uint32_t* err_flag, uint32_t code) {
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (!mbar_test_wait(bar, parity)) {
+        if ((++spins & 0xffffu) == 0) {
+            const uint64_t now = globaltimer();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 4000000000ull) {
                 if (err_flag) atomicExch(err_flag, code);
                 __threadfence_system();
                 __trap();
@@ -142,6 +172,110 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
         : "memory");
 }
 
+// ---- CTA pair (cta_group::2): one M=256 MMA spans the two CTAs of a cluster; each CTA holds its own 128 rows of A and
+// of the accumulator and HALF of the B rows (weights), so weight traffic and weight shared-memory reads per SM halve.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void proxy_fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// commit of a cta_group::2 MMA group: the arrival is multicast to the barrier at the same offset in both CTAs
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_ss_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        :
+        : "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// One K=16 MMA whose operand descriptors advance in place (low descriptor word += step; the address field never carries
+// into the LBO field).  Written so that ptxas keeps everything in uniform registers: 5 instructions per MMA when
+// unrolled.  kPairI selects cta_group::2.
+template <bool kPairI>
+__device__ __forceinline__ void mma_ss_step(uint32_t d, uint32_t& alo, uint32_t& blo, uint32_t ahi, uint32_t bhi, uint32_t idesc,
+                                            uint32_t acc, uint32_t as, uint32_t bs) {
+    if (kPairI)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+                     "mov.b64 da, {%0, %3};\n\tmov.b64 db, {%1, %4};\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%2], da, db, %5, p;\n\t"
+                     "add.u32 %0, %0, %7;\n\tadd.u32 %1, %1, %8;\n\t}"
+                     : "+r"(alo), "+r"(blo) : "r"(d), "r"(ahi), "r"(bhi), "r"(idesc), "r"(acc), "r"(as), "r"(bs) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+                     "mov.b64 da, {%0, %3};\n\tmov.b64 db, {%1, %4};\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%2], da, db, %5, p;\n\t"
+                     "add.u32 %0, %0, %7;\n\tadd.u32 %1, %1, %8;\n\t}"
+                     : "+r"(alo), "+r"(blo) : "r"(d), "r"(ahi), "r"(bhi), "r"(idesc), "r"(acc), "r"(as), "r"(bs) : "memory");
+}
+// same with the A operand in TMEM (column address += 8 per K=16)
+template <bool kPairI>
+__device__ __forceinline__ void mma_ts_step(uint32_t d, uint32_t& a_tmem, uint32_t& blo, uint32_t bhi, uint32_t idesc, uint32_t acc,
+                                            uint32_t bs) {
+    if (kPairI)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                     "mov.b64 db, {%1, %3};\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%2], [%0], db, %4, p;\n\t"
+                     "add.u32 %0, %0, 8;\n\tadd.u32 %1, %1, %6;\n\t}"
+                     : "+r"(a_tmem), "+r"(blo) : "r"(d), "r"(bhi), "r"(idesc), "r"(acc), "r"(bs) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                     "mov.b64 db, {%1, %3};\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%2], [%0], db, %4, p;\n\t"
+                     "add.u32 %0, %0, 8;\n\tadd.u32 %1, %1, %6;\n\t}"
+                     : "+r"(a_tmem), "+r"(blo) : "r"(d), "r"(bhi), "r"(idesc), "r"(acc), "r"(bs) : "memory");
+}
+// nk MMAs of one slab; the common slab depths are fully unrolled
+template <bool kPairI, bool kFromSmem>
+__device__ __forceinline__ void mma_slab(int nk, uint32_t d, uint32_t& a, uint32_t& blo, uint32_t ahi, uint32_t bhi, uint32_t idesc,
+                                         uint32_t acc, uint32_t as, uint32_t bs) {
+    auto one = [&](uint32_t ac) {
+        if (kFromSmem) mma_ss_step<kPairI>(d, a, blo, ahi, bhi, idesc, ac, as, bs);
+        else mma_ts_step<kPairI>(d, a, blo, bhi, idesc, ac, bs);
+    };
+    one(acc);
+    if (nk == 8) {
+#pragma unroll
+        for (int k = 1; k < 8; k++) one(1u);
+    } else if (nk == 4) {
+#pragma unroll
+        for (int k = 1; k < 4; k++) one(1u);
+    } else {
+#pragma unroll 1
+        for (int k = 1; k < nk; k++) one(1u);
+    }
+}
+
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE ("interleave") canonical layout
 //   ((8,m),(8,2)) : ((16 B, SBO), (2 B, LBO))      (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::K>)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -152,8 +286,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;                 // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
 }
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
-__device__ __forceinline__ uint32_t umma_idesc(uint32_t n) {
-    return (1u << 4) | ((n >> 3) << 17) | ((uint32_t)(QB_TILE_M >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc(uint32_t n, uint32_t m = QB_TILE_M) {
+    return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 #define QB_R8(v, o) "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
@@ -214,6 +348,19 @@ __device__ __forceinline__ uint32_t pack_h2_relu(float a, float b) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// explicit shared-space load (32-bit shared address): a C++ pointer to shared memory goes through a generic address,
+// which the compiler rebuilds from a slow special-register read (see `opaque` in the kernel)
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds1(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 // same load, but pinned in program order (asm volatile): for operands that should be fetched just in time from L1
 // instead of being hoisted by the compiler into a long-lived register block
@@ -323,18 +470,22 @@ __device__ __forceinline__ void acc_to_tmem_operand(uint32_t taddr, int c0, int 
 struct Tracer {
     unsigned long long* buf;
     int n;
+    bool writer;
     __device__ __forceinline__ void init(const MlpParams& p, int role, bool active) {
-        buf = (p.trace && blockIdx.x == 0 && active) ? p.trace + role * QB_TRACE_EVENTS : nullptr;
+        buf = (p.trace && blockIdx.x == 0) ? p.trace + role * QB_TRACE_EVENTS : nullptr;    // warp-uniform: off = one uniform branch
+        writer = active;
         n = 0;
     }
     __device__ __forceinline__ void ev(uint32_t id) {
-        if (buf && n < QB_TRACE_EVENTS) buf[n++] = ((unsigned long long)clock64() << 16) | id;
+        if (buf) {
+            if (writer && n < QB_TRACE_EVENTS) buf[n++] = ((unsigned long long)clock64() << 16) | id;
+        }
     }
 };
 
 }  // namespace
 
-template <bool kScore, bool kResident>
+template <bool kScore, bool kResident, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_constant__ MlpParams p) {
     extern __shared__ __align__(1024) uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t bars[2][QB_BAR_COUNT];     // one barrier set per tile slot
@@ -361,36 +512,62 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     const int64_t n_sets = kResident ? (n_beams + 3) / 4 : (n_tiles + NT - 1) / NT;
     const int64_t set_first = kResident ? (int64_t)(blockIdx.x >> 2) : (int64_t)blockIdx.x;
     const int64_t set_stride = kResident ? (int64_t)(gridDim.x >> 2) : (int64_t)gridDim.x;
+    // CTA pair: both CTAs walk the same number of sets (they share every MMA).  Resident mode gives both the same set
+    // indices (adjacent code quarters); otherwise the peer's set is the leader's + 1 and may be past the end (all rows
+    // invalid: it computes on row 0's operands and writes nothing).
+    const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int64_t set_lead_off = (kPair && !kResident) ? (int64_t)cta_rank : 0;
+    auto more_sets = [&](int64_t set) { return set - set_lead_off < n_sets; };
 
     // ---- one-time setup ------------------------------------------------------------------------------------------
     if (tid == 0) {
         for (int t = 0; t < 2; t++) {
             mbar_init(smem_u32(&bars[t][QB_BAR_NONE]), 1);
-            mbar_init(smem_u32(&bars[t][QB_BAR_AE_READY]), kEpiThreads);
-            mbar_init(smem_u32(&bars[t][QB_BAR_AH_READY]), kEpiThreads);
-            mbar_init(smem_u32(&bars[t][QB_BAR_HACC_FREE]), kEpiThreads);
+            // epilogue -> MMA issuer: one elected arrival per epilogue warp, from both CTAs of a pair (the issuer lives
+            // in the leader CTA)
+            mbar_init(smem_u32(&bars[t][QB_BAR_AE_READY]), (kPair ? 2 : 1) * kEpiWarps);
+            mbar_init(smem_u32(&bars[t][QB_BAR_AH_READY]), (kPair ? 2 : 1) * kEpiWarps);
+            mbar_init(smem_u32(&bars[t][QB_BAR_HACC_FREE]), (kPair ? 2 : 1) * kEpiWarps);
             mbar_init(smem_u32(&bars[t][QB_BAR_HACC_FULL]), 1);
             mbar_init(smem_u32(&bars[t][QB_BAR_EACC_FULL]), 1);
         }
         mbar_init(smem_u32(&tres_bar), 1);
         for (int b = 0; b < 3; b++) { mbar_init(smem_u32(&rows_full[b]), 1); mbar_init(smem_u32(&rows_empty[b]), kEpiThreads); }
         for (int s = 0; s < QB_MAX_STAGE; s++) {
-            mbar_init(smem_u32(&w_full[s]), 1);
+            mbar_init(smem_u32(&w_full[s]), (kPair && leader) ? 2 : 1);   // leader: own half landed + the peer's relay
             mbar_init(smem_u32(&w_empty[s]), (uint32_t)pl.n_tiles);   // released by every tile slot's MMA warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                     "r"((uint32_t)pl.tmem_alloc_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                         "r"((uint32_t)pl.tmem_alloc_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                         "r"((uint32_t)pl.tmem_alloc_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (kPair) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
-    const uint32_t smem_base = smem_u32(dyn_smem);
+    // Shared-window addresses, computed ONCE and made opaque to the compiler.  Left alone, it re-derives every
+    // __cvta_generic_to_shared() at its use from S2UR SR_CgaCtaId, a special-register read that costs ~300 cycles
+    // (device trace) -- per barrier operation, in every role's inner loop.
+    auto opaque = [](uint32_t v) { uint32_t r; asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v)); return r; };
+    const uint32_t smem_base = opaque(smem_u32(dyn_smem));
+    const uint32_t a_bars = opaque(smem_u32(&bars[0][0])), a_wfull = opaque(smem_u32(&w_full[0])), a_wempty = opaque(smem_u32(&w_empty[0]));
+    const uint32_t a_tres = opaque(smem_u32(&tres_bar)), a_rfull = opaque(smem_u32(&rows_full[0])), a_rempty = opaque(smem_u32(&rows_empty[0]));
+    const uint32_t a_beam = opaque(smem_u32(&beam_rows[0][0][0][0]));
+    const uint32_t a_dist = opaque(smem_u32(&dist_part[0][0][0]));
+    auto bar_addr = [&](int t, int b) { return a_bars + (uint32_t)(t * QB_BAR_COUNT + b) * 8u; };
     const uint32_t tile_cols = (uint32_t)pl.tmem_tile_cols;
 
     // (unconditional on purpose: ptxas only budgets registers per region when every path executes the setmaxnreg)
@@ -401,13 +578,13 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         uint32_t stage = 0, phase = 0;
         if (kResident) {    // this CTA's quarter of T_m and C_m: per 4-column block 64 codes x 16 B = 1 KB, contiguous in the tables
             if (elect_one()) {
-                mbar_expect_tx(smem_u32(&tres_bar), (uint32_t)(pl.De + pl.D) * 256u);
+                mbar_expect_tx(a_tres, (uint32_t)(pl.De + pl.D) * 256u);
                 for (int c4 = 0; c4 < (pl.De >> 2); c4++)
                     bulk_g2s(smem_base + pl.smem_tres + c4 * 1024, p.t_blk + ((size_t)c4 * pl.K + hq * 64) * 4, 1024,
-                             smem_u32(&tres_bar));
+                             a_tres);
                 for (int c4 = 0; c4 < (pl.D >> 2); c4++)
                     bulk_g2s(smem_base + pl.smem_tres + pl.De * 256 + c4 * 1024, p.cb_blk + ((size_t)c4 * pl.K + hq * 64) * 4, 1024,
-                             smem_u32(&tres_bar));
+                             a_tres);
             }
             __syncwarp();
         }
@@ -416,37 +593,40 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         auto push_rows = [&](int64_t set, int64_t k) {
             if (set >= n_sets) return;
             const int b = (int)(k % 3);
-            mbar_wait(smem_u32(&rows_empty[b]), (uint32_t)(((k / 3) & 1) ^ 1), p.err_flag, 0x600 + b);
+            mbar_wait((a_rempty + (uint32_t)(b) * 8u), (uint32_t)(((k / 3) & 1) ^ 1), p.err_flag, 0x600 + b);
             if (elect_one()) {
                 const uint32_t de_b = (uint32_t)pl.De * 4u, d_b = (uint32_t)pl.D * 4u;
-                mbar_expect_tx(smem_u32(&rows_full[b]), 4u * (de_b + d_b));
+                mbar_expect_tx((a_rfull + (uint32_t)(b) * 8u), 4u * (de_b + d_b));
                 for (int t = 0; t < 4; t++) {       // tile slot t / 2, beam t % 2 of the tile
                     int64_t beam = 4 * set + t;
                     if (beam >= n_beams) beam = 0;
-                    bulk_g2s(smem_u32(&beam_rows[b][t >> 1][t & 1][0]), p.u + beam * pl.De, de_b, smem_u32(&rows_full[b]));
-                    bulk_g2s(smem_u32(&beam_rows[b][t >> 1][t & 1][pl.De]), p.r + beam * pl.D, d_b, smem_u32(&rows_full[b]));
+                    bulk_g2s((a_beam + (uint32_t)(((b * 2 + (t >> 1)) * 2 + (t & 1)) * 256) * 4u), p.u + beam * pl.De, de_b, (a_rfull + (uint32_t)(b) * 8u));
+                    bulk_g2s((a_beam + (uint32_t)(((b * 2 + (t >> 1)) * 2 + (t & 1)) * 256 + pl.De) * 4u), p.r + beam * pl.D, d_b, (a_rfull + (uint32_t)(b) * 8u));
                 }
             }
             __syncwarp();
         };
         int64_t kset = 0;
         if (kResident) push_rows(set_first, 0);
-        for (int64_t set = set_first; set < n_sets; set += set_stride, kset++) {
+        for (int64_t set = set_first; more_sets(set); set += set_stride, kset++) {
             if (kResident) push_rows(set + set_stride, kset + 1);
             for (int l = 0; l <= pl.L; l++) {
                 const int i0 = (l < pl.L) ? 0 : pl.n_ops_block;
                 const int i1 = (l < pl.L) ? pl.n_ops_block : n_ops;
                 const uint8_t* wbase = p.w_blob + ((l < pl.L) ? (size_t)l * (size_t)pl.block_w_bytes : 0);
                 for (int i = i0; i < i1; i++) {
-                    const uint32_t n_slab = p.ops[i].n_slab, slab_bytes = p.ops[i].slab_bytes, last_bytes = p.ops[i].last_bytes;
-                    const uint8_t* src = wbase + p.ops[i].w_off;
+                    const QbOp& op = p.ops[i];
+                    const uint32_t n_slab = op.n_slab, slab_bytes = op.slab_bytes, last_bytes = op.last_bytes;
+                    const uint8_t* src = wbase + op.w_off;
                     for (uint32_t s = 0; s < n_slab; s++) {
-                        const uint32_t bytes = (s + 1 == n_slab) ? last_bytes : slab_bytes;
-                        mbar_wait(smem_u32(&w_empty[stage]), phase ^ 1, p.err_flag, 0x100 + stage);
+                        // CTA pair: each CTA streams only its half of the slab's rows (packed half after half)
+                        const uint32_t full = (s + 1 == n_slab) ? last_bytes : slab_bytes;
+                        const uint32_t bytes = kPair ? full >> 1 : full;
+                        mbar_wait((a_wempty + stage * 8u), phase ^ 1, p.err_flag, 0x100 + stage);
                         if (elect_one()) {
-                            mbar_expect_tx(smem_u32(&w_full[stage]), bytes);
-                            bulk_g2s(smem_base + pl.smem_ring + stage * pl.slot_bytes, src + (size_t)s * slab_bytes, bytes,
-                                     smem_u32(&w_full[stage]));
+                            mbar_expect_tx((a_wfull + stage * 8u), bytes);
+                            bulk_g2s(smem_base + pl.smem_ring + stage * pl.slot_bytes,
+                                     src + (size_t)s * slab_bytes + (kPair ? cta_rank * bytes : 0u), bytes, (a_wfull + stage * 8u));
                         }
                         __syncwarp();
                         if (++stage == (uint32_t)pl.n_stage) { stage = 0; phase ^= 1; }
@@ -461,69 +641,93 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         // weights are fetched once per two tiles while the two issue streams overlap each other's bookkeeping.
         // Kept lean and warp-uniform on purpose: a lone warp retires a dependent instruction every ~4-6 cycles.
         const int t = warp - kMmaWarp;
-        if (t < NT) {
+        if (kPair && !leader) {
+            // Peer CTA of a pair: the leader issues every MMA.  One warp here relays "my half of the slab has landed" to
+            // the leader's w_full barrier (a bulk copy can only signal a barrier of the CTA it writes to).
+            if (t == 0) {
+                uint32_t stage = 0, phase = 0;
+                for (int64_t set = set_first; more_sets(set); set += set_stride) {
+                    for (int l = 0; l <= pl.L; l++) {
+                        const int i0 = (l < pl.L) ? 0 : pl.n_ops_block;
+                        const int i1 = (l < pl.L) ? pl.n_ops_block : n_ops;
+                        for (int i = i0; i < i1; i++) {
+                            const uint32_t n_slab = p.ops[i].n_slab;
+                            for (uint32_t s = 0; s < n_slab; s++) {
+                                mbar_wait((a_wfull + stage * 8u), phase, p.err_flag, 0x700 + stage);
+                                if (elect_one()) mbar_arrive_cluster(mapa_rank((a_wfull + stage * 8u), 0));
+                                __syncwarp();
+                                if (++stage == (uint32_t)pl.n_stage) { stage = 0; phase ^= 1; }
+                            }
+                        }
+                    }
+                }
+            }
+        } else if (t < NT) {
             uint32_t stage = 0, phase = 0;
             uint32_t par = 0;
             Tracer tr;
             tr.init(p, 1 + t, (tid & 31) == 0);      // trace roles 1 / 2: MMA warps of tile slots 0 / 1
-            const uint32_t ring_lo = (smem_base + pl.smem_ring) >> 4;
+            const uint32_t ring_lo = ((smem_base + pl.smem_ring) >> 4) & 0x3FFFu;    // descriptor address fields (14 bits, 16-B units)
             const uint32_t slot_lo = (uint32_t)pl.slot_bytes >> 4;
-            const uint64_t a_hi = umma_desc(0, kAkcBytes, 128);
             const uint32_t tcol = tmem_base + (uint32_t)t * tile_cols;
-            const uint32_t ae_lo = (smem_base + pl.smem_ae[t]) >> 4;
-            for (int64_t set = set_first; set < n_sets; set += set_stride) {
+            const uint32_t ae_lo = ((smem_base + pl.smem_ae[t]) >> 4) & 0x3FFFu;
+            for (int64_t set = set_first; more_sets(set); set += set_stride) {
                 for (int l = 0; l <= pl.L; l++) {
                     const int i0 = (l < pl.L) ? 0 : pl.n_ops_block;
                     const int i1 = (l < pl.L) ? pl.n_ops_block : n_ops;
                     for (int i = i0; i < i1; i++) {
-                        const QbOp& op = p.ops[i];
+                        const QbOp& op = p.ops[i];          // kernel-parameter bank -> uniform registers
                         const uint32_t n = op.n;
-                        const uint64_t b_hi = umma_desc(0, n * 16u, 128);
-                        const uint32_t b_step = 2u * n;                 // descriptor address units (16 B) per K=16
-                        const uint32_t idesc = umma_idesc(n);
+                        // pair: this CTA's slab half has n / 2 rows per k-chunk; the MMA is M = 256 over both CTAs
+                        const uint32_t b_lbo = (kPair ? n >> 1 : n) << 16;         // LBO field (bytes / 16) of the low descriptor word
+                        const uint32_t b_step = kPair ? n : 2u * n;                // descriptor address units (16 B) per K=16
+                        const uint32_t idesc = umma_idesc(n, kPair ? 2 * QB_TILE_M : QB_TILE_M);
                         const bool from_smem = op.a_src == QB_A_E;
-                        const int ks = op.ks;
+                        const int ks16 = op.ks >> 4;
                         const uint32_t n_slab = op.n_slab;
-                        if (op.wait_a) {
-                            mbar_wait(smem_u32(&bars[t][op.wait_a]), (par >> op.wait_a) & 1, p.err_flag, 0x200 + op.wait_a);
-                            par ^= 1u << op.wait_a;
-                        }
-                        if (op.wait_d) {
-                            mbar_wait(smem_u32(&bars[t][op.wait_d]), (par >> op.wait_d) & 1, p.err_flag, 0x200 + op.wait_d);
-                            par ^= 1u << op.wait_d;
-                        }
-                        tr.ev(0x200 + i);
                         const uint32_t d_tmem = tcol + op.d_col;
-                        uint32_t a_cur = from_smem ? ae_lo + (uint32_t)op.a_off * (kAkcBytes >> 4) : tcol + op.a_off;
+                        // A operand cursor: low descriptor word (shared memory; LBO = one k-chunk of the tile) or TMEM column
+                        uint32_t a_cur = from_smem ? (((uint32_t)kAkcBytes >> 4) << 16) | (ae_lo + (uint32_t)op.a_off * (kAkcBytes >> 4))
+                                                   : tcol + op.a_off;
                         uint32_t acc = op.accumulate;
-                        int k_left = op.k_total;
+                        int k16_left = op.k_total >> 4;
+                        const uint32_t commit_bar = op.commit;
+                        const uint32_t wa = op.wait_a, wd = op.wait_d;
                         for (uint32_t s = 0; s < n_slab; s++) {
-                            const int nk = (k_left < ks ? k_left : ks) >> 4;
-                            k_left -= ks;
-                            mbar_wait(smem_u32(&w_full[stage]), phase, p.err_flag, 0x300 + stage);
-                            tc_fence_after();
-                            const uint32_t b_lo = ring_lo + stage * slot_lo;
-                            if (elect_one()) {
-                                if (from_smem) {
-#pragma unroll 4
-                                    for (int k = 0; k < nk; k++) {
-                                        tc_mma_ss(d_tmem, a_hi | (uint64_t)(a_cur + (uint32_t)k * ((2 * kAkcBytes) >> 4)),
-                                                  b_hi | (uint64_t)(b_lo + (uint32_t)k * b_step), idesc, acc);
-                                        acc = 1;
-                                    }
-                                } else {
-#pragma unroll 4
-                                    for (int k = 0; k < nk; k++) {
-                                        tc_mma_ts(d_tmem, a_cur + (uint32_t)k * 8u, b_hi | (uint64_t)(b_lo + (uint32_t)k * b_step), idesc, acc);
-                                        acc = 1;
-                                    }
+                            const int nk = k16_left < ks16 ? k16_left : ks16;
+                            k16_left -= ks16;
+                            // (no tcgen05.fence after this wait: the slab was written and is read by the async proxy)
+                            mbar_wait((a_wfull + stage * 8u), phase, p.err_flag, 0x300 + stage);
+                            const uint32_t b_lo = b_lbo | (ring_lo + stage * slot_lo);
+                            if (s == 0) {
+                                // Operand barriers LAST: everything above (op decode, the weight wait) is off the
+                                // epilogue -> MMA hand-off path; an issuing warp retires only ~1 instruction per 6 cycles.
+                                if (wa) {
+                                    mbar_wait(bar_addr(t, wa), (par >> wa) & 1, p.err_flag, 0x200 + wa);
+                                    par ^= 1u << wa;
                                 }
-                                tc_commit(smem_u32(&w_empty[stage]));
-                                if (s + 1 == n_slab && op.commit) tc_commit(smem_u32(&bars[t][op.commit]));
+                                if (wd) {
+                                    mbar_wait(bar_addr(t, wd), (par >> wd) & 1, p.err_flag, 0x200 + wd);
+                                    par ^= 1u << wd;
+                                }
+                                if (wa | wd) tc_fence_after();   // orders the epilogue's tcgen05.st / ld before these MMAs
+                                tr.ev(0x200 + i);
+                            }
+                            if (elect_one()) {
+                                uint32_t a_l = a_cur, b_l = b_lo;      // cursors local to the issuing lane (the warp-wide ones advance below)
+                                if (from_smem) mma_slab<kPair, true>(nk, d_tmem, a_l, b_l, kDescHi, kDescHi, idesc, acc, (2 * kAkcBytes) >> 4, b_step);
+                                else mma_slab<kPair, false>(nk, d_tmem, a_l, b_l, kDescHi, kDescHi, idesc, acc, 0u, b_step);
+                                if (kPair) {        // both CTAs recycle the ring slot / see the accumulator
+                                    tc_commit_pair((a_wempty + stage * 8u));
+                                    if (s + 1 == n_slab && commit_bar) tc_commit_pair(bar_addr(t, commit_bar));
+                                } else {
+                                    tc_commit((a_wempty + stage * 8u));
+                                    if (s + 1 == n_slab && commit_bar) tc_commit(bar_addr(t, commit_bar));
+                                }
                             }
                             __syncwarp();
-                            acc = 1;
                             a_cur += (uint32_t)nk * (from_smem ? ((2 * kAkcBytes) >> 4) : 8u);
+                            acc = 1;
                             if (++stage == (uint32_t)pl.n_stage) { stage = 0; phase ^= 1; }
                         }
                         tr.ev(0x400 + i);
@@ -543,15 +747,27 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         uint32_t par0 = 0, par1 = 0;
         Tracer tr;
         tr.init(p, 0, tid == 0);
+        // "operand ready / accumulator free" signal to the MMA issuer of tile slot t: every thread fences its own TMEM /
+        // shared-memory writes, the warp converges and one lane arrives (barrier counts are per warp).  In a CTA pair
+        // the issuer sits in the leader CTA, so the arrival goes to the leader's barrier through the cluster window.
+        auto arrive_issuer = [&](int t, int bar, bool wrote_smem) {
+            tc_fence_before();
+            if (wrote_smem) { if (kPair) proxy_fence_async_all(); else proxy_fence_async(); }
+            __syncwarp();
+            if ((tid & 31) == 0) {
+                if (kPair) mbar_arrive_cluster(mapa_rank(bar_addr(t, bar), 0));
+                else mbar_arrive(bar_addr(t, bar));
+            }
+        };
         const int De = pl.De, K = pl.K, D = pl.D;
         int e0c, e1c, o0c, o1c;             // this thread's columns of e / of the output (no out_proj)
         group_range(De, cg, e0c, e1c);
         group_range(D, cg, o0c, o1c);
-        if (kResident) mbar_wait(smem_u32(&tres_bar), 0, p.err_flag, 0x500);
+        if (kResident) mbar_wait(a_tres, 0, p.err_flag, 0x500);
         int64_t kset = 0;
-        for (int64_t set = set_first; set < n_sets; set += set_stride, kset++) {
+        for (int64_t set = set_first; more_sets(set); set += set_stride, kset++) {
             const int rb = (int)(kset % 3);
-            if (kResident) mbar_wait(smem_u32(&rows_full[rb]), (uint32_t)((kset / 3) & 1), p.err_flag, 0x610 + rb);
+            if (kResident) mbar_wait((a_rfull + (uint32_t)(rb) * 8u), (uint32_t)((kset / 3) & 1), p.err_flag, 0x610 + rb);
             // per-tile row context, kept in scalars (no runtime-indexed arrays)
             int code0 = 0, code1 = 0;
             int64_t beam0 = 0, beam1 = 0, row0 = 0, row1 = 0;
@@ -601,8 +817,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 const float* up = p.u + beam * De;
                 if (!kResident && cg == 0 && r * 32 < De) prefetch_l1(up + r * 32);   // the per-beam row is shared by many rows: pull it into L1
                 // 32 columns per iteration: all 16 operand loads are issued before the first use, one wide TMEM store
-                const float4* ts4 = reinterpret_cast<const float4*>(dyn_smem + pl.smem_tres) + (r & 63);   // resident: [col/4][64][4]
-                const float4* us4 = reinterpret_cast<const float4*>(&beam_rows[rb][t][r >> 6][0]);
+                const uint32_t ts_a = smem_base + (uint32_t)pl.smem_tres + (uint32_t)(r & 63) * 16u;   // resident: [col/4][64][4]
+                const uint32_t us_a = a_beam + (uint32_t)((rb * 2 + t) * 2 + (r >> 6)) * 1024u;
 #pragma unroll 1
                 for (int c = e0c; c < e1c; c += 32) {
                     const int n = e1c - c;          // 16 or >= 32
@@ -611,7 +827,10 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         float4 tb[4], ub[4];
                         if (kResident) {
 #pragma unroll
-                            for (int i = 0; i < 4; i++) { tb[i] = ts4[((c >> 2) + 4 * h + i) * 64]; ub[i] = us4[(c >> 2) + 4 * h + i]; }
+                            for (int i = 0; i < 4; i++) {
+                                tb[i] = lds4(ts_a + (uint32_t)((c >> 2) + 4 * h + i) * 1024u);
+                                ub[i] = lds4(us_a + (uint32_t)((c >> 2) + 4 * h + i) * 16u);
+                            }
                         } else {
                             const float* base = p.t_blk + ((size_t)((c >> 2) + 4 * h) * K + code) * 4;
 #pragma unroll
@@ -644,9 +863,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 }
                 tr.ev(14);
                 tmem_wait_st();
-                tc_fence_before();
-                proxy_fence_async();
-                mbar_arrive(smem_u32(&bars[t][QB_BAR_AE_READY]));
+                arrive_issuer(t, QB_BAR_AE_READY, true);
                 tr.ev(2 + 0x80 * t);
             };
 #pragma unroll 1
@@ -655,16 +872,17 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             float acc0 = 0.f, acc1 = 0.f;
             auto wait_bar = [&](int t, int bar, uint32_t code) {
                 uint32_t& par = t ? par1 : par0;
-                mbar_wait(smem_u32(&bars[t][bar]), (par >> bar) & 1, p.err_flag, code);
+                mbar_wait(bar_addr(t, bar), (par >> bar) & 1, p.err_flag, code);
                 par ^= 1u << bar;
                 tc_fence_after();
             };
             // final epilogue of columns [c0, c1) at accumulator address taddr (o[d0 + c0 ..]); cb = skip codeword of the
             // first 32 columns, fetched by the caller BEFORE it waited for the accumulator
             auto final_cols = [&](uint32_t taddr, int c0, int c1, int d0, int code, int64_t beam, int64_t row, bool valid,
-                                  float4 (&cb)[8], float& acc, const float* rows_smem) {
-                const float* src = kResident ? rows_smem + d0 : (kScore ? p.r : p.xhat_in) + beam * D + d0;
-                const float4* cs4 = reinterpret_cast<const float4*>(dyn_smem + pl.smem_tres + pl.De * 256) + (r & 63);   // resident C_m quarter
+                                  float4 (&cb)[8], float& acc, uint32_t rows_a) {
+                const float* src = (kScore ? p.r : p.xhat_in) + beam * D + d0;         // not used in resident mode
+                const uint32_t rs_a = rows_a + (uint32_t)d0 * 4u;                        // resident: r_b row in shared memory
+                const uint32_t cs_a = smem_base + (uint32_t)(pl.smem_tres + pl.De * 256) + (uint32_t)(r & 63) * 16u;   // resident C_m quarter
                 const bool skip = pl.skip != 0;
                 float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;       // four independent accumulation chains
 #pragma unroll 1
@@ -680,8 +898,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         for (int i = 0; i < 4; i++) {
                             const int cc = cb0 + 16 * h + 4 * i;
                             if (kResident) {
-                                tv[i] = *reinterpret_cast<const float4*>(src + cc);
-                                cv[i] = skip ? cs4[((d0 + cc) >> 2) * 64] : make_float4(0.f, 0.f, 0.f, 0.f);
+                                tv[i] = lds4(rs_a + (uint32_t)cc * 4u);
+                                cv[i] = skip ? lds4(cs_a + (uint32_t)((d0 + cc) >> 2) * 1024u) : make_float4(0.f, 0.f, 0.f, 0.f);
                             } else {
                                 tv[i] = ldg4(src + cc);
                                 cv[i] = cb[4 * h + i];          // all zero when the model has no outer skip
@@ -727,8 +945,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         wait_bar(t, QB_BAR_HACC_FULL, 0x404);
                         tr.ev(3 + 0x80 * t);
                         acc_to_tmem_operand(lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col, c0, c1, 1 + q);
-                        tc_fence_before();
-                        mbar_arrive(smem_u32(&bars[t][QB_BAR_AH_READY]));
+                        arrive_issuer(t, QB_BAR_AH_READY, false);
                         tr.ev(4 + 0x80 * t);
                     }
                 }
@@ -739,9 +956,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         tr.ev(5 + 0x80 * t);
                         acc_to_smem_operand(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, e0c, e1c,
                                             smem_base + pl.smem_ae[t] + (uint32_t)r * 16u);
-                        tc_fence_before();
-                        proxy_fence_async();
-                        mbar_arrive(smem_u32(&bars[t][QB_BAR_AE_READY]));
+                        arrive_issuer(t, QB_BAR_AE_READY, true);
                         tr.ev(6 + 0x80 * t);
                     }
                 }
@@ -760,7 +975,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     tr.ev(5 + 0x80 * t);
                     float a = 0.f;
                     final_cols(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, o0c, o1c, 0, t ? code1 : code0, t ? beam1 : beam0,
-                               t ? row1 : row0, t ? valid1 : valid0, cb, a, &beam_rows[rb][t][r >> 6][De]);
+                               t ? row1 : row0, t ? valid1 : valid0, cb, a,
+                               a_beam + (uint32_t)(((rb * 2 + t) * 2 + (r >> 6)) * 256 + De) * 4u);
                     if (t) acc1 = a; else acc0 = a;
                     tc_fence_before();
                     tr.ev(7 + 0x80 * t);
@@ -782,25 +998,32 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         wait_bar(t, QB_BAR_HACC_FULL, 0x414);
                         const uint32_t ta = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
                         float a = t ? acc1 : acc0;
-                        final_cols(ta, c0, c1, qq * pl.oc, t ? code1 : code0, t ? beam1 : beam0, t ? row1 : row0, t ? valid1 : valid0, cb, a, nullptr);
+                        final_cols(ta, c0, c1, qq * pl.oc, t ? code1 : code0, t ? beam1 : beam0, t ? row1 : row0, t ? valid1 : valid0, cb, a, 0u);
                         if (t) acc1 = a; else acc0 = a;
-                        tc_fence_before();
-                        if (qq + 1 < pl.n_ochunk) mbar_arrive(smem_u32(&bars[t][QB_BAR_HACC_FREE]));
+                        if (qq + 1 < pl.n_ochunk) arrive_issuer(t, QB_BAR_HACC_FREE, false);
+                        else tc_fence_before();
                     }
                 }
             }
             if (kScore) {   // the column groups of a row meet in shared memory
-                if (cg > 0) { dist_part[0][cg - 1][r] = acc0; dist_part[1][cg - 1][r] = acc1; }
+                constexpr int kParts = kColGroups > 1 ? kColGroups - 1 : 1;       // dist_part[tile][part][row]
+                if (cg > 0) {
+                    sts1(a_dist + (uint32_t)((0 * kParts + cg - 1) * QB_TILE_M + r) * 4u, acc0);
+                    sts1(a_dist + (uint32_t)((1 * kParts + cg - 1) * QB_TILE_M + r) * 4u, acc1);
+                }
                 named_bar_sync(5, kEpiThreads);
                 if (cg == 0) {
 #pragma unroll
-                    for (int g = 0; g < kColGroups - 1; g++) { acc0 += dist_part[0][g][r]; acc1 += dist_part[1][g][r]; }
+                    for (int g = 0; g < kColGroups - 1; g++) {
+                        acc0 += lds1(a_dist + (uint32_t)((0 * kParts + g) * QB_TILE_M + r) * 4u);
+                        acc1 += lds1(a_dist + (uint32_t)((1 * kParts + g) * QB_TILE_M + r) * 4u);
+                    }
                     if (valid0) p.dist[row0] = acc0;
                     if (valid1) p.dist[row1] = acc1;
                 }
                 named_bar_sync(5, kEpiThreads);
             }
-            if (kResident) mbar_arrive(smem_u32(&rows_empty[rb]));
+            if (kResident) mbar_arrive((a_rempty + (uint32_t)(rb) * 8u));
             tr.ev(8);
         }
     }
@@ -808,11 +1031,17 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     // ---- teardown ------------------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
+    if (kPair) cluster_sync_all();      // no CTA of a pair leaves while the other may still signal its barriers / read its smem
     tc_fence_after();
     if (warp == kMmaWarp) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)pl.tmem_alloc_cols)
-                     : "memory");
+        if (kPair)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"((uint32_t)pl.tmem_alloc_cols)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"((uint32_t)pl.tmem_alloc_cols)
+                         : "memory");
     }
 }
 
@@ -824,10 +1053,14 @@ cudaError_t mlp_set_smem_attr(int smem_bytes) {
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (smem_bytes <= current[dev]) return cudaSuccess;
-    e = cudaFuncSetAttribute(qb_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(qb_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(qb_mlp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess) current[dev] = smem_bytes;
+    const void* fns[] = {(const void*)qb_mlp_kernel<true, false, false>, (const void*)qb_mlp_kernel<true, true, false>,
+                         (const void*)qb_mlp_kernel<false, false, false>, (const void*)qb_mlp_kernel<true, false, true>,
+                         (const void*)qb_mlp_kernel<true, true, true>, (const void*)qb_mlp_kernel<false, false, true>};
+    for (const void* f : fns) {
+        e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    current[dev] = smem_bytes;
     return e;
 }
 
@@ -839,21 +1072,43 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
     // resident tables: score launches over all 256 codes of every beam (2 tiles per beam), shape qualified by the planner
     const bool resident = p.mode == QB_MODE_SCORE && p.A == 0 && p.C == 256 && p.plan.K == 256 && p.plan.smem_tres >= 0 &&
                           p.plan.n_tiles == 2 && (p.n_rows & 255) == 0 && n_sm >= 4;
+    const bool pair = p.plan.pair != 0 && n_sm >= 2;     // the weights are packed for the pair kernel: no other choice
+    if (p.plan.pair && !pair) return cudaErrorInvalidConfiguration;
     int grid;
     if (resident) {
         const int64_t sets = ((p.n_rows >> 8) + 3) / 4;       // per code quarter
         const int64_t per_quarter = sets < n_sm / 4 ? sets : n_sm / 4;
-        grid = (int)(4 * per_quarter);
+        grid = (int)(4 * per_quarter);                         // a multiple of 4: CTA pairs are code quarters (0,1) / (2,3)
     } else {
         grid = (int)(n_sets < n_sm ? n_sets : n_sm);
+        if (pair) grid = (grid + 1) & ~1;                      // whole pairs; a peer without work of its own follows its leader
+        if (pair && grid > n_sm) grid = n_sm & ~1;
     }
     static const int exp_bits = getenv("QB_EXP") ? atoi(getenv("QB_EXP")) : 0;
     auto launch = [&](const MlpParams& q0) {
         MlpParams q = q0;
         q.exp = exp_bits;
-        if (resident) qb_mlp_kernel<true, true><<<grid, kThreads, q.plan.smem_total, stream>>>(q);
-        else if (q.mode == QB_MODE_SCORE) qb_mlp_kernel<true, false><<<grid, kThreads, q.plan.smem_total, stream>>>(q);
-        else qb_mlp_kernel<false, false><<<grid, kThreads, q.plan.smem_total, stream>>>(q);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = (size_t)q.plan.smem_total;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = pair ? 2 : 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (pair) {
+            if (resident) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, true, true>, q);
+            if (q.mode == QB_MODE_SCORE) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, true>, q);
+            return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, true>, q);
+        }
+        if (resident) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, true, false>, q);
+        if (q.mode == QB_MODE_SCORE) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, false>, q);
+        return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, false>, q);
     };
     // Debug: QB_MLP_TRACE=<file>[:<launch index>] dumps the event log of CTA 0 for one launch (synchronises).
     static const char* trace_env = getenv("QB_MLP_TRACE");
@@ -867,7 +1122,8 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
         const size_t bytes = (3 * QB_TRACE_EVENTS + 512) * sizeof(unsigned long long);
         cudaMalloc((void**)&q.trace, bytes);
         cudaMemsetAsync(q.trace, 0, bytes, stream);
-        launch(q);
+        cudaError_t le = launch(q);
+        if (le != cudaSuccess) return le;
         cudaStreamSynchronize(stream);
         std::vector<unsigned long long> h(3 * QB_TRACE_EVENTS + 512);
         cudaMemcpy(h.data(), q.trace, bytes, cudaMemcpyDeviceToHost);
@@ -887,8 +1143,8 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
         }
         return cudaGetLastError();
     }
-    launch(p);
-    return cudaGetLastError();
+    cudaError_t le = launch(p);
+    return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 }  // namespace qb

@@ -124,13 +124,24 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     p->n_stage = n_stage;
     p->smem_total = off + n_stage * p->slot_bytes;
 
+    // ---- CTA pair: the M = 256 MMA needs N % 16 == 0 (shared-memory A) / N % 32 == 0 (TMEM A); N is the full op width
+    {
+        const int n_eparts = (De + 255) / 256;
+        const int epart = round_up((De + n_eparts - 1) / n_eparts, 16);
+        bool ok = true;
+        if (L > 0)
+            for (int n0 = 0; n0 < De; n0 += epart) ok = ok && (std::min(epart, De - n0) % 32 == 0);
+        if (opt.pair == 2 && !ok) { *err = "pair mode needs every down-projection width to be a multiple of 32"; return -1; }
+        p->pair = (opt.pair == 1) ? 0 : (ok ? 1 : 0);
+    }
+
     // ---- op list ------------------------------------------------------------------------------------------------
     ops->clear();
     uint32_t w_off = 0;
     // GEMM  D[128, n] (+)= A[128, k_total] . W[rows n][cols k_total]^T, W cut along K into ring-slot-sized slabs
     auto emit_gemm = [&](int n, int k_total, uint8_t a_src, int a_unit0, int d_col, bool acc_first,
                          uint8_t wait_a, uint8_t wait_d, uint8_t commit) {
-        int ks = (p->slot_bytes / (2 * n)) / 16 * 16;
+        int ks = ((p->pair ? 2 : 1) * p->slot_bytes / (2 * n)) / 16 * 16;   // a pair CTA holds half the rows of a slab
         if (opt.max_slab_k > 0) ks = std::min(ks, opt.max_slab_k);
         ks = std::max(16, std::min(ks, k_total));
         const int n_slab = (k_total + ks - 1) / ks;
@@ -174,8 +185,7 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     p->n_ops_out = (int)ops->size() - p->n_ops_block;
     if (ops->size() > QB_MAX_OPS) { *err = "op list too long"; return -1; }
     for (const QbOp& op : *ops)
-    for (const QbOp& op : *ops)
-        if ((int)op.slab_bytes > p->slot_bytes || op.n_slab < 1) { *err = "internal: slab larger than ring slot"; return -1; }
+        if ((int)op.slab_bytes > (p->pair ? 2 : 1) * p->slot_bytes || op.n_slab < 1) { *err = "internal: slab larger than ring slot"; return -1; }
     p->w_blob_bytes = std::max<int64_t>(w_off, 16);
     return 0;
 }
@@ -191,9 +201,12 @@ int pack_step_weights(const QbStepPlan& p, const std::vector<QbOp>& ops, const f
         for (int s = 0; s < op.n_slab; s++) {
             uint16_t* dst = blob + (base + op.w_off + (size_t)s * op.slab_bytes) / 2;
             const int k0 = s * op.ks, kn = std::min<int>(op.ks, op.k_total - k0);
+            // pair mode: rows [0, n/2) then rows [n/2, n), each half as [k/8][n/2][8]
+            const int nh = p.pair ? op.n / 2 : op.n;
             for (int k = 0; k < kn; k++)
                 for (int r = 0; r < op.n; r++)
-                    dst[((size_t)(k / 8) * op.n + r) * 8 + (k % 8)] = f32_to_f16(w[(size_t)(row0 + r) * ld + col0 + k0 + k]);
+                    dst[(size_t)(r / nh) * nh * kn + ((size_t)(k / 8) * nh + (r % nh)) * 8 + (k % 8)] =
+                        f32_to_f16(w[(size_t)(row0 + r) * ld + col0 + k0 + k]);
         }
     };
     for (int l = 0; l <= p.L; l++) {
@@ -261,7 +274,7 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
                    int n_plan_out, void* ops_out, int max_ops) {
     qb::PlanOptions opt;
     if (opts5) {
-        opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.ctas_per_sm = opts5[1] >> 8; opt.slot_bytes = opts5[2];
+        opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = opts5[1] >> 8; opt.slot_bytes = opts5[2];
         opt.max_stage = opts5[3] & 0xff; opt.no_resident = opts5[3] >> 8; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
@@ -271,7 +284,7 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
     const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_tiles, p.tmem_alloc_cols,
                          p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk, p.oc, p.n_ochunk, p.tmem_e_col, p.tmem_h_col,
                          p.tmem_tile_cols, p.smem_tres, p.smem_ring, p.slot_bytes, p.n_stage, p.smem_total,
-                         (int32_t)p.block_w_bytes, (int32_t)p.w_blob_bytes};
+                         (int32_t)p.block_w_bytes, (int32_t)p.w_blob_bytes, p.pair};
     const int nv = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < nv && i < n_plan_out; i++) plan_out[i] = v[i];
     if ((int)ops.size() > max_ops) return -2;
@@ -283,7 +296,7 @@ int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int
                  const float* const* down, const float* out_proj, uint16_t* blob, int64_t blob_halfs) {
     qb::PlanOptions opt;
     if (opts5) {
-        opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.ctas_per_sm = opts5[1] >> 8; opt.slot_bytes = opts5[2];
+        opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = opts5[1] >> 8; opt.slot_bytes = opts5[2];
         opt.max_stage = opts5[3] & 0xff; opt.no_resident = opts5[3] >> 8; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;

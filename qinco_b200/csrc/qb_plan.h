@@ -43,7 +43,7 @@ enum QbBar : uint8_t {
 struct QbOp {
     uint32_t w_off;      // byte offset of the first slab (multiple of 16): block ops relative to the block's weights,
                          // out_proj ops relative to the step blob; slabs are contiguous
-    uint32_t slab_bytes; // n * ks * 2
+    uint32_t slab_bytes; // n * ks * 2 (both halves in pair mode)
     uint32_t last_bytes; // bytes of the last slab (k_total - (n_slab-1)*ks columns)
     uint16_t n;          // MMA N (rows of W): multiple of 16, 16..256
     uint16_t ks;         // K extent of a full slab: multiple of 16
@@ -83,6 +83,8 @@ struct QbStepPlan {
     int32_t slot_bytes;
     int32_t n_stage;
     int32_t smem_total;
+    int32_t pair;            // 1: CTA-pair kernel (cta_group::2, M = 256 over two CTAs): every slab is packed as two row
+                             // halves, CTA r of a pair streams half r into a ring slot of slot_bytes
     int64_t block_w_bytes;   // packed weight bytes of one residual block
     int64_t w_blob_bytes;    // packed weight bytes for this step (L blocks + out_proj)
 };

@@ -19,7 +19,7 @@ OP_DTYPE = np.dtype([("w_off", "<u4"), ("slab_bytes", "<u4"), ("last_bytes", "<u
                      ("accumulate", "u1"), ("wait_a", "u1"), ("wait_d", "u1"), ("commit", "u1"), ("pad", "u1", 4)])
 PLAN_FIELDS = ["D", "De", "Dh", "L", "K", "has_proj", "skip", "n_tiles", "tmem_alloc_cols", "n_ops_block", "n_ops_out",
                "hc", "n_hchunk", "oc", "n_ochunk", "tmem_e_col", "tmem_h_col", "tmem_tile_cols", "smem_tres", "smem_ring",
-               "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes"]
+               "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes", "pair"]
 A_E, A_H = 0, 1
 BAR_AE_READY, BAR_AH_READY, BAR_HACC_FREE, BAR_HACC_FULL, BAR_EACC_FULL = 1, 2, 3, 4, 5
 
@@ -133,7 +133,10 @@ def replay(plan, ops, blob, T, CB, WxT, codes, xhat):
         elif op["wait_a"] == BAR_AH_READY:
             state["AH"] = f16(np.maximum(tmem[:, hcol:hcol + state["hw"]], 0))   # in-place packed fp16 operand
         nn, ks, kt = int(op["n"]), int(op["ks"]), int(op["k_total"])
-        assert op["slab_bytes"] == nn * ks * 2 <= plan["slot_bytes"]
+        pair = bool(plan["pair"])
+        assert op["slab_bytes"] == nn * ks * 2 <= plan["slot_bytes"] * (2 if pair else 1)
+        if pair:       # cta_group::2 shapes: N % 16 with A in shared memory, N % 32 with A in TMEM
+            assert nn % (32 if op["a_src"] == A_H else 16) == 0
         assert op["n_slab"] == -(-kt // ks) and op["last_bytes"] == nn * (kt - (int(op["n_slab"]) - 1) * ks) * 2
         c0 = int(op["d_col"])
         acc = bool(op["accumulate"])
@@ -141,7 +144,11 @@ def replay(plan, ops, blob, T, CB, WxT, codes, xhat):
             kk = min(ks, kt - s * ks)
             off = base + int(op["w_off"]) + s * int(op["slab_bytes"])
             slab = bytes_view[off: off + nn * kk * 2].view(np.float16).astype(np.float32)
-            W = slab.reshape(kk // 8, nn, 8).transpose(1, 0, 2).reshape(nn, kk)
+            if pair:   # CTA r of the pair streams rows [r n/2, (r+1) n/2), each half laid out [k/8][n/2][8]
+                W = np.concatenate([h.reshape(kk // 8, nn // 2, 8).transpose(1, 0, 2).reshape(nn // 2, kk)
+                                    for h in slab.reshape(2, -1)])
+            else:
+                W = slab.reshape(kk // 8, nn, 8).transpose(1, 0, 2).reshape(nn, kk)
             if op["a_src"] == A_E:
                 k0 = int(op["a_off"]) * 8 + s * ks
                 a = state["AE"][:, k0:k0 + kk]
@@ -192,7 +199,7 @@ SHAPES = {
 
 
 @pytest.mark.parametrize("name", list(SHAPES))
-@pytest.mark.parametrize("opts", [None, [64, 1, 8192, 3, 32], [0, 0, 32768, 0, 0]])
+@pytest.mark.parametrize("opts", [None, [64, 1, 8192, 3, 32], [0, 0, 32768, 0, 0], [0, 1 << 8, 0, 0, 0]])
 def test_op_list_replay_matches_oracle(lib, name, opts):
     cfg = synth.make_cfg(None, **SHAPES[name])
     w = synth.make_weights(cfg, seed=3, n_train=512, kmeans_iters=1, fp16_exact=True)
