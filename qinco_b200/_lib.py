@@ -151,7 +151,7 @@ class Handle:
         mean = _f32(weights["data_mean"]) if "data_mean" in weights else np.zeros(D, np.float32)
         keep.append(mean)
         d.data_mean = mean.ctypes.data_as(C.POINTER(C.c_float))
-        d.data_std = float(np.asarray(weights.get("data_std", 1.0)))
+        d.data_std = float(np.asarray(weights.get("data_std", 1.0)).reshape(-1)[0])
         for k, v in (plan_opts or {}).items():
             setattr(d, "opt_" + k, int(v))
         h = C.c_void_p()

@@ -12,7 +12,7 @@ namespace qb {
 struct PlanOptions {
     int hc = 0;           // H chunk width (0 = auto)
     int n_tiles = 0;      // 128-row tiles in flight per CTA (0 = auto: 2 when TMEM and shared memory allow)
-    int pair = 0;         // CTA-pair (cta_group::2) kernel: 0 = auto (on when every MMA shape allows it), 1 = off, 2 = on
+    int pair = 0;         // CTA-pair (cta_group::2) kernel: 0 = auto (currently off), 1 = off, 2 = on (needs N % 32 == 0 down-projections)
     int no_resident = 0;  // 1: never keep table halves resident (debug / A-B tests)
     int slot_bytes = 0;   // weight ring slot size (0 = 16 KiB)
     int max_stage = 0;    // cap on ring depth (0 = QB_MAX_STAGE)

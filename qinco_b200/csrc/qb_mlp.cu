@@ -43,8 +43,8 @@ constexpr int kColGroups = kEpiWarps / 4;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiThreads + 128;  // + one warpgroup: producer warp, one MMA warp per tile slot, one idle warp
 // Registers are a per-scheduler pool (16 K per SM sub-partition = 3 warps x 168 at launch).  The service warpgroup
-// hands most of its share back (setmaxnreg.dec) and the epilogue warpgroups take it (setmaxnreg.inc): 2 x 216 + 56 <= 512.
-constexpr int kEpiRegs = 216, kSvcRegs = 56;
+// hands most of its share back (setmaxnreg.dec) and the epilogue warpgroups take it (setmaxnreg.inc): 2 x 232 + 40 = 504 <= 512.
+constexpr int kEpiRegs = 232, kSvcRegs = 40;
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;   // MMA warps: kMmaWarp + tile slot
 constexpr int kAkcBytes = QB_TILE_M * 16;   // bytes of one 8-element k-chunk of an A operand tile
 constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);   // high word of every UMMA smem descriptor here: SBO = 128 B, version 1
@@ -578,13 +578,9 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         uint32_t stage = 0, phase = 0;
         if (kResident) {    // this CTA's quarter of T_m and C_m: per 4-column block 64 codes x 16 B = 1 KB, contiguous in the tables
             if (elect_one()) {
-                mbar_expect_tx(a_tres, (uint32_t)(pl.De + pl.D) * 256u);
-                for (int c4 = 0; c4 < (pl.De >> 2); c4++)
-                    bulk_g2s(smem_base + pl.smem_tres + c4 * 1024, p.t_blk + ((size_t)c4 * pl.K + hq * 64) * 4, 1024,
-                             a_tres);
+                mbar_expect_tx(a_tres, (uint32_t)pl.D * 256u);
                 for (int c4 = 0; c4 < (pl.D >> 2); c4++)
-                    bulk_g2s(smem_base + pl.smem_tres + pl.De * 256 + c4 * 1024, p.cb_blk + ((size_t)c4 * pl.K + hq * 64) * 4, 1024,
-                             a_tres);
+                    bulk_g2s(smem_base + pl.smem_tres + c4 * 1024, p.cb_blk + ((size_t)c4 * pl.K + hq * 64) * 4, 1024, a_tres);
             }
             __syncwarp();
         }
@@ -764,15 +760,29 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         group_range(De, cg, e0c, e1c);
         group_range(D, cg, o0c, o1c);
         if (kResident) mbar_wait(a_tres, 0, p.err_flag, 0x500);
+        // Resident mode: this thread's code never changes, so its slice of the T_m row (<= 64 columns) lives in registers
+        // for the whole launch; reading it from shared memory for every tile costs as much shared-memory bandwidth as a
+        // quarter of the tile's MMAs.
+        float4 treg[16];
+        if (kResident) {
+            const float* tsrc = p.t_blk + ((size_t)(e0c >> 2) * K + (hq * 64 + (r & 63))) * 4;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                treg[i] = (e0c + 4 * i < e1c) ? ldg4(tsrc + (size_t)i * K * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         int64_t kset = 0;
+        // per-tile row context, kept in scalars (no runtime-indexed arrays).  It belongs to the set whose tiles are
+        // currently initialised: without an out_proj the init of the NEXT set's tile t is issued right after the final
+        // epilogue of the current tile t, so tile t's MMAs restart while the other tile is still in its final epilogue.
+        int code0 = 0, code1 = 0;
+        int64_t beam0 = 0, beam1 = 0, row0 = 0, row1 = 0;
+        bool valid0 = false, valid1 = false;
+        bool primed = false;        // the current set's tiles were initialised by the previous iteration
         for (int64_t set = set_first; more_sets(set); set += set_stride, kset++) {
             const int rb = (int)(kset % 3);
-            if (kResident) mbar_wait((a_rfull + (uint32_t)(rb) * 8u), (uint32_t)((kset / 3) & 1), p.err_flag, 0x610 + rb);
-            // per-tile row context, kept in scalars (no runtime-indexed arrays)
-            int code0 = 0, code1 = 0;
-            int64_t beam0 = 0, beam1 = 0, row0 = 0, row1 = 0;
-            bool valid0 = false, valid1 = false;
-            auto row_ctx = [&](int t, int64_t& row, int64_t& beam, int& code, bool& valid) {
+            if (kResident && !primed) mbar_wait((a_rfull + (uint32_t)(rb) * 8u), (uint32_t)((kset / 3) & 1), p.err_flag, 0x610 + rb);
+            auto row_ctx = [&](int64_t set, int t, int64_t& row, int64_t& beam, int& code, bool& valid) {
+                code = 0; beam = 0; row = 0; valid = false;
                 if (kResident) {            // tile slot t, rows 0-63 / 64-127 = code quarter hq of beams 4*set + 2t / + 2t + 1
                     beam = 4 * set + 2 * t + (r >> 6);
                     code = hq * 64 + (r & 63);
@@ -796,8 +806,10 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     if (code >= K) code = K - 1;   // never read outside the tables (bad codes are rejected on the host)
                 }
             };
-            row_ctx(0, row0, beam0, code0, valid0);
-            row_ctx(1, row1, beam1, code1, valid1);
+            if (!primed) {
+                row_ctx(set, 0, row0, beam0, code0, valid0);
+                row_ctx(set, 1, row1, beam1, code1, valid1);
+            }
             tr.ev(1);
             // table row block: columns [c, c + 32) of a [cols/4][K][4] table for `code`, `n` (16 or >= 32) of them.  Kept to
             // 32 columns (32 registers): anything that spills is re-read from L2, which costs more than a second batch.
@@ -811,31 +823,18 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 }
             };
             // ---- init: e0 = T_m[code] + u_b over this thread's columns ------------------------------------------------
-            auto init_tile = [&](int t, int code, int64_t beam) {
+            auto init_tile = [&](int t, int code, int64_t beam, int rb) {
                 const uint32_t tl = lane_base + (uint32_t)t * tile_cols;
                 const uint32_t ae_dst = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
                 const float* up = p.u + beam * De;
                 if (!kResident && cg == 0 && r * 32 < De) prefetch_l1(up + r * 32);   // the per-beam row is shared by many rows: pull it into L1
-                // 32 columns per iteration: all 16 operand loads are issued before the first use, one wide TMEM store
-                const uint32_t ts_a = smem_base + (uint32_t)pl.smem_tres + (uint32_t)(r & 63) * 16u;   // resident: [col/4][64][4]
+                // 32 columns per batch: operand loads first, one wide TMEM store, four shared-memory k-chunk rows
                 const uint32_t us_a = a_beam + (uint32_t)((rb * 2 + t) * 2 + (r >> 6)) * 1024u;
-#pragma unroll 1
-                for (int c = e0c; c < e1c; c += 32) {
-                    const int n = e1c - c;          // 16 or >= 32
+                auto batch = [&](int c, int n, auto&& operands) {     // n = 16 or >= 32
                     uint32_t e[32];
-                    auto half16 = [&](int h) {      // columns c + 16 h .. + 16: 8 operand loads in flight, then the sums
+                    auto half16 = [&](int h) {
                         float4 tb[4], ub[4];
-                        if (kResident) {
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                tb[i] = lds4(ts_a + (uint32_t)((c >> 2) + 4 * h + i) * 1024u);
-                                ub[i] = lds4(us_a + (uint32_t)((c >> 2) + 4 * h + i) * 16u);
-                            }
-                        } else {
-                            const float* base = p.t_blk + ((size_t)((c >> 2) + 4 * h) * K + code) * 4;
-#pragma unroll
-                            for (int i = 0; i < 4; i++) { tb[i] = ldg4(base + (size_t)i * K * 4); ub[i] = ldg4(up + c + 16 * h + 4 * i); }
-                        }
+                        operands(h, tb, ub);
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
                             e[16 * h + 4 * i + 0] = __float_as_uint(tb[i].x + ub[i].x); e[16 * h + 4 * i + 1] = __float_as_uint(tb[i].y + ub[i].y);
@@ -860,14 +859,38 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         tmem_st16p(tl + pl.tmem_e_col + c, e);
                         to_smem(0); to_smem(1);
                     }
+                };
+                if (kResident) {
+#pragma unroll
+                    for (int b = 0; b < 2; b++) {       // <= 64 columns per thread in resident mode (planner)
+                        const int c = e0c + 32 * b;
+                        if (c < e1c)
+                            batch(c, e1c - c, [&](int h, float4 (&tb)[4], float4 (&ub)[4]) {
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    tb[i] = treg[8 * b + 4 * h + i];
+                                    ub[i] = lds4(us_a + (uint32_t)((c >> 2) + 4 * h + i) * 16u);
+                                }
+                            });
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = e0c; c < e1c; c += 32)
+                        batch(c, e1c - c, [&](int h, float4 (&tb)[4], float4 (&ub)[4]) {
+                            const float* base = p.t_blk + ((size_t)((c >> 2) + 4 * h) * K + code) * 4;
+#pragma unroll
+                            for (int i = 0; i < 4; i++) { tb[i] = ldg4(base + (size_t)i * K * 4); ub[i] = ldg4(up + c + 16 * h + 4 * i); }
+                        });
                 }
                 tr.ev(14);
                 tmem_wait_st();
                 arrive_issuer(t, QB_BAR_AE_READY, true);
                 tr.ev(2 + 0x80 * t);
             };
+            if (!primed) {
 #pragma unroll 1
-            for (int t = 0; t < NT; t++) init_tile(t, t ? code1 : code0, t ? beam1 : beam0);
+                for (int t = 0; t < NT; t++) init_tile(t, t ? code1 : code0, t ? beam1 : beam0, rb);
+            }
             // ---- residual blocks -----------------------------------------------------------------------------------
             float acc0 = 0.f, acc1 = 0.f;
             auto wait_bar = [&](int t, int bar, uint32_t code) {
@@ -882,7 +905,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                                   float4 (&cb)[8], float& acc, uint32_t rows_a) {
                 const float* src = (kScore ? p.r : p.xhat_in) + beam * D + d0;         // not used in resident mode
                 const uint32_t rs_a = rows_a + (uint32_t)d0 * 4u;                        // resident: r_b row in shared memory
-                const uint32_t cs_a = smem_base + (uint32_t)(pl.smem_tres + pl.De * 256) + (uint32_t)(r & 63) * 16u;   // resident C_m quarter
+                const uint32_t cs_a = smem_base + (uint32_t)pl.smem_tres + (uint32_t)(r & 63) * 16u;   // resident C_m quarter
                 const bool skip = pl.skip != 0;
                 float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;       // four independent accumulation chains
 #pragma unroll 1
@@ -962,7 +985,20 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 }
             }
             // ---- final epilogue straight from Eacc (no out_proj); the skip codeword is only alive here ------------------
+            constexpr int kParts = kColGroups > 1 ? kColGroups - 1 : 1;       // dist_part[tile][part][row]
+            auto publish_dist = [&](int t, float a, int64_t row, bool valid) {    // the column groups of a row meet in shared memory
+                if (cg > 0) sts1(a_dist + (uint32_t)((t * kParts + cg - 1) * QB_TILE_M + r) * 4u, a);
+                named_bar_sync(5, kEpiThreads);
+                if (cg == 0) {
+#pragma unroll
+                    for (int g = 0; g < kColGroups - 1; g++) a += lds1(a_dist + (uint32_t)((t * kParts + g) * QB_TILE_M + r) * 4u);
+                    if (valid) p.dist[row] = a;
+                }
+            };
+            const int64_t set_next = set + set_stride;
+            const bool has_next = more_sets(set_next);
             if (!pl.has_proj) {
+                const int rbn = (int)((kset + 1) % 3);
 #pragma unroll 1
                 for (int t = 0; t < NT; t++) {
                     float4 cb[8];
@@ -977,10 +1013,17 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     final_cols(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, o0c, o1c, 0, t ? code1 : code0, t ? beam1 : beam0,
                                t ? row1 : row0, t ? valid1 : valid0, cb, a,
                                a_beam + (uint32_t)(((rb * 2 + t) * 2 + (r >> 6)) * 256 + De) * 4u);
-                    if (t) acc1 = a; else acc0 = a;
                     tc_fence_before();
                     tr.ev(7 + 0x80 * t);
+                    if (kScore) publish_dist(t, a, t ? row1 : row0, t ? valid1 : valid0);
+                    if (has_next) {         // tile slot t is free: start its next set now
+                        if (kResident && t == 0)
+                            mbar_wait((a_rfull + (uint32_t)(rbn) * 8u), (uint32_t)(((kset + 1) / 3) & 1), p.err_flag, 0x610 + rbn);
+                        if (t) row_ctx(set_next, 1, row1, beam1, code1, valid1); else row_ctx(set_next, 0, row0, beam0, code0, valid0);
+                        init_tile(t, t ? code1 : code0, t ? beam1 : beam0, rbn);
+                    }
                 }
+                primed = has_next;
             }
             // ---- out_proj chunks ---------------------------------------------------------------------------------------
             if (pl.has_proj) {
@@ -1005,23 +1048,9 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     }
                 }
             }
-            if (kScore) {   // the column groups of a row meet in shared memory
-                constexpr int kParts = kColGroups > 1 ? kColGroups - 1 : 1;       // dist_part[tile][part][row]
-                if (cg > 0) {
-                    sts1(a_dist + (uint32_t)((0 * kParts + cg - 1) * QB_TILE_M + r) * 4u, acc0);
-                    sts1(a_dist + (uint32_t)((1 * kParts + cg - 1) * QB_TILE_M + r) * 4u, acc1);
-                }
-                named_bar_sync(5, kEpiThreads);
-                if (cg == 0) {
-#pragma unroll
-                    for (int g = 0; g < kColGroups - 1; g++) {
-                        acc0 += lds1(a_dist + (uint32_t)((0 * kParts + g) * QB_TILE_M + r) * 4u);
-                        acc1 += lds1(a_dist + (uint32_t)((1 * kParts + g) * QB_TILE_M + r) * 4u);
-                    }
-                    if (valid0) p.dist[row0] = acc0;
-                    if (valid1) p.dist[row1] = acc1;
-                }
-                named_bar_sync(5, kEpiThreads);
+            if (pl.has_proj && kScore) {
+                publish_dist(0, acc0, row0, valid0);
+                if (NT > 1) publish_dist(1, acc1, row1, valid1);
             }
             if (kResident) mbar_arrive((a_rempty + (uint32_t)(rb) * 8u));
             tr.ev(8);

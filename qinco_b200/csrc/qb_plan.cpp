@@ -108,13 +108,12 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     int off = 0;
     for (int t = 0; t < 2; t++) { p->smem_ae[t] = off; if (t < n_tiles) off += ae_bytes; }
     // Resident tables (score launches with all K = 256 candidates per beam): a CTA then only ever works on ONE quarter of
-    // the codes (64 codes x 2 beams per tile), whose rows of T_m and of the skip codebook stay in shared memory instead
-    // of being gathered from L2 for every tile (the gathers cost as much L2->SM bandwidth as the weights).
+    // the codes (64 codes x 2 beams per tile), whose rows of T_m (registers) and of the skip codebook (shared memory) stay
+    // on the SM instead of being gathered from L2 for every tile (the gathers cost as much L2->SM bandwidth as the weights).
     p->smem_tres = -1;
-    if (n_tiles == 2 && !p->has_proj && K == 256 && (De + D) * 256 <= 64 * 1024 && budget - off - (De + D) * 256 >= 4 * 16384 &&
-        opt.no_resident == 0) {
+    if (n_tiles == 2 && !p->has_proj && K == 256 && De <= 128 && budget - off - D * 256 >= 4 * 16384 && opt.no_resident == 0) {
         p->smem_tres = off;
-        off += (De + D) * 256;
+        off += D * 256;          // the skip-codebook quarter; the T_m row slice of a thread (<= 64 columns) sits in registers
         if (opt.slot_bytes <= 0) p->slot_bytes = 16384;      // a deeper ring of smaller slabs fits next to the tables
     }
     p->smem_ring = off;
@@ -132,7 +131,9 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
         if (L > 0)
             for (int n0 = 0; n0 < De; n0 += epart) ok = ok && (std::min(epart, De - n0) % 32 == 0);
         if (opt.pair == 2 && !ok) { *err = "pair mode needs every down-projection width to be a multiple of 32"; return -1; }
-        p->pair = (opt.pair == 1) ? 0 : (ok ? 1 : 0);
+        // Auto = off: the pair kernel is validated (parity tests run it) but the extra cross-CTA signalling latency makes it
+        // slower than two independent CTAs while the hand-off chain, not weight traffic, bounds the kernel.
+        p->pair = (opt.pair == 2) ? 1 : 0;
     }
 
     // ---- op list ------------------------------------------------------------------------------------------------

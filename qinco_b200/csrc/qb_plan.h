@@ -77,8 +77,8 @@ struct QbStepPlan {
     int32_t tmem_tile_cols;  // columns per tile slot
     // shared memory carve-up (byte offsets from the 1024-aligned dynamic smem base)
     int32_t smem_ae[2];      // A_E per tile slot: [De/8][128][16B]
-    int32_t smem_tres;       // resident quarter of T_m ([De/4][64][4] fp32) followed by the same quarter of C_m ([D/4][64][4]),
-                             // or -1 when the shape does not qualify
+    int32_t smem_tres;       // resident quarter of C_m ([D/4][64][4] fp32; the T_m rows live in registers), or -1 when the
+                             // shape does not qualify
     int32_t smem_ring;       // ring of n_stage slots of slot_bytes
     int32_t slot_bytes;
     int32_t n_stage;

@@ -149,7 +149,7 @@ class QINCo:
         self.device = torch.device("cuda", idx)
         self._h = _lib.Handle(self.cfg, self._weights, device=idx, plan_opts=self._plan_opts)
         self.data_mean = torch.from_numpy(self._weights["data_mean"].copy()).to(self.device)
-        self.data_std = torch.tensor(float(self._weights["data_std"]), device=self.device)
+        self.data_std = torch.tensor(float(np.asarray(self._weights["data_std"]).reshape(-1)[0]), device=self.device)
         self._ws = None
         self.built = True
         return self

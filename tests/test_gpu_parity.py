@@ -35,6 +35,30 @@ def models(golden_loader):
         m._h.close()
 
 
+@pytest.mark.parametrize("name", ["s_a0_b1", "s_a16_b8", "proj_a8_b4", "l_a16_b16"])
+def test_cta_pair_kernel_matches_reference(name, golden_loader):
+    """The cta_group::2 variant of the MLP kernel (plan option pair = 2: one M = 256 MMA over two CTAs, half of every
+    weight slab per CTA) against the same reference outputs as the default kernel."""
+    from qinco_b200.model import QINCo
+    cfg, w, z = golden_loader(name)
+    model = QINCo(cfg, w, device="cuda:0", plan_opts={"n_tiles": 2 << 8})
+    try:
+        assert model._h.info(1)["pair"] == 1
+        codes_ref = torch.from_numpy(z["codes_ref"]).cuda()
+        dec = model(codes_ref, step="decode")
+        model.synchronize()
+        assert rel_mse(dec.cpu().numpy(), z["dec_ref"]) <= DEC_TOL
+        x = z["x"]
+        xn = (x - w["data_mean"]) / np.float32(w["data_std"])
+        c = model(torch.from_numpy(x).cuda(), step="encode").cpu().numpy()
+        model.synchronize()
+        agree = float((c == z["codes_ref"]).all(0).mean())
+        mse_ours, mse_ref = orc.mse(xn, orc.decode(cfg, w, c)), orc.mse(xn, z["xhat_ref"])
+        assert agree >= 0.8 and abs(mse_ours - mse_ref) <= ENC_TOL_SMALL * mse_ref, (agree, mse_ours, mse_ref)
+    finally:
+        model._h.close()
+
+
 def rel_mse(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-30))

@@ -199,11 +199,14 @@ SHAPES = {
 
 
 @pytest.mark.parametrize("name", list(SHAPES))
-@pytest.mark.parametrize("opts", [None, [64, 1, 8192, 3, 32], [0, 0, 32768, 0, 0], [0, 1 << 8, 0, 0, 0]])
+@pytest.mark.parametrize("opts", [None, [64, 1, 8192, 3, 32], [0, 0, 32768, 0, 0], [0, 2 << 8, 0, 0, 0]])
 def test_op_list_replay_matches_oracle(lib, name, opts):
     cfg = synth.make_cfg(None, **SHAPES[name])
     w = synth.make_weights(cfg, seed=3, n_train=512, kmeans_iters=1, fp16_exact=True)
+    if opts and opts[1] >> 8 == 2 and cfg["L"] > 0 and any(w % 32 for w in ([cfg["de"]] if cfg["de"] <= 256 else [cfg["de"] // 2])):
+        pytest.skip("CTA-pair mode needs down-projection widths that are multiples of 32")
     plan, ops = export_plan(lib, cfg, opts)
+    assert plan["pair"] == (1 if opts and opts[1] >> 8 == 2 else 0)
     # structural invariants of the plan
     assert plan["n_stage"] >= 2 and plan["n_tiles"] in (1, 2)
     assert plan["smem_total"] + 4096 <= 227 * 1024
