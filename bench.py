@@ -169,18 +169,121 @@ def run_reference(args, wl):
     }))
 
 
+def main_pairwise(args):
+    """--workload c5pw: the pairwise additive decoder at the Contriever shape of BASELINE
+    config 5 (d=768, 8x8 codes -> 16 tables of 65 536 rows, 3.2 GB).  HBM-bound gather-accumulate: the roofline block
+    is bytes, not flops."""
+    import torch
+    from qinco_b200.pairwise import PairwiseDecoderIVF
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    D, M, K, Mt, ivf_K = 768, 8, 256, 16, 4096
+    n = args.n or 500_000
+    g = torch.Generator().manual_seed(77)
+    book = torch.randn((Mt, K * K, D), generator=g, dtype=torch.float32)
+    comb = torch.stack([torch.randint(0, M + 5, (Mt,), generator=g), torch.randint(0, M + 5, (Mt,), generator=g)])
+    imap = torch.randint(0, K, (ivf_K, 5), generator=g)
+    dec = PairwiseDecoderIVF(dict(codebook_MKD=book, combine_mvals_m=comb, ivf_code_map=imap), K=K, M=M, device=dev)
+    g2 = torch.Generator().manual_seed(1234 + rank)
+    codes_h = torch.randint(0, K, (n, M), generator=g2, dtype=torch.uint8).pin_memory()
+    ivf_h = torch.randint(0, ivf_K, (n,), generator=g2, dtype=torch.int32).pin_memory()
+    codes, ivf = codes_h.to(dev), ivf_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        out = dec.decode_u8(codes, ivf)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = dec.launch_count
+    e0.record()
+    for _ in range(args.steps):
+        out = dec.decode_u8(codes, ivf)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    launches = dec.launch_count - l0
+    value = world * n * args.steps / (ms * 1e-3)
+    bytes_per_vec = Mt * D * 4 + D * 4 + M + 4
+    # end to end: host codes in, decoded vectors back on the host (what the search's re-ranking loop does per batch)
+    e2e = None
+    if not args.no_e2e:
+        ne = min(n, 65536)
+        out_pin = torch.empty((ne, D), dtype=torch.float32).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        k = max(1, min(args.steps, 3))
+        for _ in range(k):
+            o = dec.decode_u8(codes_h[:ne].to(dev, non_blocking=True), ivf_h[:ne].to(dev, non_blocking=True))
+            out_pin.copy_(o, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        e2e = {"value": world * ne * k / dt, "unit": "vectors/s", "h2d_bytes_per_step": ne * (M + 4), "d2h_bytes_per_step": ne * D * 4,
+               "api": "PairwiseDecoderIVF.decode_u8 on pinned host codes + copy of the decoded vectors back to the host", "steps": k}
+    if rank == 0:
+        peaks = load_peaks()
+        achieved = value / world * bytes_per_vec / 1e9
+        line = {"metric": "vectors/sec decoded (pairwise additive decoder, d=768, 16 tables of 65536 rows)", "value": value,
+                "unit": "vectors/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "pairwise decoder forward, Contriever shape of BASELINE config 5", "D": D, "M": M, "K": K,
+                           "tables": Mt, "ivf_K": ivf_K, "vectors_per_gpu_per_step": n, "table_bytes": dec.table_bytes,
+                           "l2": "table (3.2 GB) and outputs far larger than L2"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "qb_pairwise_kernel", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+                             "frac": achieved / peaks["hbm"], "traffic": None, "bytes_per_vector": bytes_per_vec,
+                             "peak_source": "MEASURED_PEAKS.json (hbm_gbs)" if "MEASURED" in peaks["source"] else peaks["source"]},
+                "clocks": clocks}
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import qinco_oracle as orc
+            ns = 20000
+            cm = codes_h[:ns].numpy().T.astype(np.int64)
+            t0 = time.perf_counter()
+            ref = orc.pairwise_decode(book.numpy(), comb.numpy(), imap.numpy(), K, cm, ivf_h[:ns].numpy())
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": ns / dt, "unit": "vectors/s", "cores": 1, "kind": "port",
+                                    "sample": f"first {ns} vectors, oracle/qinco_oracle.py pairwise_decode (numpy gather + add)"}
+            line["parity"] = {"sample": ns, "bit_identical": bool(np.array_equal(out[:ns].cpu().numpy(), ref))}
+        print(json.dumps(line))
+    dec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS) + ["c5pw"])
     ap.add_argument("--n", type=int, default=0, help="vectors per GPU per step (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--plan-opts", default="", help="kernel planner overrides, e.g. slot_bytes=8192,pair=1,hc=64,max_stage=4 (pair: 0 auto, 1 off, 2 on)")
     args = ap.parse_args()
+    if args.workload == "c5pw":
+        args.warmup = max(args.warmup, 3)
+        main_pairwise(args)
+        return
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
@@ -251,6 +354,29 @@ def main():
     ms = float(t.item())
     value = world * n * args.steps / (ms * 1e-3)
 
+    # ---- decode of the codes just produced (device resident): the matching fused gather + MLP + accumulate path
+    dec = None
+    if not args.no_decode:
+        model.decode_u8(codes, denormalize=True)
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k_dec = max(1, min(args.steps, 3))
+        d0.record()
+        for _ in range(k_dec):
+            xdec = model.decode_u8(codes, denormalize=True)
+        d1.record()
+        barrier()
+        td = torch.tensor([d0.elapsed_time(d1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dec_ms = float(td.item()) / k_dec
+        D_, De_, Dh_, L_, M_ = cfg["D"], cfg["de"], cfg["dh"], cfg["L"], cfg["M"]
+        dec_flops = 2 * (M_ - 1) * (2 * L_ * De_ * Dh_ + (D_ * De_ if De_ != D_ else 0) + D_ * De_)   # hoisted form, per vector
+        dec = {"value": world * n / (dec_ms * 1e-3), "unit": "vectors/s decoded", "ms_per_pass": dec_ms, "passes": k_dec,
+               "tflops": n / (dec_ms * 1e-3) * dec_flops / 1e12, "flops_per_vector": dec_flops,
+               "hbm_gbs_algorithmic": n / (dec_ms * 1e-3) * (4 * D_ + M_) / 1e9,
+               "mse_vs_input": float(((xdec[: min(n, 65536)] - x_dev[: min(n, 65536)]) ** 2).sum(1).mean().item())}
+
     # ---- end to end: pinned host buffers through the C-ABI host call (H2D + encode + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
@@ -305,6 +431,8 @@ def main():
         }
         if e2e:
             out["e2e"] = e2e
+        if dec:
+            out["decode"] = dec
         if world == 1 and not args.no_cpu_baseline:
             ns = min(n, 8192)
             rate, n_s, ref_codes, ref_xhat, threads, port = cpu_port_rate(cfg, w, x_host[:ns].numpy())

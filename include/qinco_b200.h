@@ -120,6 +120,30 @@ int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int
 int qb_plan_tables(int D, int De, int K, const float* codebook, const float* in_proj, const float* concat_w,
                    const float* concat_b, float* t_blk, float* cb_blk, float* wx_t);
 
+/* ---- Pairwise additive decoder, forward only ------------------------------------------
+ * Replaces PairwiseDecoderIVF.forward + map_codes (qinco/search/pairwise_decoder.py:88-93, :126-130), called by the IVF
+ * search's re-ranking stage (qinco/search/search_tasks.py:448-471).  Tables are the module's own tensors:
+ * codebook_MKD [Mt, K*K, D] fp32, combine_mvals_m [2, Mt] int64, ivf_code_map [ivf_K, 5] int64 (host pointers, copied). */
+typedef struct qb_pairwise qb_pairwise;
+typedef struct qb_pairwise_desc {
+    int32_t D, M, K;            /* vector dim, codes per vector (without the IVF code), base codebook size (<= 256) */
+    int32_t Mt;                 /* number of pairwise codebooks = round(n_pairwise_codebooks * M) */
+    int32_t ivf_K;              /* number of IVF centroids */
+    int32_t device;
+    const float* codebook;      /* [Mt][K*K][D] */
+    const int64_t* combine;     /* [2][Mt], entries in [0, M + 5) */
+    const int64_t* ivf_code_map;/* [ivf_K][5], entries in [0, K) */
+} qb_pairwise_desc;
+int qb_pairwise_create(const qb_pairwise_desc* desc, qb_pairwise** out);
+int qb_pairwise_destroy(qb_pairwise* h);
+/* forward(codes_MB, ivf_codes): codes_dev [n, M] uint8 row-major, ivf_codes_dev [n] int32 -> out_dev [n, D] fp32.
+ * Asynchronous on `stream`; bit-identical to the reference's fp32 sum (same order of additions). */
+int qb_pairwise_decode(qb_pairwise* h, const uint8_t* codes_dev, const int32_t* ivf_codes_dev, int64_t n, float* out_dev,
+                       void* stream);
+int qb_pairwise_check(qb_pairwise* h);                 /* device-side error word (out-of-range codes) */
+int64_t qb_pairwise_launch_count(const qb_pairwise* h);
+const char* qb_pairwise_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

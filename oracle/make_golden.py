@@ -106,6 +106,23 @@ def gen_v1():
     print(f"{name}: n={n} codes{codes.shape} mse_ref={mse_ref:g}")
 
 
+PAIRWISE_CASE = ("pairwise_ivf", dict(D=32, M=4, K=16, Mt=8, ivf_K=40), 77)
+
+
+def gen_pairwise():
+    import torch
+    name, kw, n = PAIRWISE_CASE
+    book, comb, imap = synth.make_pairwise_tables(seed=2024, **kw)
+    rng = np.random.default_rng(5)
+    codes = rng.integers(0, kw["K"], (kw["M"], n)).astype(np.int64)
+    ivf = rng.integers(0, kw["ivf_K"], n).astype(np.int64)
+    ref = ref_loader.build_pairwise(book, comb, imap, kw["K"])
+    with torch.no_grad():
+        out = ref(torch.from_numpy(codes), torch.from_numpy(ivf)).numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), cfg=json.dumps(kw), seed=2024, codes=codes, ivf_codes=ivf, out_ref=out)
+    print(f"{name}: n={n} out{out.shape}")
+
+
 if __name__ == "__main__":
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -115,3 +132,5 @@ if __name__ == "__main__":
             gen_case(name, kw, n, ms, ws)
     if not only or V1_CASE[0] in only:
         gen_v1()
+    if not only or PAIRWISE_CASE[0] in only:
+        gen_pairwise()

@@ -198,3 +198,17 @@ def codec_decode(cfg, w, codes, bs, db_scale=1.0):
 def mse(x, xhat):
     """mean over vectors of the squared error (qinco/utils.py:87-97)."""
     return float(((np.asarray(x, np.float64) - np.asarray(xhat, np.float64)) ** 2).sum(-1).mean())
+
+
+def pairwise_decode(codebook_MKD, combine_mvals_m, ivf_code_map, K_base, codes_MB, ivf_codes):
+    """PairwiseDecoderIVF.forward + map_codes (reference qinco/search/pairwise_decoder.py:88-93, :126-130), numpy fp32.
+
+    codes_MB [M, n] ints, ivf_codes [n] ints -> [n, D] float32; the rows are added in table order, like the reference."""
+    codes_MB = np.asarray(codes_MB, np.int64)
+    ext = np.concatenate([codes_MB, np.asarray(ivf_code_map, np.int64)[np.asarray(ivf_codes, np.int64)].T])   # :128
+    comb = ext[np.asarray(combine_mvals_m[0], np.int64)] * int(K_base) + ext[np.asarray(combine_mvals_m[1], np.int64)]   # :129
+    book = np.asarray(codebook_MKD, np.float32)
+    xhat = book[0][comb[0]].copy()                                                                               # :90
+    for j in range(1, book.shape[0]):
+        xhat += book[j][comb[j]]                                                                                 # :91-92
+    return xhat

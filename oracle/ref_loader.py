@@ -92,3 +92,32 @@ def v1_codec():
         sys.path.insert(0, v1)
     import codec_qinco
     return codec_qinco
+
+
+def pairwise_decoder_class():
+    """The reference's PairwiseDecoderIVF class (qinco/search/pairwise_decoder.py).  Its module imports qinco.metrics,
+    which subclasses torcheval.metrics.Metric at import time; torcheval is absent here and irrelevant to forward(), so a
+    stub module with an empty `Metric` base class satisfies the import."""
+    _stub_accelerate()
+    if "torcheval" not in sys.modules:
+        te, tm = types.ModuleType("torcheval"), types.ModuleType("torcheval.metrics")
+        tm.Metric = type("Metric", (object,), {})
+        te.metrics = tm
+        sys.modules["torcheval"], sys.modules["torcheval.metrics"] = te, tm
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    from qinco.search.pairwise_decoder import PairwiseDecoderIVF
+    return PairwiseDecoderIVF
+
+
+def build_pairwise(codebook_MKD, combine_mvals_m, ivf_code_map, K_base):
+    """An instance of the reference class with just the tensors forward()/map_codes() read (no cfg, no training)."""
+    import torch
+    cls = pairwise_decoder_class()
+    obj = cls.__new__(cls)
+    torch.nn.Module.__init__(obj)
+    obj.K_base = int(K_base)
+    obj.codebook_MKD = torch.nn.Parameter(torch.as_tensor(codebook_MKD), requires_grad=False)
+    obj.combine_mvals_m = torch.nn.Parameter(torch.as_tensor(combine_mvals_m), requires_grad=False)
+    obj.ivf_code_map = torch.nn.Parameter(torch.as_tensor(ivf_code_map), requires_grad=False)
+    return obj

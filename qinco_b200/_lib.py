@@ -21,7 +21,9 @@ STATUS = {0: "QB_OK", -1: "QB_ERR_INVALID", -2: "QB_ERR_CUDA", -3: "QB_ERR_WORKS
 # every symbol include/qinco_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ["qb_version", "qb_last_error", "qb_model_create", "qb_model_destroy", "qb_encode_workspace_bytes",
            "qb_decode_workspace_bytes", "qb_encode", "qb_decode", "qb_encode_host", "qb_decode_host", "qb_check",
-           "qb_launch_count", "qb_timing_enable", "qb_timing_read", "qb_model_info", "qb_debug_step", "qb_plan_export", "qb_plan_pack", "qb_plan_tables"]
+           "qb_launch_count", "qb_timing_enable", "qb_timing_read", "qb_model_info", "qb_debug_step", "qb_plan_export", "qb_plan_pack", "qb_plan_tables",
+           "qb_pairwise_create", "qb_pairwise_destroy", "qb_pairwise_decode", "qb_pairwise_check", "qb_pairwise_launch_count",
+           "qb_pairwise_last_error"]
 
 _fpp = C.POINTER(C.POINTER(C.c_float))
 
@@ -36,6 +38,13 @@ class QbModelDesc(C.Structure):
         ("opt_hc", C.c_int32), ("opt_n_tiles", C.c_int32), ("opt_slot_bytes", C.c_int32), ("opt_max_stage", C.c_int32),
         ("opt_max_slab_k", C.c_int32), ("opt_stagger", C.c_int32),
     ]
+
+
+class QbPairwiseDesc(C.Structure):
+    """Mirror of qb_pairwise_desc (include/qinco_b200.h)."""
+    _fields_ = [("D", C.c_int32), ("M", C.c_int32), ("K", C.c_int32), ("Mt", C.c_int32), ("ivf_K", C.c_int32),
+                ("device", C.c_int32), ("codebook", C.POINTER(C.c_float)), ("combine", C.POINTER(C.c_int64)),
+                ("ivf_code_map", C.POINTER(C.c_int64))]
 
 
 class QbError(RuntimeError):
@@ -82,6 +91,13 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.qb_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
     lib.qb_model_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.c_int]
     lib.qb_debug_step.argtypes = [vp, C.c_int, vp, vp, i64, vp, vp, sz, vp]
+    lib.qb_pairwise_create.argtypes = [C.POINTER(QbPairwiseDesc), C.POINTER(vp)]
+    lib.qb_pairwise_destroy.argtypes = [vp]
+    lib.qb_pairwise_decode.argtypes = [vp, vp, vp, i64, vp, vp]
+    lib.qb_pairwise_check.argtypes = [vp]
+    lib.qb_pairwise_launch_count.argtypes = [vp]
+    lib.qb_pairwise_launch_count.restype = i64
+    lib.qb_pairwise_last_error.restype = C.c_char_p
     _lib = lib
     return lib
 

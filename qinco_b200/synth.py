@@ -161,3 +161,15 @@ def from_v1_state(sd: dict) -> tuple[dict, dict]:
     w["data_mean"] = np.zeros((D,), np.float32)
     w["data_std"] = np.array(1.0, np.float32)
     return cfg, w
+
+
+def make_pairwise_tables(D, M, K, Mt, ivf_K, seed):
+    """Synthetic tables of the shapes PairwiseDecoderIVF holds after training (pairwise_decoder.py:73-86)."""
+    rng = np.random.default_rng(seed)
+    book = rng.standard_normal((Mt, K * K, D)).astype(np.float32)
+    comb = np.stack([rng.integers(0, M + 5, Mt), rng.integers(0, M + 5, Mt)]).astype(np.int64)
+    comb[:, 0] = (0, min(1, M + 4))
+    if Mt > 1:
+        comb[:, 1] = (M, M + 4)      # a pair made of IVF-derived codes only
+    imap = rng.integers(0, K, (ivf_K, 5)).astype(np.int64)
+    return book, comb, imap
