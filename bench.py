@@ -169,6 +169,12 @@ def run_reference(args, wl):
     }))
 
 
+def traffic_of(workload):
+    """Measured DRAM bytes per launch of the workload's dominant kernel (ncu --set full capture, profiles/traffic.json)."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(tp)).get(workload) if os.path.exists(tp) else None
+
+
 def main_pairwise(args):
     """--workload c5pw: the pairwise additive decoder at the Contriever shape of BASELINE
     config 5 (d=768, 8x8 codes -> 16 tables of 65 536 rows, 3.2 GB).  HBM-bound gather-accumulate: the roofline block
@@ -246,7 +252,7 @@ def main_pairwise(args):
                            "l2": "table (3.2 GB) and outputs far larger than L2"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "qb_pairwise_kernel", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
-                             "frac": achieved / peaks["hbm"], "traffic": None, "bytes_per_vector": bytes_per_vec,
+                             "frac": achieved / peaks["hbm"], "traffic": traffic_of("c5pw") if n == 500_000 else None, "bytes_per_vector": bytes_per_vec,
                              "peak_source": "MEASURED_PEAKS.json (hbm_gbs)" if "MEASURED" in peaks["source"] else peaks["source"]},
                 "clocks": clocks}
         if e2e:
@@ -405,10 +411,7 @@ def main():
         fl_launch = flops_min_per_candidate(cfg)
         achieved = rows_score * fl_launch / (ms_score * 1e-3) / 1e12 if ms_score > 0 else 0.0
         step_ms = {k: v[0] / args.steps for k, v in kinds.items()}
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(args.workload)
+        traffic = traffic_of(args.workload)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -1,0 +1,96 @@
+"""Command line of the reference's codec, on the B200 kernels.
+
+    python -m qinco_b200.cli --encode --model M.pt --i x.npy --o codes.npy [--raw] [--v2] [--A a --B b]
+    python -m qinco_b200.cli --decode --model M.pt --i codes.npy --o y.npy [--raw] [--v2]
+
+Same arguments and file formats as reference qinco_v1/codec_qinco.py:80-158 (`--encode/--decode --model --i --o --raw
+--batch_size --device --float16`).  `--v2` reads a QINCo2 checkpoint (qinco/utils.py:118-136) instead of a pickled v1
+module and, with `--o out.npz`, writes the encoded-database layout of task=encode (qinco/search/search_tasks.py:122-131).
+Hydra / accelerate orchestration is out of scope; multi-GPU runs use torchrun + qinco_b200.shard.
+"""
+from __future__ import annotations
+
+import argparse
+
+import numpy as np
+import torch
+
+from . import codec, io
+from .model import QINCo
+
+
+def build_parser():
+    ap = argparse.ArgumentParser(prog="qinco_b200.cli")
+    g = ap.add_argument_group("what to do")
+    g.add_argument("--encode", default=False, action="store_true")
+    g.add_argument("--decode", default=False, action="store_true")
+    g = ap.add_argument_group("files")
+    g.add_argument("--model", default="", help="QINCo model to use")
+    g.add_argument("--i", required=True, help="input vectors (npy or fvecs/bvecs format) / codes")
+    g.add_argument("--o", required=True, help="output (npy, raw, or .npz encoded database with --v2)")
+    g.add_argument("--raw", default=False, action="store_true", help="codes are in raw format (no header)")
+    g.add_argument("--v2", default=False, action="store_true", help="QINCo2 checkpoint (save_model dict) instead of a v1 module")
+    g = ap.add_argument_group("computation options")
+    g.add_argument("--batch_size", default=4096, type=int)
+    g.add_argument("--device", default="cuda:0")
+    g.add_argument("--float16", default=False, action="store_true", help="accepted for compatibility (operands are always fp16)")
+    g.add_argument("--A", type=int, default=None, help="v2: override the number of pre-selected candidates")
+    g.add_argument("--B", type=int, default=None, help="v2: override the beam width")
+    return ap
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    print("args:", args)
+    assert args.encode ^ args.decode, "one of encode or decode must be selected"
+    print("loading model", args.model)
+    if args.v2:
+        cfg, sd = io.load_v2_checkpoint(args.model, dict(A=args.A, B=args.B))
+        model = QINCo(cfg, sd, device=args.device)
+        M, K, D = cfg["M"], cfg["K"], cfg["D"]
+    else:
+        sd, db_scale = io.load_v1_checkpoint(args.model)
+        model = codec.QINCoV1(sd, db_scale=db_scale, device=args.device)
+        print("  database normalization factor", model.db_scale)
+        M, K, D = model.M, model.K, model.D
+    if args.encode:
+        print("reading", args.i)
+        x = io.read_vectors(args.i)
+        print(f"encoding intput vectors of size {x.shape}")
+        if args.v2:
+            codes_u8, _ = model._h.encode_host(np.ascontiguousarray(x, np.float32), normalize=True)
+            codes = codes_u8.astype(np.int64)
+        else:
+            codes = codec.encode(model, x, bs=args.batch_size, is_float16=args.float16)
+        if args.raw:
+            print(f"Packing result of size {codes.shape} to {M} * {int(np.ceil(np.log2(K)))} bits")
+            io.write_raw_codes(args.o, codes, K)
+        elif args.v2 and args.o.endswith(".npz"):
+            io.save_encoded_db(args.o, [codes], K=K, M=M, D=D)
+        else:
+            print(f"Storing result of size {codes.shape} in {args.o}")
+            np.save(args.o, codes)
+    else:
+        print("reading", args.i)
+        if args.raw:
+            codes = io.read_raw_codes(args.i, M, K)
+        elif args.i.endswith(".npz"):
+            codes, _ = io.load_encoded_db(args.i)
+        elif args.i.endswith(".npy"):
+            codes = np.load(args.i)
+        else:
+            raise RuntimeError("unrecognized format")
+        print(f"Decoding intput codes of size {codes.shape}")
+        if args.v2:
+            if codes.size and (codes.min() < 0 or codes.max() >= K):
+                raise IndexError(f"codes out of range [0, {K})")
+            y = model._h.decode_host(codes.astype(np.uint8), denormalize=True)
+        else:
+            y = codec.decode(model, codes, bs=args.batch_size, is_float16=args.float16)
+        print(f"Storing result of size {y.shape} in {args.o}")
+        np.save(args.o, y)
+    torch.cuda.synchronize()
+
+
+if __name__ == "__main__":
+    main()

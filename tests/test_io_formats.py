@@ -1,0 +1,122 @@
+"""Host-side formats: checkpoint dicts, encoded-database files, raw bit strings, vecs files."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from qinco_b200 import io, synth
+
+
+def test_bitstrings_known_answer_and_round_trip():
+    # faiss.pack_bitstrings semantics: value j at bits [j*nbits, (j+1)*nbits), least-significant bit first
+    codes = np.array([[1, 2, 3], [7, 0, 5]])
+    p = io.pack_bitstrings(codes, 3)
+    assert p.shape == (2, 2) and p.dtype == np.uint8
+    assert p.tolist() == [[1 | (2 << 3) | ((3 & 3) << 6), 3 >> 2], [7 | (0 << 3) | ((5 & 3) << 6), 5 >> 2]]
+    rng = np.random.default_rng(0)
+    for M, K in ((8, 256), (16, 256), (5, 100), (3, 2), (7, 1 << 12)):
+        nbits = int(np.ceil(np.log2(K)))
+        c = rng.integers(0, K, (37, M))
+        q = io.pack_bitstrings(c, nbits)
+        assert q.shape == (37, io.code_size_bytes(M, K))
+        assert np.array_equal(io.unpack_bitstrings(q, nbits, M), c)
+    with pytest.raises(AssertionError):
+        io.pack_bitstrings(np.array([[8]]), 3)
+
+
+def test_raw_and_encoded_db_files(tmp_path):
+    rng = np.random.default_rng(1)
+    codes = rng.integers(0, 256, (50, 8))
+    raw = str(tmp_path / "codes.raw")
+    io.write_raw_codes(raw, codes, 256)
+    assert os.path.getsize(raw) == 50 * 8
+    assert np.array_equal(io.read_raw_codes(raw, 8, 256), codes)
+    out = str(tmp_path / "db.npz")
+    io.save_encoded_db(out, [codes[:20], codes[20:]], K=256, M=8, D=128)
+    back, meta = io.load_encoded_db(out)
+    assert meta == dict(n_parts=2, K=256, M=8, D=128) and np.array_equal(back, codes) and back.dtype == np.int64
+    z = np.load(str(tmp_path / "db.part_1.npz"))
+    assert list(z.keys()) == ["codes"] and z["codes"].shape == (30, 8)
+
+
+def test_vecs_readers(tmp_path):
+    x = np.arange(24, dtype=np.float32).reshape(4, 6)
+    f = str(tmp_path / "x.fvecs")
+    np.concatenate([np.full((4, 1), 6, np.int32).view(np.float32), x], axis=1).tofile(f)
+    assert np.array_equal(io.read_vectors(f), x)
+    b = str(tmp_path / "x.bvecs")
+    xb = (np.arange(24) % 251).astype(np.uint8).reshape(4, 6)
+    np.concatenate([np.tile(np.array([6], np.int32).view(np.uint8), (4, 1)), xb], axis=1).tofile(b)
+    assert np.array_equal(io.read_vectors(b), xb.astype(np.float32))
+    n = str(tmp_path / "x.npy")
+    np.save(n, x.astype(np.float64))
+    assert io.read_vectors(n).dtype == np.float32
+
+
+def test_v2_checkpoint_dict(tmp_path):
+    """A file in the layout of save_model (qinco/utils.py:118-136) with legacy keys, read back like load_saved_model_data."""
+    cfg = synth.make_cfg(None, D=32, M=3, K=16, L=2, de=48, dh=64, A=4, B=2)
+    w = synth.make_weights(cfg, seed=1, n_train=256, kmeans_iters=1)
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in w.items()}
+    sd["steps.0.substep.codebook.weight"] = torch.zeros(16, 32)                       # dropped by the loader
+    sd["steps.1.residual_blocks.0.in_proj.weight"] = sd.pop("steps.1.in_proj.weight")    # legacy location
+    sd["steps.1.xtarget_mean"] = torch.zeros(32)                                      # training-only buffer, ignored later
+    path = str(tmp_path / "ckpt.pt")
+    torch.save({"epoch": 3, "model": sd, "optimizer": None, "scheduler": None, "logger": None,
+                "parameters": {"K": 16, "M": 3, "de": 48, "dh": 64, "L": 2, "A": 4, "B": 2, "ivf_in_use": False,
+                               "qinco1_mode": False}, "data_dim": 32}, path)
+    got_cfg, got_sd = io.load_v2_checkpoint(path, dict(B=8, A=None))
+    assert got_cfg == dict(D=32, M=3, K=16, L=2, de=48, dh=64, A=4, B=8, qinco1_mode=False)
+    assert "steps.0.substep.codebook.weight" not in got_sd and "steps.1.in_proj.weight" in got_sd
+    assert np.array_equal(got_sd["steps.2.codebook.weight"], np.asarray(w["steps.2.codebook.weight"]))
+    with pytest.raises(ValueError):      # A > 0 requested for a model trained with A = 0 (qinco/utils.py:166-169)
+        io.cfg_from_v2_checkpoint({"model": sd, "parameters": {"A": 0, "M": 3, "K": 16, "L": 2}, "data_dim": 32}, dict(A=8))
+    with pytest.raises(NotImplementedError):
+        io.cfg_from_v2_checkpoint({"model": sd, "parameters": {"ivf_in_use": True}, "data_dim": 32})
+    # parameters missing: shapes are inferred from the tensors
+    assert io.cfg_from_v2_checkpoint({"model": io.clean_v2_state_dict(sd)})["dh"] == 64
+
+
+def test_v1_checkpoint_state_dict(tmp_path):
+    cfg = synth.make_cfg(None, D=16, M=3, K=8, L=2, de=16, dh=24, A=0, B=1, qinco1_mode=True)
+    w = synth.make_weights(cfg, seed=2, n_train=128, kmeans_iters=1)
+    v1 = {k: torch.from_numpy(np.asarray(v)) for k, v in synth.to_v1_state(cfg, w).items()}
+    path = str(tmp_path / "v1.pt")
+    torch.save({"state_dict": v1, "db_scale": 2.5}, path)
+    sd, scale = io.load_v1_checkpoint(path)
+    assert scale == 2.5
+    cfg2, w2 = synth.from_v1_state(sd)
+    assert cfg2["M"] == 3 and cfg2["L"] == 2 and cfg2["dh"] == 24
+    assert np.array_equal(w2["steps.1.concat.mlp.weight"], np.asarray(w["steps.1.concat.mlp.weight"]))
+
+
+@pytest.mark.gpu
+def test_cli_round_trip(tmp_path):
+    """--encode / --decode through the CLI, v1 (npy + raw) and v2 (encoded database) formats."""
+    from qinco_b200 import cli
+    cfg = synth.make_cfg(None, D=32, M=4, K=64, L=1, de=32, dh=32, A=0, B=1, qinco1_mode=True)
+    w = synth.make_weights(cfg, seed=5, n_train=1024, kmeans_iters=1)
+    x = synth.make_data(300, 32, seed=9)
+    xin = str(tmp_path / "x.npy")
+    np.save(xin, x)
+    m1 = str(tmp_path / "v1.pt")
+    torch.save({"state_dict": {k: torch.from_numpy(np.asarray(v)) for k, v in synth.to_v1_state(cfg, w).items()}, "db_scale": 1.0}, m1)
+    cli.main(["--encode", "--model", m1, "--i", xin, "--o", str(tmp_path / "c.npy")])
+    cli.main(["--encode", "--model", m1, "--i", xin, "--o", str(tmp_path / "c.raw"), "--raw"])
+    c = np.load(str(tmp_path / "c.npy"))
+    assert c.shape == (300, 4) and np.array_equal(io.read_raw_codes(str(tmp_path / "c.raw"), 4, 64), c)
+    cli.main(["--decode", "--model", m1, "--i", str(tmp_path / "c.raw"), "--o", str(tmp_path / "y.npy"), "--raw"])
+    y = np.load(str(tmp_path / "y.npy"))
+    assert y.shape == (300, 32) and ((y - x) ** 2).sum() < (x ** 2).sum()
+    cfg2 = synth.make_cfg(None, D=32, M=4, K=64, L=1, de=32, dh=32, A=8, B=4)
+    w2 = synth.make_weights(cfg2, seed=6, n_train=1024, kmeans_iters=1)
+    m2 = str(tmp_path / "v2.pt")
+    torch.save({"model": {k: torch.from_numpy(np.asarray(v)) for k, v in w2.items()},
+                "parameters": {k: cfg2[k] for k in ("K", "M", "de", "dh", "L", "A", "B", "qinco1_mode")}, "data_dim": 32}, m2)
+    cli.main(["--encode", "--v2", "--model", m2, "--i", xin, "--o", str(tmp_path / "db.npz")])
+    codes, meta = io.load_encoded_db(str(tmp_path / "db.npz"))
+    assert codes.shape == (300, 4) and meta["K"] == 64 and meta["D"] == 32
+    cli.main(["--decode", "--v2", "--model", m2, "--i", str(tmp_path / "db.npz"), "--o", str(tmp_path / "y2.npy")])
+    y2 = np.load(str(tmp_path / "y2.npy"))
+    assert y2.shape == (300, 32) and ((y2 - x) ** 2).sum() < (x ** 2).sum()
