@@ -44,6 +44,10 @@ CASES = {
     "proj_a8_b4":     (dict(D=96, M=4, K=256, L=3, de=192, dh=160, A=8, B=4, qinco1_mode=False), 40, (0.25, 1.5), 24),
     "q1_l4":          (dict(D=128, M=4, K=256, L=4, de=128, dh=256, A=0, B=1, qinco1_mode=True), 32, (0.0, 1.0), 25),
     "l_a16_b16":      (dict(D=128, M=4, K=256, L=4, de=384, dh=384, A=16, B=16, qinco1_mode=False), 16, (0.0, 1.0), 26),
+    # IVF-QINCo: step 0 = arg-min over ivf_K centroids, then M implicit-codebook steps; codes [M+1, n]
+    "ivf_a8_b4":      (dict(D=32, M=3, K=64, L=2, de=32, dh=48, A=8, B=4, qinco1_mode=False, ivf_K=200), 96, (0.25, 1.5), 31),
+    "ivf_a4_b8":      (dict(D=32, M=3, K=64, L=1, de=48, dh=32, A=4, B=8, qinco1_mode=False, ivf_K=77), 64, (0.0, 1.0), 32),
+    "ivf_a0_b1":      (dict(D=128, M=3, K=256, L=2, de=128, dh=256, A=0, B=1, qinco1_mode=False, ivf_K=1000), 48, (0.0, 1.0), 33),
 }
 V1_CASE = ("v1_codec", dict(D=128, M=8, K=256, L=2, de=128, dh=256, A=0, B=1, qinco1_mode=True), 96, 3.5, 31)
 
@@ -70,7 +74,7 @@ def gen_case(name, kw, n, mean_std, wseed):
         enc_dec_gap = float((model.decode(codes) - xhat).abs().max())
         assert enc_dec_gap <= 1e-4 * float(xhat.abs().max()), enc_dec_gap
     wrap_equal = -1
-    if cfg["A"] > 0 or cfg["B"] == 1:      # the wrapper's A=0 encoder assumes B=1 (qinco_inference.py:126)
+    if (cfg["A"] > 0 or cfg["B"] == 1) and not cfg.get("ivf_K"):      # the wrapper's A=0 encoder assumes B=1 (qinco_inference.py:126)
         wrap = ref_loader.build_v2(cfg, w, inference=True)
         with torch.no_grad():
             wrap_equal = int(torch.equal(wrap(xt, step="encode"), codes))

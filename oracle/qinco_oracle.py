@@ -90,12 +90,21 @@ def step_mlp(cfg, w, m, c, xhat):
 # ---------------------------------------------------------------------------
 # decode (qinco_base.py:447-452, 282-290; qinco_inference.py:66-75; v1 model_qinco.py:91-95)
 # ---------------------------------------------------------------------------
+def n_steps(cfg):
+    """Number of quantisation steps = rows of the code matrix: cfg._M_ivf = M (+1 with an IVF first step)."""
+    return cfg["M"] + (1 if cfg.get("ivf_K") else 0)
+
+
 def decode(cfg, w, codes_MB):
-    """codes [M, n] int -> xhat [n, D] fp32, normalised space."""
+    """codes [M_ivf, n] int -> xhat [n, D] fp32, normalised space."""
     codes_MB = np.asarray(codes_MB).astype(np.int64)
-    assert codes_MB.shape[0] == cfg["M"]
-    xhat = w["steps.0.codebook.weight"][codes_MB[0]].astype(np.float32)
-    for m in range(1, cfg["M"]):
+    S = n_steps(cfg)
+    assert codes_MB.shape[0] == S
+    if cfg.get("ivf_K"):                                 # IVFBook.decode (qinco_base.py:176-183): centroid lookup
+        xhat = w["steps.0.ivf_centroids.weight"][codes_MB[0]].astype(np.float32)
+    else:
+        xhat = w["steps.0.codebook.weight"][codes_MB[0]].astype(np.float32)
+    for m in range(1, S):
         c = w[f"steps.{m}.codebook.weight"][codes_MB[m]]
         xhat = xhat + step_mlp(cfg, w, m, c, xhat)
     return xhat
@@ -106,9 +115,13 @@ def decode(cfg, w, codes_MB):
 # ---------------------------------------------------------------------------
 def _encode_step(cfg, w, m, x, xhat_BFD, hist):
     """One beam step.  x:[n,D]; xhat_BFD:[n,F,D]; hist: list of [n,F] int64 (one per earlier step)."""
-    K, D, M, A, Bw = cfg["K"], cfg["D"], cfg["M"], cfg["A"], cfg["B"]
+    K, D, M, A, Bw = cfg["K"], cfg["D"], n_steps(cfg), cfg["A"], cfg["B"]
     n, F_in, _ = xhat_BFD.shape
-    F_out = Bw if m < M - 1 else 1                       # qinco_base.py:310
+    F_out = Bw if m < M - 1 else 1                       # qinco_base.py:310 (M = cfg._M_ivf)
+    if m == 0 and cfg.get("ivf_K"):                      # IVFBook.encode / quantize (qinco_base.py:148-174): F = 1, arg-min
+        cent = w["steps.0.ivf_centroids.weight"]
+        codes = approx_pairwise_distance(x, cent).argmin(-1)
+        return cent[codes].reshape(n, 1, D).astype(np.float32), [codes.reshape(n, 1).astype(np.int64)]
     cb = w[f"steps.{m}.codebook.weight"]
     if m == 0:                                           # codebook_only (:218,:263): candidates are raw codewords
         cand = np.broadcast_to(cb[None, None], (n, F_in, K, D)) + xhat_BFD[:, :, None, :]
@@ -116,7 +129,7 @@ def _encode_step(cfg, w, m, x, xhat_BFD, hist):
         C = K
     else:
         if A > 0:                                        # :316-324, substep :114-121
-            n_codes = A
+            n_codes = max(A, Bw) if (m == 1 and cfg.get("ivf_K")) else A   # qinco_base.py:108-112
             r = (x[:, None, :] - xhat_BFD).reshape(n * F_in, D)
             d_pre = pairwise_distances(r, w[f"steps.{m}.substep.codebook.weight"])
             idx = topk_smallest(d_pre, n_codes).reshape(n, F_in, n_codes)
@@ -148,13 +161,13 @@ def encode(cfg, w, x, max_rows=65536):
     n = len(x)
     per_vec = cfg["B"] * (cfg["A"] or cfg["K"])
     bs = max(1, max_rows // per_vec)
-    codes = np.empty((cfg["M"], n), np.int64)
+    codes = np.empty((n_steps(cfg), n), np.int64)
     xhat = np.empty((n, cfg["D"]), np.float32)
     for i0 in range(0, n, bs):
         xb = x[i0:i0 + bs]
         xh = np.zeros((len(xb), 1, cfg["D"]), np.float32)  # :475
         hist = []
-        for m in range(cfg["M"]):
+        for m in range(n_steps(cfg)):
             xh, hist = _encode_step(cfg, w, m, xb, xh, hist)
         assert xh.shape[1] == 1                            # :480-482
         codes[:, i0:i0 + bs] = np.stack([h[:, 0] for h in hist])

@@ -51,15 +51,19 @@ def build_v2(cfg: dict, weights: dict, inference: bool = False):
 
     c = SharedCfgState(dict(
         task="eval", M=cfg["M"], K=cfg["K"], L=cfg["L"], de=cfg["de"], dh=cfg["dh"], A=cfg["A"], B=cfg["B"],
-        qinco1_mode=cfg["qinco1_mode"], enc_max_bs=65536, ivf_in_use=False, batch=64, codebook_noise_init=0.0,
+        qinco1_mode=cfg["qinco1_mode"], enc_max_bs=65536, ivf_in_use=bool(cfg.get("ivf_K")), batch=64, codebook_noise_init=0.0,
+        ivf_K=cfg.get("ivf_K"),
     ))
     c._accelerator = _FakeAccelerator()
     c._D = cfg["D"]
-    c._M_ivf = cfg["M"]
-    c._K_vals = [cfg["K"]] * cfg["M"]
+    c._M_ivf = cfg["M"] + (1 if cfg.get("ivf_K") else 0)        # qinco/qinco_tasks.py:378-383
+    c._K_vals = ([cfg["ivf_K"]] if cfg.get("ivf_K") else []) + [cfg["K"]] * cfg["M"]
     c._ivf_book = None
     c._qinco_jit = False
     with torch.no_grad():
+        if cfg.get("ivf_K"):
+            from qinco.model.qinco_base import IVFBook
+            c._ivf_book = IVFBook(c, weights["steps.0.ivf_centroids.weight"])
         model = QINCo(c)
         sd = {k: torch.from_numpy(v.copy()) for k, v in weights.items()}
         missing, unexpected = model.load_state_dict(sd, strict=False)

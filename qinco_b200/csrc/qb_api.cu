@@ -426,7 +426,7 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
     opt.slot_bytes = d->opt_slot_bytes;
     if (opt.pair == 0)
         if (const char* e = getenv("QB_PAIR")) opt.pair = atoi(e);   // debug / A-B runs: 1 = single-CTA kernel, 2 = force pairs
-    opt.max_stage = d->opt_max_stage & 0xff; opt.no_resident = d->opt_max_stage >> 8; opt.max_slab_k = d->opt_max_slab_k;
+    opt.max_stage = d->opt_max_stage & 0xff; opt.no_resident = (d->opt_max_stage >> 8) & 1; opt.no_hsplit = (d->opt_max_stage >> 9) & 1; opt.max_slab_k = d->opt_max_slab_k;
     int max_smem = 0;
     for (int s = 1; s < m->M; s++) {
         StepDev& sd = m->steps[s];

@@ -466,6 +466,23 @@ __device__ __forceinline__ void acc_to_tmem_operand(uint32_t taddr, int c0, int 
     tmem_wait_st();
 }
 
+// One K half of a split H chunk (width 2 * kColGroups * 32 = 128... in general cw, a multiple of 64): fp32 columns
+// [h * cw/2 + cg * cw/4, + cw/4) of this thread's row -> relu -> packed fp16 written at columns [(h * cw/2 + cg * cw/4) / 2, ...).
+// The packed block of the upper column group lands on fp32 columns the lower group reads in the same half, hence the
+// barrier between the loads and the stores; across halves the targets of half 1 were all read in half 0.
+__device__ __forceinline__ void acc_to_tmem_operand_half(uint32_t taddr, int c0, int n, int quarter_bar) {
+    uint32_t va[32];          // n = 16 or 32 columns
+    tmem_ld_cols(taddr + c0, n, va);
+    tmem_wait_ld();
+    named_bar_sync(quarter_bar, kColGroups * 32);
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) w[j] = pack_h2_relu(__uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
+    __syncwarp();
+    if (n >= 32) tmem_st16(taddr + (c0 >> 1), w); else tmem_st8(taddr + (c0 >> 1), w);
+    tmem_wait_st();
+}
+
 // Debug event log (MlpParams::trace, CTA 0 only): role 0 = epilogue thread 0, 1 = MMA issuer, 2 = producer.
 struct Tracer {
     unsigned long long* buf;
@@ -529,6 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             mbar_init(smem_u32(&bars[t][QB_BAR_AE_READY]), (kPair ? 2 : 1) * kEpiWarps);
             mbar_init(smem_u32(&bars[t][QB_BAR_AH_READY]), (kPair ? 2 : 1) * kEpiWarps);
             mbar_init(smem_u32(&bars[t][QB_BAR_HACC_FREE]), (kPair ? 2 : 1) * kEpiWarps);
+            mbar_init(smem_u32(&bars[t][QB_BAR_AH2_READY]), (kPair ? 2 : 1) * kEpiWarps);
             mbar_init(smem_u32(&bars[t][QB_BAR_HACC_FULL]), 1);
             mbar_init(smem_u32(&bars[t][QB_BAR_EACC_FULL]), 1);
         }
@@ -688,7 +706,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         uint32_t acc = op.accumulate;
                         int k16_left = op.k_total >> 4;
                         const uint32_t commit_bar = op.commit;
-                        const uint32_t wa = op.wait_a, wd = op.wait_d;
+                        const uint32_t wa = op.wait_a, wd = op.wait_d, wa2_slab = op.wait_a2_slab;
                         for (uint32_t s = 0; s < n_slab; s++) {
                             const int nk = k16_left < ks16 ? k16_left : ks16;
                             k16_left -= ks16;
@@ -708,6 +726,10 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                                 }
                                 if (wa | wd) tc_fence_after();   // orders the epilogue's tcgen05.st / ld before these MMAs
                                 tr.ev(0x200 + i);
+                            } else if (s == wa2_slab) {     // (wa2_slab != 0) second K half of a split H chunk
+                                mbar_wait(bar_addr(t, QB_BAR_AH2_READY), (par >> QB_BAR_AH2_READY) & 1, p.err_flag, 0x200 + QB_BAR_AH2_READY);
+                                par ^= 1u << QB_BAR_AH2_READY;
+                                tc_fence_after();
                             }
                             if (elect_one()) {
                                 uint32_t a_l = a_cur, b_l = b_lo;      // cursors local to the issuing lane (the warp-wide ones advance below)
@@ -967,8 +989,19 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     for (int t = 0; t < NT; t++) {
                         wait_bar(t, QB_BAR_HACC_FULL, 0x404);
                         tr.ev(3 + 0x80 * t);
-                        acc_to_tmem_operand(lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col, c0, c1, 1 + q);
-                        arrive_issuer(t, QB_BAR_AH_READY, false);
+                        const uint32_t th = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
+                        if (kColGroups == 2 && pl.h_split && cw == pl.hc && (cw >> 2) <= 32) {
+                            // two K halves, each split over the two column groups: the down-projection starts on the
+                            // first half while the second is converted
+                            const int qw = cw >> 2;
+                            acc_to_tmem_operand_half(th, cg * qw, qw, 1 + q);
+                            arrive_issuer(t, QB_BAR_AH_READY, false);
+                            acc_to_tmem_operand_half(th, (cw >> 1) + cg * qw, qw, 1 + q);
+                            arrive_issuer(t, QB_BAR_AH2_READY, false);
+                        } else {
+                            acc_to_tmem_operand(th, c0, c1, 1 + q);
+                            arrive_issuer(t, QB_BAR_AH_READY, false);
+                        }
                         tr.ev(4 + 0x80 * t);
                     }
                 }

@@ -140,11 +140,18 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     ops->clear();
     uint32_t w_off = 0;
     // GEMM  D[128, n] (+)= A[128, k_total] . W[rows n][cols k_total]^T, W cut along K into ring-slot-sized slabs
+    // H chunks of the full width hc (a multiple of 64) are handed over in two K halves: the down-projection starts on
+    // the first half while the epilogue still converts the second (shortens the per-tile dependency chain)
+    p->h_split = (opt.no_hsplit == 0 && L > 0 && hc % 64 == 0 && hc >= 64) ? 1 : 0;
     auto emit_gemm = [&](int n, int k_total, uint8_t a_src, int a_unit0, int d_col, bool acc_first,
-                         uint8_t wait_a, uint8_t wait_d, uint8_t commit) {
+                         uint8_t wait_a, uint8_t wait_d, uint8_t commit, bool split_k = false) {
         int ks = ((p->pair ? 2 : 1) * p->slot_bytes / (2 * n)) / 16 * 16;   // a pair CTA holds half the rows of a slab
         if (opt.max_slab_k > 0) ks = std::min(ks, opt.max_slab_k);
         ks = std::max(16, std::min(ks, k_total));
+        if (split_k) {       // slabs must end on the half boundary: the largest multiple of 16 <= ks dividing k_total / 2
+            const int half = k_total / 2;
+            while (half % ks) ks -= 16;
+        }
         const int n_slab = (k_total + ks - 1) / ks;
         QbOp op;
         std::memset(&op, 0, sizeof(op));
@@ -155,6 +162,7 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
         op.a_off = (uint16_t)a_unit0; op.d_col = (uint16_t)d_col;
         op.n_slab = (uint8_t)n_slab; op.a_src = a_src; op.accumulate = acc_first ? 1 : 0;
         op.wait_a = wait_a; op.wait_d = wait_d; op.commit = commit;
+        op.wait_a2_slab = (split_k && wait_a) ? (uint8_t)((k_total / 2) / ks) : 0;
         w_off += (uint32_t)(n * k_total * 2);
         ops->push_back(op);
     };
@@ -171,7 +179,8 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
                 const int n = std::min(epart, De - n0);
                 const bool last = (j == p->n_hchunk - 1) && (n0 + n >= De);
                 emit_gemm(n, cw, QB_A_H, p->tmem_h_col, p->tmem_e_col + n0, true,
-                          n0 == 0 ? QB_BAR_AH_READY : QB_BAR_NONE, QB_BAR_NONE, last ? QB_BAR_EACC_FULL : QB_BAR_NONE);
+                          n0 == 0 ? QB_BAR_AH_READY : QB_BAR_NONE, QB_BAR_NONE, last ? QB_BAR_EACC_FULL : QB_BAR_NONE,
+                          p->h_split && cw == hc);
             }
         }
     }
@@ -276,7 +285,7 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
     qb::PlanOptions opt;
     if (opts5) {
         opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = opts5[1] >> 8; opt.slot_bytes = opts5[2];
-        opt.max_stage = opts5[3] & 0xff; opt.no_resident = opts5[3] >> 8; opt.max_slab_k = opts5[4];
+        opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
     std::vector<QbOp> ops;
@@ -285,7 +294,7 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
     const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_tiles, p.tmem_alloc_cols,
                          p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk, p.oc, p.n_ochunk, p.tmem_e_col, p.tmem_h_col,
                          p.tmem_tile_cols, p.smem_tres, p.smem_ring, p.slot_bytes, p.n_stage, p.smem_total,
-                         (int32_t)p.block_w_bytes, (int32_t)p.w_blob_bytes, p.pair};
+                         (int32_t)p.block_w_bytes, (int32_t)p.w_blob_bytes, p.pair, p.h_split};
     const int nv = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < nv && i < n_plan_out; i++) plan_out[i] = v[i];
     if ((int)ops.size() > max_ops) return -2;
@@ -298,7 +307,7 @@ int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int
     qb::PlanOptions opt;
     if (opts5) {
         opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = opts5[1] >> 8; opt.slot_bytes = opts5[2];
-        opt.max_stage = opts5[3] & 0xff; opt.no_resident = opts5[3] >> 8; opt.max_slab_k = opts5[4];
+        opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
     std::vector<QbOp> ops;

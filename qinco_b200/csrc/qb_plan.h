@@ -37,7 +37,9 @@ enum QbBar : uint8_t {
     QB_BAR_HACC_FREE = 3,   // epilogue finished reading an out_proj chunk from Hacc        count 128
     QB_BAR_HACC_FULL = 4,   // MMA -> epilogue (tcgen05.commit)                             count 1
     QB_BAR_EACC_FULL = 5,
-    QB_BAR_COUNT = 6
+    QB_BAR_AH2_READY = 6,   // second K half of a split H chunk is in TMEM (its own barrier: with one barrier the epilogue
+                            // could complete two phases before the issuer looks, and a parity wait cannot see that)
+    QB_BAR_COUNT = 7
 };
 
 struct QbOp {
@@ -56,7 +58,8 @@ struct QbOp {
     uint8_t wait_a;      // QbBar to wait on before issuing (A operand ready), or NONE
     uint8_t wait_d;      // QbBar to wait on before issuing (accumulator free), or NONE
     uint8_t commit;      // QbBar to tcgen05.commit to after the GEMM, or NONE
-    uint8_t pad[4];
+    uint8_t wait_a2_slab; // != 0: wait on QB_BAR_AH2_READY before this slab (the A operand arrives in two K halves)
+    uint8_t pad[3];
 };
 static_assert(sizeof(QbOp) == 32, "QbOp must stay 32 bytes");
 
@@ -83,6 +86,8 @@ struct QbStepPlan {
     int32_t slot_bytes;
     int32_t n_stage;
     int32_t smem_total;
+    int32_t h_split;         // 1: a full-width H chunk is converted and handed to the MMA issuer in two K halves (two
+                             // arrivals on AH_READY per chunk; the down-projection's slabs end on the half boundary)
     int32_t pair;            // 1: CTA-pair kernel (cta_group::2, M = 256 over two CTAs): every slab is packed as two row
                              // halves, CTA r of a pair streams half r into a ring slot of slot_bytes
     int64_t block_w_bytes;   // packed weight bytes of one residual block

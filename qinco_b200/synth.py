@@ -41,6 +41,10 @@ def make_cfg(preset: str | None = None, *, D: int, **over) -> dict:
     for k in ("L", "dh", "A", "B", "M", "K"):
         cfg[k] = int(cfg[k])
     cfg["qinco1_mode"] = bool(cfg["qinco1_mode"])
+    if cfg.get("ivf_K"):        # IVF-QINCo: step 0 is an arg-min over ivf_K centroids, then M implicit-codebook steps
+        cfg["ivf_K"] = int(cfg["ivf_K"])
+    else:
+        cfg.pop("ivf_K", None)
     return cfg
 
 
@@ -81,6 +85,8 @@ def make_weights(cfg: dict, seed: int = 4321, gain: float = 0.5, n_train: int = 
     fp16-operand CUDA path and the fp32 oracle see identical weights.
     """
     D, M, K, L, De, Dh, A = (cfg[k] for k in ("D", "M", "K", "L", "de", "dh", "A"))
+    ivf_K = int(cfg.get("ivf_K") or 0)
+    n_steps = M + 1 if ivf_K else M          # reference cfg._M_ivf (qinco/qinco_tasks.py:378-383)
     rng = np.random.default_rng(seed)
     w: dict[str, np.ndarray] = {}
 
@@ -93,7 +99,13 @@ def make_weights(cfg: dict, seed: int = 4321, gain: float = 0.5, n_train: int = 
     # plain residual k-means for the explicit codebooks (and their pre-selection twins)
     xt = rng.standard_normal((n_train, D), dtype=np.float32)
     resid = xt
-    for m in range(M):
+    for m in range(n_steps):
+        if ivf_K and m == 0:                 # frozen IVF centroids (qinco_base.py:128-146), key as in IVFBook
+            cb = _kmeans(resid, ivf_K, kmeans_iters, rng).astype(np.float32)
+            cb += rng.standard_normal(cb.shape, dtype=np.float32) * np.float32(0.02 * cb.std())
+            w["steps.0.ivf_centroids.weight"] = cb
+            resid = resid - cb[_sqdist(resid, cb).argmin(1)]
+            continue
         cb = _kmeans(resid, K, kmeans_iters, rng).astype(np.float32)
         # empty-cluster re-seeding can duplicate a codeword, and exact duplicates are exact ties whose
         # winner is a topk implementation detail: jitter so all K codewords are distinct

@@ -36,6 +36,10 @@ GOLDEN_V2 = ["tiny_q1", "tiny_a0_b1", "tiny_a8_b4", "tiny_a0_b4", "s_a0_b1", "s_
              "proj_a8_b4", "q1_l4", "l_a16_b16"]
 
 
+# IVF-QINCo fixtures: code matrices have M + 1 rows, row 0 = the IVF code
+GOLDEN_IVF = ["ivf_a8_b4", "ivf_a4_b8", "ivf_a0_b1"]
+
+
 @pytest.fixture(scope="session")
 def golden_loader():
     cache = {}

@@ -16,10 +16,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 OP_DTYPE = np.dtype([("w_off", "<u4"), ("slab_bytes", "<u4"), ("last_bytes", "<u4"), ("n", "<u2"), ("ks", "<u2"),
                      ("k_total", "<u2"), ("a_off", "<u2"), ("d_col", "<u2"), ("n_slab", "u1"), ("a_src", "u1"),
-                     ("accumulate", "u1"), ("wait_a", "u1"), ("wait_d", "u1"), ("commit", "u1"), ("pad", "u1", 4)])
+                     ("accumulate", "u1"), ("wait_a", "u1"), ("wait_d", "u1"), ("commit", "u1"), ("wait_a2_slab", "u1"),
+                     ("pad", "u1", 3)])
 PLAN_FIELDS = ["D", "De", "Dh", "L", "K", "has_proj", "skip", "n_tiles", "tmem_alloc_cols", "n_ops_block", "n_ops_out",
                "hc", "n_hchunk", "oc", "n_ochunk", "tmem_e_col", "tmem_h_col", "tmem_tile_cols", "smem_tres", "smem_ring",
-               "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes", "pair"]
+               "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes", "pair", "h_split"]
 A_E, A_H = 0, 1
 BAR_AE_READY, BAR_AH_READY, BAR_HACC_FREE, BAR_HACC_FULL, BAR_EACC_FULL = 1, 2, 3, 4, 5
 
@@ -138,6 +139,9 @@ def replay(plan, ops, blob, T, CB, WxT, codes, xhat):
         if pair:       # cta_group::2 shapes: N % 16 with A in shared memory, N % 32 with A in TMEM
             assert nn % (32 if op["a_src"] == A_H else 16) == 0
         assert op["n_slab"] == -(-kt // ks) and op["last_bytes"] == nn * (kt - (int(op["n_slab"]) - 1) * ks) * 2
+        if op["wait_a2_slab"]:     # H chunk handed over in two K halves: the second wait sits exactly on the half boundary
+            assert plan["h_split"] and op["a_src"] == A_H and op["wait_a"] == BAR_AH_READY
+            assert int(op["wait_a2_slab"]) * ks == kt // 2 and kt == plan["hc"]
         c0 = int(op["d_col"])
         acc = bool(op["accumulate"])
         for s in range(int(op["n_slab"])):
@@ -199,7 +203,7 @@ SHAPES = {
 
 
 @pytest.mark.parametrize("name", list(SHAPES))
-@pytest.mark.parametrize("opts", [None, [64, 1, 8192, 3, 32], [0, 0, 32768, 0, 0], [0, 2 << 8, 0, 0, 0]])
+@pytest.mark.parametrize("opts", [None, [64, 1, 8192, 3, 32], [0, 0, 32768, 0, 0], [0, 2 << 8, 0, 0, 0], [0, 0, 0, 2 << 8, 0]])
 def test_op_list_replay_matches_oracle(lib, name, opts):
     cfg = synth.make_cfg(None, **SHAPES[name])
     w = synth.make_weights(cfg, seed=3, n_train=512, kmeans_iters=1, fp16_exact=True)

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_V2
+from conftest import GOLDEN_IVF, GOLDEN_V2
 from oracle import qinco_oracle as orc
 
 
@@ -96,4 +96,20 @@ def test_torch_port_matches_reference(name, golden_loader):
     codes = port.forward(z["x"], "encode").numpy()
     np.testing.assert_array_equal(codes, z["codes_ref"])
     dec = port.forward(z["codes_ref"], "decode").numpy()
+    assert ((dec - z["dec_ref"]) ** 2).sum() / (z["dec_ref"] ** 2).sum() <= 1e-10
+
+
+@pytest.mark.parametrize("name", GOLDEN_IVF)
+def test_ivf_model_matches_reference(name, golden_loader):
+    """IVF-QINCo (IVFBook first step, qinco_base.py:128-196; step 1 pre-selects max(A, B) candidates, :108-112):
+    the oracle returns the unmodified reference's codes (row 0 = IVF code) bit-exactly and its decode."""
+    cfg, w, z = golden_loader(name)
+    x = z["x"]
+    xn = (x - w["data_mean"]) / np.float32(w["data_std"])
+    codes, xhat = orc.encode(cfg, w, xn)
+    assert codes.shape == z["codes_ref"].shape == (cfg["M"] + 1, len(x))
+    np.testing.assert_array_equal(codes, z["codes_ref"])
+    assert codes[0].max() < cfg["ivf_K"] and codes[1:].max() < cfg["K"]
+    assert np.abs(xhat - z["xhat_ref"]).max() <= 2e-5 * np.abs(z["xhat_ref"]).max()
+    dec = orc.forward(cfg, w, z["codes_ref"], "decode")
     assert ((dec - z["dec_ref"]) ** 2).sum() / (z["dec_ref"] ** 2).sum() <= 1e-10
