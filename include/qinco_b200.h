@@ -61,6 +61,11 @@ typedef struct {
     /* kernel planner overrides, 0 = automatic; opt_n_tiles = n_tiles | pair << 8 (pair: 0 auto, 1 off, 2 on) */
     int32_t opt_hc, opt_n_tiles, opt_slot_bytes, opt_max_stage, opt_max_slab_k;
     int32_t opt_stagger;     /* start delay (cycles) of the second CTA per SM; 0 = automatic, < 0 = none */
+    /* IVF-QINCo (cfg.ivf_in_use; IVFBook, qinco_base.py:128-196): ivf_K > 0 makes step 0 an arg-min over ivf_K centroids
+     * and steps 1..M implicit-codebook steps (cfg._M_ivf = M + 1).  The per-step arrays then have M + 1 entries indexed
+     * by step (entry 0 unused, codebook[0] may be NULL); M stays the number of uint8 codes per vector. */
+    int32_t ivf_K;
+    const float* ivf_centroids;            /* [ivf_K][D], normalised space (steps.0.ivf_centroids.weight) */
 } qb_model_desc;
 
 int qb_version(void);
@@ -86,6 +91,14 @@ int qb_encode(qb_model* m, const float* x_dev, int64_t n, int normalize, uint8_t
  * denormalize != 0, forward(codes, step="decode") (qinco_base.py:536-537): codes_dev [n, M] uint8 -> out_dev [n, D]. */
 int qb_decode(qb_model* m, const uint8_t* codes_dev, int64_t n, int denormalize, float* out_dev, void* workspace_dev,
               size_t workspace_bytes, void* stream);
+
+/* IVF-QINCo models (desc.ivf_K > 0): the code matrix of the reference has M + 1 rows, row 0 the IVF code.  Here the IVF
+ * codes travel in their own int32 array; codes_dev stays [n, M] uint8.  qb_encode / qb_decode refuse IVF models and these
+ * refuse plain ones. */
+int qb_encode_ivf(qb_model* m, const float* x_dev, int64_t n, int normalize, int32_t* ivf_codes_dev, uint8_t* codes_dev,
+                  float* xhat_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+int qb_decode_ivf(qb_model* m, const int32_t* ivf_codes_dev, const uint8_t* codes_dev, int64_t n, int denormalize,
+                  float* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Host-buffer variants = the batch loops of qinco_v1/codec_qinco.py:25-46 and :54-72 (H2D, encode/decode, D2H per
  * chunk, through pinned staging owned by the model).  xhat_host may be NULL. */

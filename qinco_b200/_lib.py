@@ -23,7 +23,7 @@ SYMBOLS = ["qb_version", "qb_last_error", "qb_model_create", "qb_model_destroy",
            "qb_decode_workspace_bytes", "qb_encode", "qb_decode", "qb_encode_host", "qb_decode_host", "qb_check",
            "qb_launch_count", "qb_timing_enable", "qb_timing_read", "qb_model_info", "qb_debug_step", "qb_plan_export", "qb_plan_pack", "qb_plan_tables",
            "qb_pairwise_create", "qb_pairwise_destroy", "qb_pairwise_decode", "qb_pairwise_check", "qb_pairwise_launch_count",
-           "qb_pairwise_last_error"]
+           "qb_pairwise_last_error", "qb_encode_ivf", "qb_decode_ivf"]
 
 _fpp = C.POINTER(C.POINTER(C.c_float))
 
@@ -37,6 +37,7 @@ class QbModelDesc(C.Structure):
         ("data_mean", C.POINTER(C.c_float)), ("data_std", C.c_float),
         ("opt_hc", C.c_int32), ("opt_n_tiles", C.c_int32), ("opt_slot_bytes", C.c_int32), ("opt_max_stage", C.c_int32),
         ("opt_max_slab_k", C.c_int32), ("opt_stagger", C.c_int32),
+        ("ivf_K", C.c_int32), ("ivf_centroids", C.POINTER(C.c_float)),
     ]
 
 
@@ -82,6 +83,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.qb_decode_workspace_bytes.restype = sz
     lib.qb_encode.argtypes = [vp, vp, i64, C.c_int, vp, vp, vp, sz, vp]
     lib.qb_decode.argtypes = [vp, vp, i64, C.c_int, vp, vp, sz, vp]
+    lib.qb_encode_ivf.argtypes = [vp, vp, i64, C.c_int, vp, vp, vp, vp, sz, vp]
+    lib.qb_decode_ivf.argtypes = [vp, vp, vp, i64, C.c_int, vp, vp, sz, vp]
     lib.qb_encode_host.argtypes = [vp, vp, i64, C.c_int, vp, vp]
     lib.qb_decode_host.argtypes = [vp, vp, i64, C.c_int, vp]
     lib.qb_check.argtypes = [vp]
@@ -144,21 +147,29 @@ class Handle:
             keep.append(pa)
             return pa.ptr
 
-        cb = _PtrArray([weights[f"steps.{m}.codebook.weight"] for m in range(M)])
+        ivf_K = int(cfg.get("ivf_K") or 0)
+        S = M + 1 if ivf_K else M          # quantisation steps (cfg._M_ivf); per-step arrays are indexed by step
+        cb = _PtrArray([None if (ivf_K and m == 0) else weights[f"steps.{m}.codebook.weight"] for m in range(S)])
         keep.append(cb)
         d = QbModelDesc()
         d.D, d.De, d.Dh, d.L, d.M, d.K, d.A, d.B = D, De, Dh, L, M, K, A, B
         d.qinco1_mode = int(bool(cfg["qinco1_mode"]))
         d.device = int(device)
         d.codebook = cb.ptr
-        steps = range(M)
+        steps = range(S)
+        if ivf_K:
+            cent = _f32(weights["steps.0.ivf_centroids.weight"])
+            assert cent.shape == (ivf_K, D), f"steps.0.ivf_centroids.weight must be [{ivf_K}, {D}]"
+            keep.append(cent)
+            d.ivf_K = ivf_K
+            d.ivf_centroids = cent.ctypes.data_as(C.POINTER(C.c_float))
         d.substep_codebook = arr("steps.{m}.substep.codebook.weight", steps) if A > 0 else None
         d.concat_w = arr("steps.{m}.concat.mlp.weight", steps)
         d.concat_b = arr("steps.{m}.concat.mlp.bias", steps)
         ups = _PtrArray([g(f"steps.{m}.residual_blocks.{l}.up_proj.weight") if m >= 1 else None
-                         for m in range(M) for l in range(L)])
+                         for m in range(S) for l in range(L)])
         downs = _PtrArray([g(f"steps.{m}.residual_blocks.{l}.down_proj.weight") if m >= 1 else None
-                           for m in range(M) for l in range(L)])
+                           for m in range(S) for l in range(L)])
         keep += [ups, downs]
         d.up_w, d.down_w = ups.ptr, downs.ptr
         if De != D:
@@ -196,6 +207,12 @@ class Handle:
 
     def decode(self, codes_ptr, n, denormalize, out_ptr, ws_ptr, ws_bytes, stream):
         check(self._lib.qb_decode(self._h, codes_ptr, n, int(denormalize), out_ptr, ws_ptr, ws_bytes, stream))
+
+    def encode_ivf(self, x_ptr, n, normalize, ivf_ptr, codes_ptr, xhat_ptr, ws_ptr, ws_bytes, stream):
+        check(self._lib.qb_encode_ivf(self._h, x_ptr, n, int(normalize), ivf_ptr, codes_ptr, xhat_ptr, ws_ptr, ws_bytes, stream))
+
+    def decode_ivf(self, ivf_ptr, codes_ptr, n, denormalize, out_ptr, ws_ptr, ws_bytes, stream):
+        check(self._lib.qb_decode_ivf(self._h, ivf_ptr, codes_ptr, n, int(denormalize), out_ptr, ws_ptr, ws_bytes, stream))
 
     def encode_host(self, x: np.ndarray, normalize: bool, want_xhat: bool = False):
         x = _f32(x)

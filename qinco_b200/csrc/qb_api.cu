@@ -67,6 +67,12 @@ struct HostSlot {
 
 struct qb_model {
     int D = 0, De = 0, Dh = 0, L = 0, M = 0, K = 0, A = 0, B = 0, q1 = 0, device = 0, n_sm = 0;
+    // M = uint8 codes per vector.  S = quantisation steps: M, or M + 1 with an IVF first step (then step s >= 1 writes
+    // code column s - 1 and the IVF code lives in its own int32 array).
+    int S = 0, ivf_K = 0;
+    float* ivf_cent = nullptr;    // [ivf_K][D]
+    float* ivf_cnorm = nullptr;   // [ivf_K]
+    int col(int step) const { return ivf_K ? step - 1 : step; }
     float data_std = 1.f;
     int stagger = 0;
     bool has_mean = false;
@@ -113,14 +119,17 @@ int check_desc(const qb_model_desc* d) {
     if (d->L < 0) return fail(QB_ERR_INVALID, "L must be >= 0");
     if (!(d->data_std > 0.f)) return fail(QB_ERR_INVALID, "data_std must be > 0 (qinco_base.py:526)");
     if (!d->codebook) return fail(QB_ERR_INVALID, "codebook pointers missing");
-    for (int m = 0; m < d->M; m++)
+    if (d->ivf_K < 0) return fail(QB_ERR_INVALID, "ivf_K must be >= 0");
+    if (d->ivf_K > 0 && !d->ivf_centroids) return fail(QB_ERR_INVALID, "ivf_K > 0 needs ivf_centroids");
+    const int S = d->ivf_K > 0 ? d->M + 1 : d->M;
+    for (int m = d->ivf_K > 0 ? 1 : 0; m < S; m++)
         if (!d->codebook[m]) return fail(QB_ERR_INVALID, "codebook[m] is NULL");
-    if (d->M > 1) {
+    if (S > 1) {
         if (!d->concat_w || !d->concat_b) return fail(QB_ERR_INVALID, "concat weights missing");
         if (d->L > 0 && (!d->up_w || !d->down_w)) return fail(QB_ERR_INVALID, "residual block weights missing");
         if (d->A > 0 && !d->substep_codebook) return fail(QB_ERR_INVALID, "A > 0 needs substep codebooks");
         if (d->De != d->D && (!d->in_proj || !d->out_proj)) return fail(QB_ERR_INVALID, "de != D needs in_proj/out_proj");
-        for (int m = 1; m < d->M; m++) {
+        for (int m = 1; m < S; m++) {
             if (!d->concat_w[m] || !d->concat_b[m]) return fail(QB_ERR_INVALID, "concat weights of a step are NULL");
             if (d->A > 0 && !d->substep_codebook[m]) return fail(QB_ERR_INVALID, "substep codebook of a step is NULL");
             if (d->De != d->D && (!d->in_proj[m] || !d->out_proj[m])) return fail(QB_ERR_INVALID, "projection of a step is NULL");
@@ -217,8 +226,8 @@ qb::MlpParams base_mlp(const qb_model* m, int step) {
     return p;
 }
 
-int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, uint8_t* codes, float* xhat_out, void* ws,
-                 cudaStream_t st) {
+int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, int32_t* ivf_codes, uint8_t* codes, float* xhat_out,
+                 void* ws, cudaStream_t st) {
     Workspace w;
     carve(m, ws, n, &w);
     const int D = m->D, M = m->M, K = m->K, A = m->A, B = m->B;
@@ -226,9 +235,16 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, uint8_t*
     const float* mean = (normalize && m->has_mean) ? m->mean : nullptr;
     const float inv_std_div = normalize ? m->data_std : 1.f;
     int cur = 0;
-    // ---- step 0 (qinco_base.py:218,263; qinco_inference.py:239-246)
-    const int F1 = (M == 1) ? 1 : B;
-    {
+    const int S = m->S;
+    // ---- step 0 (qinco_base.py:218,263; qinco_inference.py:239-246), or the IVF arg-min (IVFBook.encode, :165-174; F = 1)
+    const int F1 = m->ivf_K ? 1 : ((M == 1) ? 1 : B);
+    if (m->ivf_K) {
+        qb::IvfParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.D = D; p.ivf_K = m->ivf_K; p.n = n; p.x = x; p.mean = mean; p.std_div = inv_std_div;
+        p.cent = m->ivf_cent; p.cnorm = m->ivf_cnorm; p.codes_out = ivf_codes; p.xhat_out = w.xhat[cur];
+        QB_CUDA(timed_launch(m, KIND_PREP, n, st, [&] { return qb::launch_ivf_assign(p, st); }));
+    } else {
         qb::PrepParams p;
         std::memset(&p, 0, sizeof(p));
         p.D = D; p.De = m->De; p.K = K; p.A = F1; p.F = 1; p.step0 = 1; p.M = M;
@@ -239,10 +255,14 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, uint8_t*
         QB_CUDA(timed_launch(m, KIND_PREP, n, st, [&] { return qb::launch_prep(p, st); }));
     }
     int F_in = F1;
-    for (int step = 1; step < M; step++) {
+    for (int step = 1; step < S; step++) {
         const StepDev& s = m->steps[step];
-        const int F_out = (step < M - 1) ? B : 1;
-        const bool last = step == M - 1;
+        const int F_out = (step < S - 1) ? B : 1;
+        const bool last = step == S - 1;
+        // the first implicit-codebook step after an IVF step starts from ONE beam and must still supply B of them:
+        // it pre-selects max(A, B) candidates (QincoSubstep._n_codes, qinco_base.py:108-112)
+        const int A = (m->A > 0 && m->ivf_K && step == 1) ? std::max(m->A, B) : m->A;
+        const int C = A > 0 ? A : K;
         {
             qb::PrepParams p;
             std::memset(&p, 0, sizeof(p));
@@ -263,7 +283,7 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, uint8_t*
         {
             qb::SelectParams p;
             std::memset(&p, 0, sizeof(p));
-            p.F_in = F_in; p.F_out = F_out; p.C = C; p.A = A; p.M = M; p.m = step; p.n = n;
+            p.F_in = F_in; p.F_out = F_out; p.C = C; p.A = A; p.M = M; p.m = m->col(step); p.n = n;
             p.dist = w.dist; p.idx = A > 0 ? w.idx : nullptr;
             p.hist_in = w.hist[cur]; p.hist_out = last ? codes : w.hist[cur ^ 1];
             p.sel_parent = w.selp; p.sel_code = w.selc;
@@ -287,7 +307,8 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, uint8_t*
 
 size_t decode_bytes_per_vector(const qb_model* m) { return (size_t)2 * m->D * 4 + (size_t)m->De * 4; }
 
-int decode_chunk(qb_model* m, const uint8_t* codes, int64_t n, int denormalize, float* out, void* ws, cudaStream_t st) {
+int decode_chunk(qb_model* m, const int32_t* ivf_codes, const uint8_t* codes, int64_t n, int denormalize, float* out, void* ws,
+                 cudaStream_t st) {
     uint8_t* p0 = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(ws), 256));
     float* xh[2];
     xh[0] = (float*)p0;
@@ -298,14 +319,20 @@ int decode_chunk(qb_model* m, const uint8_t* codes, int64_t n, int denormalize, 
     const float* shift = (denormalize && m->has_mean) ? m->mean : nullptr;
     const bool affine = denormalize && (scale != 1.f || shift);
     int cur = 0;
-    QB_CUDA(timed_launch(m, KIND_OTHER, n, st, [&] {
-        return qb::launch_decode_init(m->cb0, codes, n, M, D, m->K, (M == 1 && !affine) ? out : xh[cur], m->err_dev, st);
-    }));
+    const int S = m->S;
+    if (m->ivf_K)
+        QB_CUDA(timed_launch(m, KIND_OTHER, n, st, [&] {
+            return qb::launch_ivf_lookup(m->ivf_cent, ivf_codes, n, D, m->ivf_K, xh[cur], m->err_dev, st);
+        }));
+    else
+        QB_CUDA(timed_launch(m, KIND_OTHER, n, st, [&] {
+            return qb::launch_decode_init(m->cb0, codes, n, M, D, m->K, (M == 1 && !affine) ? out : xh[cur], m->err_dev, st);
+        }));
     if (M == 1 && affine)
         QB_CUDA(timed_launch(m, KIND_OTHER, n, st, [&] { return qb::launch_affine(xh[cur], out, n, D, scale, shift, st); }));
-    for (int step = 1; step < M; step++) {
+    for (int step = 1; step < S; step++) {
         const StepDev& s = m->steps[step];
-        const bool last = step == M - 1;
+        const bool last = step == S - 1;
         {
             qb::PrepParams p;
             std::memset(&p, 0, sizeof(p));
@@ -318,7 +345,7 @@ int decode_chunk(qb_model* m, const uint8_t* codes, int64_t n, int denormalize, 
             qb::MlpParams p = base_mlp(m, step);
             p.mode = qb::QB_MODE_APPLY;
             p.F_in = 1; p.F_out = 1; p.n_rows = n;
-            p.sel_code = codes; p.code_stride = M; p.code_off = step;
+            p.sel_code = codes; p.code_stride = M; p.code_off = m->col(step);
             p.u = u; p.xhat_in = xh[cur];
             p.xhat_out = last ? out : xh[cur ^ 1];
             if (last) { p.out_scale = scale; p.out_shift = shift; }
@@ -391,6 +418,8 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
     m->D = d->D; m->De = d->De > 0 ? d->De : d->D; m->Dh = d->Dh; m->L = d->L; m->M = d->M; m->K = d->K;
     m->A = d->A; m->B = d->B; m->q1 = d->qinco1_mode; m->device = d->device; m->n_sm = prop.multiProcessorCount;
     m->data_std = d->data_std;
+    m->ivf_K = d->ivf_K;
+    m->S = d->ivf_K > 0 ? d->M + 1 : d->M;
     auto bail = [&](int code) {
         qb_model_destroy(m);
         return code;
@@ -401,8 +430,16 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
     *m->err_host = 0;
     QB_CUDA(cudaHostGetDevicePointer((void**)&m->err_dev, m->err_host, 0));
 
-    // step 0: plain codebook, row-major and transposed
-    {
+    if (m->ivf_K) {     // step 0: frozen IVF centroids and their squared norms (IVFBook, qinco_base.py:128-146)
+        std::vector<float> cn((size_t)m->ivf_K);
+        for (int k = 0; k < m->ivf_K; k++) {
+            float sacc = 0.f;
+            for (int dd = 0; dd < D; dd++) sacc += d->ivf_centroids[(size_t)k * D + dd] * d->ivf_centroids[(size_t)k * D + dd];
+            cn[k] = sacc;
+        }
+        if ((rc = dev_upload(m, d->ivf_centroids, (size_t)m->ivf_K * D, &m->ivf_cent))) return bail(rc);
+        if ((rc = dev_upload(m, cn.data(), cn.size(), &m->ivf_cnorm))) return bail(rc);
+    } else {            // step 0: plain codebook, row-major and transposed
         std::vector<float> t((size_t)D * K);
         for (int k = 0; k < K; k++)
             for (int dd = 0; dd < D; dd++) t[(size_t)dd * K + k] = d->codebook[0][(size_t)k * D + dd];
@@ -415,7 +452,7 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         m->has_mean = nz;
         if ((rc = dev_upload(m, d->data_mean, (size_t)D, &m->mean))) return bail(rc);
     }
-    m->steps.resize(m->M);
+    m->steps.resize(m->S);
     {   // default stagger: ~1.5x the ideal MMA time of one tile (128 rows x 2*L*De*Dh MACs at ~3800 MAC/cycle)
         const double mma = 128.0 * 2.0 * m->L * m->De * m->Dh / 3800.0;
         m->stagger = d->opt_stagger > 0 ? d->opt_stagger : 0;
@@ -428,7 +465,7 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         if (const char* e = getenv("QB_PAIR")) opt.pair = atoi(e);   // debug / A-B runs: 1 = single-CTA kernel, 2 = force pairs
     opt.max_stage = d->opt_max_stage & 0xff; opt.no_resident = (d->opt_max_stage >> 8) & 1; opt.no_hsplit = (d->opt_max_stage >> 9) & 1; opt.max_slab_k = d->opt_max_slab_k;
     int max_smem = 0;
-    for (int s = 1; s < m->M; s++) {
+    for (int s = 1; s < m->S; s++) {
         StepDev& sd = m->steps[s];
         std::vector<QbOp> ops;
         std::string err;
@@ -500,10 +537,13 @@ size_t qb_decode_workspace_bytes(const qb_model* m, int64_t n) {
     return (size_t)nc * decode_bytes_per_vector(m) + kWsSlack;
 }
 
-int qb_encode(qb_model* m, const float* x_dev, int64_t n, int normalize, uint8_t* codes_dev, float* xhat_dev,
-              void* workspace_dev, size_t workspace_bytes, void* stream) {
+static int encode_impl(qb_model* m, const float* x_dev, int64_t n, int normalize, int32_t* ivf_codes_dev, uint8_t* codes_dev,
+                       float* xhat_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
     if (!m) return fail(QB_ERR_INVALID, "model is NULL");
     if (n < 0) return fail(QB_ERR_INVALID, "n < 0");
+    if ((m->ivf_K > 0) != (ivf_codes_dev != nullptr))
+        return fail(QB_ERR_INVALID, m->ivf_K ? "IVF model: use qb_encode_ivf (needs a buffer for the IVF codes)"
+                                             : "not an IVF model: use qb_encode");
     if (n == 0) return QB_OK;
     if (!x_dev || !codes_dev || !workspace_dev) return fail(QB_ERR_INVALID, "NULL buffer");
     if (workspace_bytes <= kWsSlack) return fail(QB_ERR_WORKSPACE, "workspace too small");
@@ -515,17 +555,30 @@ int qb_encode(qb_model* m, const float* x_dev, int64_t n, int normalize, uint8_t
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     for (int64_t i0 = 0; i0 < n; i0 += nc) {
         const int64_t c = std::min(nc, n - i0);
-        int rc = encode_chunk(m, x_dev + i0 * m->D, c, normalize, codes_dev + i0 * m->M,
-                              xhat_dev ? xhat_dev + i0 * m->D : nullptr, workspace_dev, st);
+        int rc = encode_chunk(m, x_dev + i0 * m->D, c, normalize, ivf_codes_dev ? ivf_codes_dev + i0 : nullptr,
+                              codes_dev + i0 * m->M, xhat_dev ? xhat_dev + i0 * m->D : nullptr, workspace_dev, st);
         if (rc) return rc;
     }
     return QB_OK;
 }
 
-int qb_decode(qb_model* m, const uint8_t* codes_dev, int64_t n, int denormalize, float* out_dev, void* workspace_dev,
-              size_t workspace_bytes, void* stream) {
+int qb_encode(qb_model* m, const float* x_dev, int64_t n, int normalize, uint8_t* codes_dev, float* xhat_dev,
+              void* workspace_dev, size_t workspace_bytes, void* stream) {
+    return encode_impl(m, x_dev, n, normalize, nullptr, codes_dev, xhat_dev, workspace_dev, workspace_bytes, stream);
+}
+
+int qb_encode_ivf(qb_model* m, const float* x_dev, int64_t n, int normalize, int32_t* ivf_codes_dev, uint8_t* codes_dev,
+                  float* xhat_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!ivf_codes_dev) return fail(QB_ERR_INVALID, "ivf_codes_dev is NULL");
+    return encode_impl(m, x_dev, n, normalize, ivf_codes_dev, codes_dev, xhat_dev, workspace_dev, workspace_bytes, stream);
+}
+
+static int decode_impl(qb_model* m, const int32_t* ivf_codes_dev, const uint8_t* codes_dev, int64_t n, int denormalize,
+                       float* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
     if (!m) return fail(QB_ERR_INVALID, "model is NULL");
     if (n < 0) return fail(QB_ERR_INVALID, "n < 0");
+    if ((m->ivf_K > 0) != (ivf_codes_dev != nullptr))
+        return fail(QB_ERR_INVALID, m->ivf_K ? "IVF model: use qb_decode_ivf (needs the IVF codes)" : "not an IVF model: use qb_decode");
     if (n == 0) return QB_OK;
     if (!codes_dev || !out_dev || !workspace_dev) return fail(QB_ERR_INVALID, "NULL buffer");
     if (workspace_bytes <= kWsSlack) return fail(QB_ERR_WORKSPACE, "workspace too small");
@@ -537,10 +590,22 @@ int qb_decode(qb_model* m, const uint8_t* codes_dev, int64_t n, int denormalize,
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     for (int64_t i0 = 0; i0 < n; i0 += nc) {
         const int64_t c = std::min(nc, n - i0);
-        int rc = decode_chunk(m, codes_dev + i0 * m->M, c, denormalize, out_dev + i0 * m->D, workspace_dev, st);
+        int rc = decode_chunk(m, ivf_codes_dev ? ivf_codes_dev + i0 : nullptr, codes_dev + i0 * m->M, c, denormalize,
+                              out_dev + i0 * m->D, workspace_dev, st);
         if (rc) return rc;
     }
     return QB_OK;
+}
+
+int qb_decode(qb_model* m, const uint8_t* codes_dev, int64_t n, int denormalize, float* out_dev, void* workspace_dev,
+              size_t workspace_bytes, void* stream) {
+    return decode_impl(m, nullptr, codes_dev, n, denormalize, out_dev, workspace_dev, workspace_bytes, stream);
+}
+
+int qb_decode_ivf(qb_model* m, const int32_t* ivf_codes_dev, const uint8_t* codes_dev, int64_t n, int denormalize,
+                  float* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!ivf_codes_dev) return fail(QB_ERR_INVALID, "ivf_codes_dev is NULL");
+    return decode_impl(m, ivf_codes_dev, codes_dev, n, denormalize, out_dev, workspace_dev, workspace_bytes, stream);
 }
 
 int qb_check(qb_model* m) {
@@ -650,7 +715,7 @@ int qb_timing_read(qb_model* m, double* ms_out, int64_t* launches_out, int64_t* 
 
 int qb_model_info(const qb_model* m, int step, int32_t* out, int n_out) {
     if (!m || !out) return fail(QB_ERR_INVALID, "NULL argument");
-    if (step < 1 || step >= m->M) return fail(QB_ERR_INVALID, "step out of range (MLP steps are 1..M-1)");
+    if (step < 1 || step >= m->S) return fail(QB_ERR_INVALID, "step out of range (MLP steps are 1..S-1)");
     const QbStepPlan& p = m->steps[step].plan;
     const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk,
                          p.n_tiles, p.oc, p.n_ochunk, p.slot_bytes, p.n_stage, p.smem_total, (int32_t)p.block_w_bytes,
@@ -663,7 +728,7 @@ int qb_model_info(const qb_model* m, int step, int32_t* out, int n_out) {
 int qb_debug_step(qb_model* m, int step, const float* xhat_dev, const uint8_t* codes_dev, int64_t n, float* out_dev,
                   void* workspace_dev, size_t workspace_bytes, void* stream) {
     if (!m) return fail(QB_ERR_INVALID, "model is NULL");
-    if (step < 1 || step >= m->M) return fail(QB_ERR_INVALID, "step out of range (MLP steps are 1..M-1)");
+    if (step < 1 || step >= m->S) return fail(QB_ERR_INVALID, "step out of range (MLP steps are 1..S-1)");
     if (n <= 0) return QB_OK;
     if (workspace_bytes < (size_t)n * m->De * 4 + 256) return fail(QB_ERR_WORKSPACE, "workspace too small (n*de*4+256)");
     QB_CUDA(cudaSetDevice(m->device));

@@ -86,6 +86,25 @@ struct SelectParams {
 };
 cudaError_t launch_select(const SelectParams& p, cudaStream_t stream);
 
+// IVF first step (reference IVFBook.quantize / encode, qinco_base.py:146-174): per vector the arg-min over ivf_K centroids
+// of  (|x|^2 + |c|^2) - 2 x.c  (the reference's approx_pairwise_distance, utils.py:336-346), ties to the lower index;
+// writes the code and the centroid as the single starting beam.
+struct IvfParams {
+    int32_t D, ivf_K;
+    int64_t n;
+    const float* x;           // [n, D] raw input
+    const float* mean;        // [D] or NULL
+    float std_div;            // divisor after the mean shift (data_std or 1)
+    const float* cent;        // [ivf_K, D]
+    const float* cnorm;       // [ivf_K]  |c|^2
+    int32_t* codes_out;       // [n]
+    float* xhat_out;          // [n, D]
+};
+cudaError_t launch_ivf_assign(const IvfParams& p, cudaStream_t stream);
+// xhat[v] = centroids[ivf_codes[v]]  (IVFBook.decode, qinco_base.py:176-183)
+cudaError_t launch_ivf_lookup(const float* cent, const int32_t* ivf_codes, int64_t n, int D, int ivf_K, float* xhat,
+                              uint32_t* err_flag, cudaStream_t stream);
+
 // xhat[v] = C_0[codes[v*M]]  (decode start, qinco_base.py:447-452 with step 0 = plain codebook lookup)
 cudaError_t launch_decode_init(const float* cb0, const uint8_t* codes, int64_t n, int M, int D, int K, float* xhat,
                                uint32_t* err_flag, cudaStream_t stream);

@@ -18,7 +18,7 @@ struct PlanOptions {
     int slot_bytes = 0;   // weight ring slot size (0 = 16 KiB)
     int max_stage = 0;    // cap on ring depth (0 = QB_MAX_STAGE)
     int max_slab_k = 0;   // cap on slab K (0 = what fits a slot)
-    int smem_budget = 0;  // bytes of dynamic shared memory the kernel may use (0 = 216 KiB)
+    int smem_budget = 0;  // bytes of dynamic shared memory the kernel may use (0 = 208 KiB)
 };
 
 uint16_t f32_to_f16(float f);

@@ -163,6 +163,126 @@ __global__ void __launch_bounds__(256) qb_select_kernel(const SelectParams p) {
     }
 }
 
+// ---- IVF first step: tiled fp32 "GEMM + arg-min".  Block = 64 vectors; centroids in tiles of 64, D in chunks of 16; thread
+// (ti, tj) of a 16 x 16 grid owns vectors ti + 16 a and centroids tj + 16 b (a, b < 4): 16 dot products in registers.
+constexpr int kIvfVB = 64, kIvfCT = 64, kIvfDC = 16, kIvfLD = kIvfDC + 4;   // +4 floats: rows 16 B apart in bank space
+
+__global__ void __launch_bounds__(256) qb_ivf_assign_kernel(const IvfParams p) {
+    __shared__ __align__(16) float xs[kIvfVB * kIvfLD];
+    __shared__ __align__(16) float cs[kIvfCT * kIvfLD];
+    __shared__ float anorm_s[kIvfVB];
+    __shared__ float best_v[kIvfVB][16];
+    __shared__ int best_i[kIvfVB][16];
+    const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+    const int64_t v0 = (int64_t)blockIdx.x * kIvfVB;
+    const int D = p.D;
+    // |x|^2 of the block's (normalised) vectors: 4 threads per vector
+    {
+        const int v = tid >> 2, part = tid & 3;
+        float s = 0.f;
+        if (v0 + v < p.n)
+            for (int d = part; d < D; d += 4) {
+                float xv = p.x[(v0 + v) * D + d];
+                if (p.mean) xv -= p.mean[d];
+                xv /= p.std_div;
+                s = fmaf(xv, xv, s);
+            }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (part == 0) anorm_s[v] = s;
+    }
+    float bv[4];
+    int bi[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) { bv[a] = FLT_MAX; bi[a] = 0x7fffffff; }
+    for (int k0 = 0; k0 < p.ivf_K; k0 += kIvfCT) {
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+        for (int d0 = 0; d0 < D; d0 += kIvfDC) {
+            __syncthreads();
+            {   // 64 rows x 16 columns each: one float4 per thread per tile
+                const int row = tid >> 2, c4 = (tid & 3) * 4;
+                float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), cv = xv;
+                if (v0 + row < p.n) {
+                    xv = *reinterpret_cast<const float4*>(p.x + (v0 + row) * D + d0 + c4);
+                    if (p.mean) {
+                        const float4 m = *reinterpret_cast<const float4*>(p.mean + d0 + c4);
+                        xv.x -= m.x; xv.y -= m.y; xv.z -= m.z; xv.w -= m.w;
+                    }
+                    xv.x /= p.std_div; xv.y /= p.std_div; xv.z /= p.std_div; xv.w /= p.std_div;
+                }
+                if (k0 + row < p.ivf_K) cv = __ldg(reinterpret_cast<const float4*>(p.cent + (size_t)(k0 + row) * D + d0 + c4));
+                *reinterpret_cast<float4*>(xs + row * kIvfLD + c4) = xv;
+                *reinterpret_cast<float4*>(cs + row * kIvfLD + c4) = cv;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int d = 0; d < kIvfDC; d += 4) {
+                float4 xa[4], cb[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) xa[a] = *reinterpret_cast<const float4*>(xs + (ti + 16 * a) * kIvfLD + d);
+#pragma unroll
+                for (int b = 0; b < 4; b++) cb[b] = *reinterpret_cast<const float4*>(cs + (tj + 16 * b) * kIvfLD + d);
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        acc[a][b] = fmaf(xa[a].x, cb[b].x, acc[a][b]); acc[a][b] = fmaf(xa[a].y, cb[b].y, acc[a][b]);
+                        acc[a][b] = fmaf(xa[a].z, cb[b].z, acc[a][b]); acc[a][b] = fmaf(xa[a].w, cb[b].w, acc[a][b]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int k = k0 + tj + 16 * b;
+            if (k < p.ivf_K) {
+                const float bn = __ldg(p.cnorm + k);
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    const float dist = (anorm_s[ti + 16 * a] + bn) - 2.f * acc[a][b];   // utils.py:346
+                    if (dist < bv[a] || (dist == bv[a] && k < bi[a])) { bv[a] = dist; bi[a] = k; }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) { best_v[ti + 16 * a][tj] = bv[a]; best_i[ti + 16 * a][tj] = bi[a]; }
+    __syncthreads();
+    if (tid < kIvfVB) {
+        float v = best_v[tid][0];
+        int i = best_i[tid][0];
+        for (int j = 1; j < 16; j++) {
+            const float ov = best_v[tid][j];
+            const int oi = best_i[tid][j];
+            if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+        }
+        if (i >= p.ivf_K) i = 0;      // all-NaN row: stay in range
+        best_i[tid][0] = i;
+        if (v0 + tid < p.n) p.codes_out[v0 + tid] = i;
+    }
+    __syncthreads();
+    for (int t = tid; t < kIvfVB * (D / 4); t += 256) {
+        const int v = t / (D / 4), d4 = t - v * (D / 4);
+        if (v0 + v < p.n)
+            *reinterpret_cast<float4*>(p.xhat_out + (v0 + v) * D + d4 * 4) =
+                __ldg(reinterpret_cast<const float4*>(p.cent + (size_t)best_i[v][0] * D + d4 * 4));
+    }
+}
+
+__global__ void qb_ivf_lookup_kernel(const float* __restrict__ cent, const int32_t* __restrict__ codes, int64_t n, int D,
+                                     int ivf_K, float* __restrict__ xhat, uint32_t* err_flag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t v = t / (D / 4);
+    const int d = (int)(t - v * (D / 4)) * 4;
+    if (v >= n) return;
+    int c = codes[v];
+    if (c < 0 || c >= ivf_K) { if (err_flag) atomicExch(err_flag, 0x20u); c = 0; }
+    *reinterpret_cast<float4*>(xhat + v * D + d) = __ldg(reinterpret_cast<const float4*>(cent + (size_t)c * D + d));
+}
+
 __global__ void qb_decode_init_kernel(const float* __restrict__ cb0, const uint8_t* __restrict__ codes, int64_t n, int M,
                                       int D, int K, float* __restrict__ xhat, uint32_t* err_flag) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,6 +323,21 @@ cudaError_t launch_select(const SelectParams& p, cudaStream_t stream) {
     const int wpb = 8;
     const int64_t grid = (p.n + wpb - 1) / wpb;
     qb_select_kernel<<<(unsigned)grid, wpb * 32, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ivf_assign(const IvfParams& p, cudaStream_t stream) {
+    if (p.n <= 0) return cudaSuccess;
+    if (p.D % 16 || p.ivf_K < 1) return cudaErrorInvalidValue;
+    qb_ivf_assign_kernel<<<(unsigned)((p.n + kIvfVB - 1) / kIvfVB), 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ivf_lookup(const float* cent, const int32_t* ivf_codes, int64_t n, int D, int ivf_K, float* xhat,
+                              uint32_t* err_flag, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const int64_t total = n * (D / 4);
+    qb_ivf_lookup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(cent, ivf_codes, n, D, ivf_K, xhat, err_flag);
     return cudaGetLastError();
 }
 

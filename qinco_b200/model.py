@@ -41,12 +41,17 @@ def normalize_cfg(cfg) -> dict:
     D = _cfg_get(cfg, "D") or _cfg_get(cfg, "_D")
     if D is None:
         raise ValueError("cfg needs D (or _D)")
-    M = _cfg_get(cfg, "_M_ivf") or _cfg_get(cfg, "M")
+    ivf_K = int(_cfg_get(cfg, "ivf_K", 0) or 0)
+    if _cfg_get(cfg, "ivf_in_use", None) is False:      # the reference keeps ivf_K around when the IVF step is off
+        ivf_K = 0
+    M = _cfg_get(cfg, "M")                       # QINCo steps = uint8 codes per vector; cfg._M_ivf = M + 1 with an IVF step
+    if M is None:
+        M = int(_cfg_get(cfg, "_M_ivf")) - (1 if ivf_K else 0)
     out = dict(D=int(D), M=int(M), K=int(_cfg_get(cfg, "K", 256)), L=int(_cfg_get(cfg, "L")),
                de=int(_cfg_get(cfg, "de") or D), dh=int(_cfg_get(cfg, "dh")), A=int(_cfg_get(cfg, "A", 0) or 0),
                B=int(_cfg_get(cfg, "B", 1) or 1), qinco1_mode=bool(_cfg_get(cfg, "qinco1_mode", False)))
-    if _cfg_get(cfg, "ivf_in_use", False) or _cfg_get(cfg, "_ivf_book", None):
-        raise NotImplementedError("IVF first step is not built yet (SURVEY.md section 8f row 2)")
+    if ivf_K:
+        out["ivf_K"] = ivf_K                     # IVFBook first step (qinco_base.py:128-196)
     return out
 
 
@@ -65,6 +70,8 @@ class QINCo:
     def __init__(self, cfg, state_dict=None, device=None, plan_opts=None):
         self.cfg = normalize_cfg(cfg)
         self.D, self.M, self.K = self.cfg["D"], self.cfg["M"], self.cfg["K"]
+        self.ivf_K = int(self.cfg.get("ivf_K") or 0)
+        self.M_ivf = self.M + (1 if self.ivf_K else 0)      # rows of the reference's code matrix (cfg._M_ivf)
         acc = _cfg_get(cfg, "_accelerator", None)
         if device is None and acc is not None:
             device = getattr(acc, "device", None)
@@ -113,7 +120,8 @@ class QINCo:
         if missing and strict:
             raise KeyError(f"missing keys in state dict: {missing[:6]}{'...' if len(missing) > 6 else ''}")
         c = self.cfg
-        shapes = {"steps.0.codebook.weight": (c["K"], c["D"])}
+        shapes = ({"steps.0.ivf_centroids.weight": (c["ivf_K"], c["D"])} if c.get("ivf_K") else
+                  {"steps.0.codebook.weight": (c["K"], c["D"])})
         for k, shp in shapes.items():
             if tuple(w[k].shape) != shp:
                 raise ValueError(f"{k}: expected shape {shp}, got {tuple(w[k].shape)}")
@@ -124,8 +132,11 @@ class QINCo:
 
     def _expected_keys(self):
         c = self.cfg
-        keys = [f"steps.{m}.codebook.weight" for m in range(c["M"])]
-        for m in range(1, c["M"]):
+        S = c["M"] + (1 if c.get("ivf_K") else 0)
+        keys = [f"steps.{m}.codebook.weight" for m in range(1 if c.get("ivf_K") else 0, S)]
+        if c.get("ivf_K"):
+            keys.append("steps.0.ivf_centroids.weight")
+        for m in range(1, S):
             keys += [f"steps.{m}.concat.mlp.weight", f"steps.{m}.concat.mlp.bias"]
             if c["A"] > 0:
                 keys.append(f"steps.{m}.substep.codebook.weight")
@@ -202,6 +213,53 @@ class QINCo:
                 self._h.decode(codes_u8.data_ptr(), n, denormalize, out.data_ptr(), ws.data_ptr(), ws.numel(), stream)
         return out
 
+    def encode_ivf_u8(self, x, normalize=False, want_xhat=True):
+        """IVF models: x [n, D] -> (ivf codes int32 [n], codes uint8 [n, M], xhat [n, D] or None); asynchronous."""
+        x = self._check_x(x)
+        n = x.shape[0]
+        ivf = torch.empty((n,), dtype=torch.int32, device=self.device)
+        codes = torch.empty((n, self.M), dtype=torch.uint8, device=self.device)
+        xhat = torch.empty((n, self.D), dtype=torch.float32, device=self.device) if want_xhat else None
+        if n:
+            ws = self._workspace(self._h.encode_workspace_bytes(n))
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream().cuda_stream
+                self._h.encode_ivf(x.data_ptr(), n, normalize, ivf.data_ptr(), codes.data_ptr(),
+                                   xhat.data_ptr() if want_xhat else None, ws.data_ptr(), ws.numel(), stream)
+        return ivf, codes, xhat
+
+    def decode_ivf_u8(self, ivf_i32, codes_u8, denormalize=False):
+        """IVF models: (ivf codes int32 [n], codes uint8 [n, M]) -> [n, D] fp32; asynchronous."""
+        assert ivf_i32.dtype == torch.int32 and codes_u8.dtype == torch.uint8 and codes_u8.shape == (ivf_i32.shape[0], self.M)
+        ivf_i32, codes_u8 = ivf_i32.contiguous(), codes_u8.contiguous()
+        n = codes_u8.shape[0]
+        out = torch.empty((n, self.D), dtype=torch.float32, device=self.device)
+        if n:
+            ws = self._workspace(self._h.decode_workspace_bytes(n))
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream().cuda_stream
+                self._h.decode_ivf(ivf_i32.data_ptr(), codes_u8.data_ptr(), n, denormalize, out.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), stream)
+        return out
+
+    def _split_ivf(self, codes_MB):
+        """[M + 1, n] integer codes (row 0 = IVF code) -> (int32 [n], uint8 [n, M]) on the device."""
+        if not isinstance(codes_MB, torch.Tensor):
+            codes_MB = torch.as_tensor(np.asarray(codes_MB))
+        if codes_MB.dim() != 2 or codes_MB.shape[0] != self.M_ivf:
+            raise AssertionError(f"codes must be [M_ivf={self.M_ivf}, n], got {tuple(codes_MB.shape)}")   # qinco_base.py:449
+        codes_MB = codes_MB.to(self.device)
+        ivf, rest = codes_MB[0], codes_MB[1:]
+        if ivf.numel() and (int(ivf.min()) < 0 or int(ivf.max()) >= self.ivf_K):
+            raise IndexError(f"IVF codes out of range [0, {self.ivf_K})")
+        if rest.numel() and (int(rest.min()) < 0 or int(rest.max()) >= self.K):
+            raise IndexError(f"codes out of range [0, {self.K})")
+        return ivf.to(torch.int32).contiguous(), rest.t().contiguous().to(torch.uint8)
+
+    @staticmethod
+    def _join_ivf(ivf_i32, codes_u8):
+        return torch.cat([ivf_i32.long()[None, :], codes_u8.t().long()], dim=0).contiguous()
+
     def _codes_to_u8(self, codes_MB):
         if not isinstance(codes_MB, torch.Tensor):
             codes_MB = torch.as_tensor(np.asarray(codes_MB))
@@ -215,13 +273,18 @@ class QINCo:
     # ---- the reference surface ------------------------------------------------------------------------------------
     @torch.no_grad()
     def encode(self, x_target_BD):
-        """Normalised space: x [n, D] -> (codes LongTensor [M, n], xhat [n, D])   (qinco_base.py:454-485)."""
+        """Normalised space: x [n, D] -> (codes LongTensor [M_ivf, n], xhat [n, D])   (qinco_base.py:454-485)."""
+        if self.ivf_K:
+            ivf, codes, xhat = self.encode_ivf_u8(x_target_BD, normalize=False, want_xhat=True)
+            return self._join_ivf(ivf, codes), xhat
         codes, xhat = self.encode_u8(x_target_BD, normalize=False, want_xhat=True)
         return codes.t().contiguous().long(), xhat
 
     @torch.no_grad()
     def decode(self, codes_MB):
-        """Normalised space: codes [M, n] (int64/int32/uint8) -> xhat [n, D] fp32   (qinco_base.py:447-452)."""
+        """Normalised space: codes [M_ivf, n] (int64/int32/uint8) -> xhat [n, D] fp32   (qinco_base.py:447-452)."""
+        if self.ivf_K:
+            return self.decode_ivf_u8(*self._split_ivf(codes_MB), denormalize=False)
         return self.decode_u8(self._codes_to_u8(codes_MB), denormalize=False)
 
     @torch.no_grad()
@@ -231,8 +294,13 @@ class QINCo:
             raise Exception("Don't use the B200 inference model for training!")
         assert float(self.data_std) > 0                                               # qinco_base.py:526
         if step == "encode":                                                          # :532-534
+            if self.ivf_K:
+                ivf, codes, _ = self.encode_ivf_u8(x_in, normalize=True, want_xhat=False)
+                return self._join_ivf(ivf, codes)
             codes, _ = self.encode_u8(x_in, normalize=True, want_xhat=False)
             return codes.t().contiguous().long()
+        if self.ivf_K:
+            return self.decode_ivf_u8(*self._split_ivf(x_in), denormalize=True)
         return self.decode_u8(self._codes_to_u8(x_in), denormalize=True)              # :536-537
 
     __call__ = forward

@@ -250,3 +250,67 @@ def test_v1_codec_matches_reference(golden_loader):
     # from a v1-keyed state dict
     m2 = codec.QINCoV1(synth.to_v1_state(cfg, w), db_scale=float(z["db_scale"]))
     np.testing.assert_array_equal(codec.encode(m2, z["x"], bs=96, verbose=False), codes)
+
+
+# ---------------------------------------------------------------------------------------------------------------- IVF
+from conftest import GOLDEN_IVF  # noqa: E402
+
+
+@pytest.mark.parametrize("name", GOLDEN_IVF)
+def test_ivf_model_matches_reference(name, golden_loader):
+    """IVF-QINCo: IVF codes (row 0) against the reference's arg-min, decode of the reference's codes,
+    encode MSE, surface shapes ([M + 1, n] int64) and errors."""
+    from qinco_b200.model import QINCo
+    cfg, w, z = golden_loader(name)
+    model = QINCo(cfg, w, device="cuda:0")
+    try:
+        x = z["x"]
+        xn = (x - w["data_mean"]) / np.float32(w["data_std"])
+        dec = model(torch.from_numpy(z["codes_ref"]).cuda(), step="decode")
+        model.synchronize()
+        assert rel_mse(dec.cpu().numpy(), z["dec_ref"]) <= DEC_TOL
+        codes = model(torch.from_numpy(x).cuda(), step="encode")
+        model.synchronize()
+        assert codes.dtype == torch.int64 and tuple(codes.shape) == (cfg["M"] + 1, len(x))
+        c = codes.cpu().numpy()
+        assert c[0].max() < cfg["ivf_K"] and c[1:].max() < cfg["K"] and c.min() >= 0
+        # the IVF code is an fp32 arg-min over distinct centroids: it must agree with the reference (ties aside)
+        assert (c[0] == z["codes_ref"][0]).mean() >= 0.98
+        agree = float((c == z["codes_ref"]).all(0).mean())
+        mse_ours, mse_ref = orc.mse(xn, orc.decode(cfg, w, c)), orc.mse(xn, z["xhat_ref"])
+        print(f"\n{name}: identical vectors {agree:.3f} mse ours {mse_ours:.5f} ref {mse_ref:.5f}")
+        assert agree >= 0.8 and abs(mse_ours - mse_ref) <= ENC_TOL_SMALL * mse_ref
+        codes2, xhat = model.encode(torch.from_numpy(xn).cuda())
+        assert torch.equal(codes2, codes)
+        assert rel_mse(xhat.cpu().numpy(), model.decode(codes2).cpu().numpy()) <= 1e-10
+        with pytest.raises(IndexError):
+            bad = z["codes_ref"].copy()
+            bad[0, 0] = cfg["ivf_K"]
+            model.decode(torch.from_numpy(bad))
+        with pytest.raises(Exception):       # the plain entry points refuse IVF models
+            model.encode_u8(torch.from_numpy(xn).cuda())
+        assert model(torch.zeros((0, cfg["D"])).cuda(), step="encode").shape == (cfg["M"] + 1, 0)
+    finally:
+        model._h.close()
+
+
+def test_ivf_assign_large_matches_oracle():
+    """The IVF arg-min kernel alone at a ragged size: 5000 vectors x 3001 centroids, d = 96, with normalisation."""
+    from qinco_b200.model import QINCo
+    cfg = synth.make_cfg(None, D=96, M=2, K=32, L=1, de=96, dh=32, A=0, B=1, ivf_K=3001)
+    w = synth.make_weights(cfg, seed=3, n_train=6000, kmeans_iters=1, data_mean=0.3, data_std=1.7)
+    x = synth.make_data(5000, 96, seed=8, mean=0.3, std=1.7)
+    xn = (x - w["data_mean"]) / np.float32(w["data_std"])
+    ref = orc.approx_pairwise_distance(xn, w["steps.0.ivf_centroids.weight"]).argmin(-1)
+    model = QINCo(cfg, w, device="cuda:0")
+    try:
+        codes = model(torch.from_numpy(x).cuda(), step="encode").cpu().numpy()
+        model.synchronize()
+        same = (codes[0] == ref)
+        assert same.mean() >= 0.999, same.mean()
+        # where they differ the two centroids are tied to fp32 rounding
+        d = orc.exact_pairwise_distance(xn[~same], w["steps.0.ivf_centroids.weight"])
+        rows = np.arange((~same).sum())
+        assert np.all(np.abs(d[rows, codes[0][~same]] - d[rows, ref[~same]]) <= 1e-4 * d[rows, ref[~same]])
+    finally:
+        model._h.close()

@@ -213,7 +213,7 @@ def test_op_list_replay_matches_oracle(lib, name, opts):
     assert plan["pair"] == (1 if opts and opts[1] >> 8 == 2 else 0)
     # structural invariants of the plan
     assert plan["n_stage"] >= 2 and plan["n_tiles"] in (1, 2)
-    assert plan["smem_total"] + 4096 <= 227 * 1024
+    assert plan["smem_total"] + 15 * 1024 <= 227 * 1024      # static shared memory of the resident variant: 14 KB
     assert plan["n_tiles"] * plan["tmem_tile_cols"] <= plan["tmem_alloc_cols"] <= 512
     assert plan["tmem_alloc_cols"] & (plan["tmem_alloc_cols"] - 1) == 0
     for op in ops:
