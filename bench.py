@@ -34,6 +34,7 @@ WORKLOADS = {
     "c2a16": dict(name="QINCo2-S 8x8 K=256 d=128 A=16 beam=1", cfg=dict(D=128, M=8, K=256, L=2, de=128, dh=256, A=16, B=1, qinco1_mode=False), n=1_000_000),
     "c3": dict(name="QINCo2-L 8x8 K=256 d=128 A=16 beam=16", cfg=dict(D=128, M=8, K=256, L=16, de=384, dh=384, A=16, B=16, qinco1_mode=False), n=100_000),
     "c3a0": dict(name="QINCo2-L 8x8 K=256 d=128 A=0 beam=16", cfg=dict(D=128, M=8, K=256, L=16, de=384, dh=384, A=0, B=16, qinco1_mode=False), n=8_192),
+    "livf": dict(name="IVF-QINCo2-L 8x8 K=256 d=128 A=16 beam=16, IVF 65536 centroids", cfg=dict(D=128, M=8, K=256, L=16, de=384, dh=384, A=16, B=16, qinco1_mode=False, ivf_K=65536), n=50_000),
     "q1": dict(name="QINCo1 8x8 K=256 d=128 L=16 beam=1", cfg=dict(D=128, M=8, K=256, L=16, de=128, dh=256, A=0, B=1, qinco1_mode=True), n=200_000),
 }
 
@@ -48,10 +49,13 @@ def flops_min_per_candidate(cfg):
 def encode_flops_min_per_vector(cfg):
     D, De, M, K, A, B = cfg["D"], cfg["de"], cfg["M"], cfg["K"], cfg["A"], cfg["B"]
     C = A or K
-    mac = K * D
-    for m in range(1, M):
-        f_in = B
-        mac += (f_in * K * D if A > 0 else 0) + f_in * C * (flops_min_per_candidate(cfg) // 2) + f_in * D * De
+    per_cand = flops_min_per_candidate(cfg) // 2
+    ivf_K = cfg.get("ivf_K") or 0
+    mac = (ivf_K or K) * D                      # step 0: plain codebook, or the IVF arg-min over ivf_K centroids
+    for m in range(1, M + (1 if ivf_K else 0)):
+        f_in = 1 if (ivf_K and m == 1) else B    # the step after an IVF step starts from one beam ...
+        c = (max(A, B) if A else K) if (ivf_K and m == 1) else C      # ... and pre-selects max(A, B) candidates
+        mac += (f_in * K * D if A > 0 else 0) + f_in * c * per_cand + f_in * D * De
     return 2 * mac
 
 
@@ -113,7 +117,7 @@ def make_model_inputs(wl, n, rank):
     import torch
     from qinco_b200 import synth
     cfg = synth.make_cfg(None, **wl["cfg"])
-    w = synth.make_weights(cfg, seed=4321, gain=0.5, n_train=8192, kmeans_iters=3)
+    w = synth.make_weights(cfg, seed=4321, gain=0.5, n_train=8192, kmeans_iters=1 if cfg.get("ivf_K") else 3)
     g = torch.Generator().manual_seed(1234 + rank)
     x = torch.randn(n, cfg["D"], generator=g, dtype=torch.float32)
     return cfg, w, x
@@ -323,8 +327,15 @@ def main():
     x_dev = x_pin.to(dev, non_blocking=True)
     gathered = torch.empty((world * n, cfg["M"]), dtype=torch.uint8, device=dev) if world > 1 else None
 
+    ivf = bool(cfg.get("ivf_K"))
+    if ivf:      # the CPU port has no IVF step; decode / e2e blocks use the plain entry points
+        args.no_cpu_baseline = args.no_e2e = args.no_decode = True
+
     def step():
-        codes, _ = model.encode_u8(x_dev, normalize=True, want_xhat=False)
+        if ivf:
+            _, codes, _ = model.encode_ivf_u8(x_dev, normalize=True, want_xhat=False)
+        else:
+            codes, _ = model.encode_u8(x_dev, normalize=True, want_xhat=False)
         if world > 1:
             dist.all_gather_into_tensor(gathered, codes)
         return codes

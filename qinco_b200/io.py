@@ -51,26 +51,42 @@ def cfg_from_v2_checkpoint(ckpt: dict, overrides: dict | None = None) -> dict:
     params.update(overrides)
     sd = ckpt["model"] if "model" in ckpt else ckpt
     D = int(ckpt.get("data_dim") or _np(sd["steps.0.codebook.weight"]).shape[1])
-    if params.get("ivf_in_use"):
-        raise NotImplementedError("IVF first step is not built yet (SURVEY.md section 8f row 2)")
-    M = params.get("M") or 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("steps."))
+    ivf = bool(params.get("ivf_in_use"))
+    n_step = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("steps."))       # cfg._M_ivf
+    M = params.get("M") or (n_step - 1 if ivf else n_step)
     K = params.get("K") or _np(sd["steps.0.codebook.weight"]).shape[0]
     L = params.get("L")
     if L is None:
         L = len({k.split(".")[3] for k in sd if k.startswith("steps.1.residual_blocks.")})
     de = params.get("de") or (_np(sd["steps.1.concat.mlp.weight"]).shape[0] if M > 1 else D)
     dh = params.get("dh") or (_np(sd["steps.1.residual_blocks.0.up_proj.weight"]).shape[0] if (M > 1 and L) else de)
-    return dict(D=D, M=int(M), K=int(K), L=int(L), de=int(de), dh=int(dh), A=int(params.get("A") or 0),
-                B=int(params.get("B") or 1), qinco1_mode=bool(params.get("qinco1_mode") or False))
+    cfg = dict(D=D, M=int(M), K=int(K), L=int(L), de=int(de), dh=int(dh), A=int(params.get("A") or 0),
+               B=int(params.get("B") or 1), qinco1_mode=bool(params.get("qinco1_mode") or False))
+    if ivf:         # IVF-QINCo: the centroids are a separate file (cfg.ivf_centroids), see load_v2_checkpoint
+        if not params.get("ivf_K"):
+            raise ValueError("an IVF checkpoint needs ivf_K (or the centroid file)")
+        cfg["ivf_K"] = int(params["ivf_K"])
+    return cfg
 
 
-def load_v2_checkpoint(path: str, overrides: dict | None = None):
-    """-> (cfg dict, state dict of numpy arrays) for qinco_b200.model.QINCo."""
+def load_v2_checkpoint(path: str, overrides: dict | None = None, ivf_centroids: str | None = None):
+    """-> (cfg dict, state dict of numpy arrays) for qinco_b200.model.QINCo.
+
+    `ivf_centroids`: the .npy the reference takes as cfg.ivf_centroids ([ivf_K, D], already normalised); it becomes
+    `steps.0.ivf_centroids.weight` like in qinco/qinco_tasks.py:565-569 and fixes ivf_K / D (qinco/utils.py:144-146)."""
     import torch
     ckpt = torch.load(str(path), map_location="cpu", weights_only=True)
-    cfg = cfg_from_v2_checkpoint(ckpt, overrides)
     sd = clean_v2_state_dict(ckpt["model"] if "model" in ckpt else ckpt)
-    return cfg, {k: _np(v) for k, v in sd.items()}
+    sd = {k: _np(v) for k, v in sd.items()}
+    overrides = dict(overrides or {})
+    if ivf_centroids is not None:
+        cent = np.load(ivf_centroids).astype(np.float32)
+        sd["steps.0.ivf_centroids.weight"] = cent
+        overrides.update(ivf_in_use=True, ivf_K=int(cent.shape[0]))
+    cfg = cfg_from_v2_checkpoint(dict(ckpt, model=sd) if "model" in ckpt else sd, overrides)
+    if cfg.get("ivf_K") and "steps.0.ivf_centroids.weight" not in sd:
+        raise ValueError("IVF checkpoint: pass ivf_centroids=<npy> (the reference's cfg.ivf_centroids)")
+    return cfg, sd
 
 
 def load_v1_checkpoint(path: str):

@@ -72,8 +72,8 @@ def test_v2_checkpoint_dict(tmp_path):
     assert np.array_equal(got_sd["steps.2.codebook.weight"], np.asarray(w["steps.2.codebook.weight"]))
     with pytest.raises(ValueError):      # A > 0 requested for a model trained with A = 0 (qinco/utils.py:166-169)
         io.cfg_from_v2_checkpoint({"model": sd, "parameters": {"A": 0, "M": 3, "K": 16, "L": 2}, "data_dim": 32}, dict(A=8))
-    with pytest.raises(NotImplementedError):
-        io.cfg_from_v2_checkpoint({"model": sd, "parameters": {"ivf_in_use": True}, "data_dim": 32})
+    ivf_cfg = io.cfg_from_v2_checkpoint({"model": sd, "parameters": {"ivf_in_use": True, "ivf_K": 1024, "L": 2}, "data_dim": 32})
+    assert ivf_cfg["ivf_K"] == 1024 and ivf_cfg["M"] == 2          # steps.0 is the IVF step: M = _M_ivf - 1
     # parameters missing: shapes are inferred from the tensors
     assert io.cfg_from_v2_checkpoint({"model": io.clean_v2_state_dict(sd)})["dh"] == 64
 
