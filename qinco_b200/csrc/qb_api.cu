@@ -42,14 +42,21 @@ int fail_cuda(cudaError_t e, const char* what) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+float row_norm2(const float* v, int n) {       // fp32 like the reference's (b ** 2).sum(-1)
+    float s = 0.f;
+    for (int i = 0; i < n; i++) s += v[i] * v[i];
+    return s;
+}
+
 struct StepDev {
     QbStepPlan plan;
     std::vector<QbOp> ops;
     uint8_t* w_blob = nullptr;
     float* t_blk = nullptr;
     float* cb_blk = nullptr;
-    float* wx_t = nullptr;
-    float* sub_cb_t = nullptr;   // [D][K] pre-selection codebook, transposed (A > 0)
+    float* wx = nullptr;         // [De][D] = Wcat[:, De:]
+    float* sub_cb = nullptr;     // [K][D] pre-selection codebook (A > 0)
+    float* sub_norm = nullptr;   // [K] squared row norms of sub_cb
 };
 
 struct HostSlot {
@@ -77,7 +84,7 @@ struct qb_model {
     int stagger = 0;
     bool has_mean = false;
     float* cb0 = nullptr;      // [K][D]
-    float* cb0_t = nullptr;    // [D][K]
+    float* cb0_norm = nullptr; // [K] squared row norms of cb0
     float* mean = nullptr;     // [D]
     std::vector<StepDev> steps;   // index m, entry 0 unused
     uint32_t* err_host = nullptr;   // mapped pinned word written by the kernels before they trap
@@ -160,7 +167,8 @@ constexpr size_t kWsSlack = 16 * 256;   // alignment padding of the carve-up
 
 int64_t default_chunk(const qb_model* m) {
     const int64_t rows_per_vec = (int64_t)m->B * (m->A > 0 ? m->A : m->K);
-    int64_t c = (int64_t)(4 << 20) / rows_per_vec;
+    static const int64_t rows_env = getenv("QB_CHUNK_ROWS") ? atoll(getenv("QB_CHUNK_ROWS")) : 0;   // tuning knob
+    int64_t c = (rows_env > 0 ? rows_env : (int64_t)(16 << 20)) / rows_per_vec;
     c = std::max<int64_t>(c, 1024);
     return c / 128 * 128;
 }
@@ -249,7 +257,7 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, int32_t*
         std::memset(&p, 0, sizeof(p));
         p.D = D; p.De = m->De; p.K = K; p.A = F1; p.F = 1; p.step0 = 1; p.M = M;
         p.n_beams = n; p.x = x; p.mean = mean; p.inv_std = inv_std_div;
-        p.xhat = m->cb0; p.sub_cb = m->cb0_t;
+        p.sub_cb = m->cb0; p.sub_norm = m->cb0_norm;
         p.xhat_out = (M == 1 && xhat_out) ? xhat_out : w.xhat[cur];
         p.hist_out = (M == 1) ? codes : w.hist[cur];
         QB_CUDA(timed_launch(m, KIND_PREP, n, st, [&] { return qb::launch_prep(p, st); }));
@@ -268,7 +276,7 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, int32_t*
             std::memset(&p, 0, sizeof(p));
             p.D = D; p.De = m->De; p.K = K; p.A = A; p.F = F_in; p.step0 = 0; p.M = M;
             p.n_beams = n * F_in; p.x = x; p.mean = mean; p.inv_std = inv_std_div;
-            p.xhat = w.xhat[cur]; p.wx_t = s.wx_t; p.sub_cb = A > 0 ? s.sub_cb_t : nullptr;
+            p.xhat = w.xhat[cur]; p.wx = s.wx; p.sub_cb = A > 0 ? s.sub_cb : nullptr; p.sub_norm = s.sub_norm;
             p.r = w.r; p.u = w.u; p.idx = w.idx;
             QB_CUDA(timed_launch(m, KIND_PREP, p.n_beams, st, [&] { return qb::launch_prep(p, st); }));
         }
@@ -338,7 +346,7 @@ int decode_chunk(qb_model* m, const int32_t* ivf_codes, const uint8_t* codes, in
             std::memset(&p, 0, sizeof(p));
             p.D = D; p.De = m->De; p.K = m->K; p.A = 0; p.F = 1; p.step0 = 0; p.M = M;
             p.n_beams = n; p.x = xh[cur]; p.inv_std = 1.f;
-            p.xhat = xh[cur]; p.wx_t = s.wx_t; p.u = u;
+            p.xhat = xh[cur]; p.wx = s.wx; p.u = u;
             QB_CUDA(timed_launch(m, KIND_PREP, n, st, [&] { return qb::launch_prep(p, st); }));
         }
         {
@@ -432,19 +440,14 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
 
     if (m->ivf_K) {     // step 0: frozen IVF centroids and their squared norms (IVFBook, qinco_base.py:128-146)
         std::vector<float> cn((size_t)m->ivf_K);
-        for (int k = 0; k < m->ivf_K; k++) {
-            float sacc = 0.f;
-            for (int dd = 0; dd < D; dd++) sacc += d->ivf_centroids[(size_t)k * D + dd] * d->ivf_centroids[(size_t)k * D + dd];
-            cn[k] = sacc;
-        }
+        for (int k = 0; k < m->ivf_K; k++) cn[k] = row_norm2(d->ivf_centroids + (size_t)k * D, D);
         if ((rc = dev_upload(m, d->ivf_centroids, (size_t)m->ivf_K * D, &m->ivf_cent))) return bail(rc);
         if ((rc = dev_upload(m, cn.data(), cn.size(), &m->ivf_cnorm))) return bail(rc);
-    } else {            // step 0: plain codebook, row-major and transposed
-        std::vector<float> t((size_t)D * K);
-        for (int k = 0; k < K; k++)
-            for (int dd = 0; dd < D; dd++) t[(size_t)dd * K + k] = d->codebook[0][(size_t)k * D + dd];
+    } else {            // step 0: plain codebook and its squared row norms
+        std::vector<float> nrm((size_t)K);
+        for (int k = 0; k < K; k++) nrm[k] = row_norm2(d->codebook[0] + (size_t)k * D, D);
         if ((rc = dev_upload(m, d->codebook[0], (size_t)K * D, &m->cb0))) return bail(rc);
-        if ((rc = dev_upload(m, t.data(), t.size(), &m->cb0_t))) return bail(rc);
+        if ((rc = dev_upload(m, nrm.data(), nrm.size(), &m->cb0_norm))) return bail(rc);
     }
     if (d->data_mean) {
         bool nz = false;
@@ -482,12 +485,17 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         if ((rc = dev_upload(m, (const uint8_t*)blob.data(), blob.size() * 2, &sd.w_blob))) return bail(rc);
         if ((rc = dev_upload(m, t_blk.data(), t_blk.size(), &sd.t_blk))) return bail(rc);
         if ((rc = dev_upload(m, cb_blk.data(), cb_blk.size(), &sd.cb_blk))) return bail(rc);
-        if ((rc = dev_upload(m, wx_t.data(), wx_t.size(), &sd.wx_t))) return bail(rc);
+        {   // Wx = Wcat[:, De:] as [De][D] rows (build_tables hands back its transpose)
+            std::vector<float> wx((size_t)De * D);
+            for (int e = 0; e < De; e++)
+                for (int dd = 0; dd < D; dd++) wx[(size_t)e * D + dd] = wx_t[(size_t)dd * De + e];
+            if ((rc = dev_upload(m, wx.data(), wx.size(), &sd.wx))) return bail(rc);
+        }
         if (m->A > 0) {
-            std::vector<float> t((size_t)D * K);
-            for (int k = 0; k < K; k++)
-                for (int dd = 0; dd < D; dd++) t[(size_t)dd * K + k] = d->substep_codebook[s][(size_t)k * D + dd];
-            if ((rc = dev_upload(m, t.data(), t.size(), &sd.sub_cb_t))) return bail(rc);
+            std::vector<float> nrm((size_t)K);
+            for (int k = 0; k < K; k++) nrm[k] = row_norm2(d->substep_codebook[s] + (size_t)k * D, D);
+            if ((rc = dev_upload(m, d->substep_codebook[s], (size_t)K * D, &sd.sub_cb))) return bail(rc);
+            if ((rc = dev_upload(m, nrm.data(), nrm.size(), &sd.sub_norm))) return bail(rc);
         }
         max_smem = std::max(max_smem, sd.plan.smem_total);
     }
@@ -738,7 +746,7 @@ int qb_debug_step(qb_model* m, int step, const float* xhat_dev, const uint8_t* c
     qb::PrepParams pp;
     std::memset(&pp, 0, sizeof(pp));
     pp.D = m->D; pp.De = m->De; pp.K = m->K; pp.F = 1; pp.M = m->M; pp.n_beams = n;
-    pp.x = xhat_dev; pp.inv_std = 1.f; pp.xhat = xhat_dev; pp.wx_t = s.wx_t; pp.u = u;
+    pp.x = xhat_dev; pp.inv_std = 1.f; pp.xhat = xhat_dev; pp.wx = s.wx; pp.u = u;
     QB_CUDA(qb::launch_prep(pp, st));
     qb::MlpParams p = base_mlp(m, step);
     p.mode = qb::QB_MODE_APPLY;

@@ -41,7 +41,6 @@ struct MlpParams {
     float out_scale;          // apply
     const float* out_shift;   // apply: [D] or NULL
     uint32_t* err_flag;       // device word set non-zero when a barrier wait timed out
-    int32_t exp;              // debug: experiment bits from the QB_EXP environment variable (0 in production)
     unsigned long long* trace;   // debug: per-role event log of CTA 0 ([3][QB_TRACE_EVENTS] of clock<<16 | id), or NULL
 };
 
@@ -62,8 +61,9 @@ struct PrepParams {
     const float* mean;        // [D] or NULL
     float inv_std;            // DIVISOR applied after the mean shift: data_std, or 1 (name kept for the struct layout)
     const float* xhat;        // [n_beams, D] (unused for step0)
-    const float* wx_t;        // [D][De]      (NULL: skip u)
+    const float* wx;          // [De][D] = Wcat[:, De:]  (NULL: skip u)
     const float* sub_cb;      // [K][D] pre-selection codebook (step0: C_0); NULL: skip selection
+    const float* sub_norm;    // [K] squared norms of sub_cb's rows
     float* r;                 // [n_beams, D] or NULL
     float* u;                 // [n_beams, De]
     uint8_t* idx;             // [n_beams, A]

@@ -12,7 +12,8 @@ namespace qb {
 namespace {
 
 constexpr int kPrepThreads = 256;
-constexpr int kPrepRows = 16;   // (vector, beam) rows per block
+constexpr int kPrepRows = 64;                 // (vector, beam) rows per block
+constexpr int kTileN = 64, kTileD = 16, kTileLD = kTileD + 4;   // output tile, D chunk, padded shared-memory row
 
 // lexicographic (value, index) minimum across the warp
 __device__ __forceinline__ void warp_argmin(float& v, int& i) {
@@ -24,107 +25,158 @@ __device__ __forceinline__ void warp_argmin(float& v, int& i) {
     }
 }
 
-// Reference: QincoSubstep.get_distances_for_codes / select_code_candidates (qinco_base.py:114-121), the hoisted
-// half of QConcat (:60-64: Wcat[:, De:] . xhat), and for step 0 QINCoInferenceEncoder.forward's first lines
-// (qinco_inference.py:239-246).
+// Beam preparation for one step (reference: QincoSubstep.get_distances_for_codes / select_code_candidates,
+// qinco_base.py:114-121; the hoisted half of QConcat, :60-64: Wcat[:, De:] . xhat; for step 0 the first lines of
+// QINCoInferenceEncoder.forward, qinco_inference.py:239-246).  Two register-tiled fp32 "GEMMs" per block of 64 rows, both
+// in the shape of the IVF kernel below (16 x 16 threads, 4 x 4 dot products each, D in chunks of 16 through shared memory):
+//   u[b][e]    = xhat_b . Wx[e]                                     (written straight from registers)
+//   dpre[b][k] = (|r_b|^2 + |S_k|^2) - 2 r_b . S_k                  (the reference's approx_pairwise_distance form,
+//                utils.py:336-346, which is what it uses for > 32 rows) -> shared memory -> top-A per row
 __global__ void __launch_bounds__(kPrepThreads) qb_prep_kernel(const PrepParams p) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(16) float dpre[];          // [kPrepRows][K] (only with a codebook to rank against)
+    __shared__ __align__(16) float xs[kPrepRows * kTileLD];
+    __shared__ __align__(16) float cs[kTileN * kTileLD];
+    __shared__ float anorm_s[kPrepRows];
     const int D = p.D, De = p.De, K = p.K;
-    float* xs = sm;                          // [kPrepRows][D]  xhat rows
-    float* rs = xs + kPrepRows * D;          // [kPrepRows][D]  residual rows
-    float* dpre = rs + kPrepRows * D;        // [kPrepRows][K]
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
     const int64_t b0 = (int64_t)blockIdx.x * kPrepRows;
     const int nrow = (int)min((int64_t)kPrepRows, p.n_beams - b0);
+    const int lrow = tid >> 2, lc4 = (tid & 3) * 4;          // this thread's float4 of a 64 x 16 chunk
 
-    for (int t = tid; t < kPrepRows * D; t += kPrepThreads) {
-        const int i = t / D, d = t - i * D;
-        float xh = 0.f, r = 0.f;
-        if (i < nrow) {
-            const int64_t b = b0 + i;
-            const int64_t v = b / p.F;
-            float xn = p.x[v * D + d];
-            if (p.mean) xn -= p.mean[d];
-            xn /= p.inv_std;   // the reference divides: (x - mean) / std (qinco_base.py:533)
-            if (!p.step0) xh = p.xhat[b * D + d];
-            r = xn - xh;
-            if (p.r) p.r[b * D + d] = r;
+    // one float4 of row lrow, columns d0 + lc4 ..: the beam's xhat (kind 0) or its residual r = xn - xhat (kind 1)
+    auto load_a = [&](int kind, int d0, bool store_r) {
+        float4 xh = make_float4(0.f, 0.f, 0.f, 0.f), r = xh;
+        if (lrow < nrow) {
+            const int64_t b = b0 + lrow;
+            const int d = d0 + lc4;
+            if (!p.step0) xh = *reinterpret_cast<const float4*>(p.xhat + b * D + d);
+            if (kind == 1) {
+                float4 xn = *reinterpret_cast<const float4*>(p.x + (b / p.F) * D + d);
+                if (p.mean) {
+                    const float4 m = *reinterpret_cast<const float4*>(p.mean + d);
+                    xn.x -= m.x; xn.y -= m.y; xn.z -= m.z; xn.w -= m.w;
+                }
+                // the reference divides: (x - mean) / std (qinco_base.py:533); inv_std holds the divisor
+                xn.x /= p.inv_std; xn.y /= p.inv_std; xn.z /= p.inv_std; xn.w /= p.inv_std;
+                r = make_float4(xn.x - xh.x, xn.y - xh.y, xn.z - xh.z, xn.w - xh.w);
+                if (store_r && p.r) *reinterpret_cast<float4*>(p.r + b * D + d) = r;
+            }
         }
-        xs[t] = xh;
-        rs[t] = r;
+        return kind == 1 ? r : xh;
+    };
+    // acc[a][b] = A-row (ti + 16 a) . B-row (n0 + tj + 16 b) over all of D; B is [n_out][D] row-major
+    auto tile_gemm = [&](int kind, const float* __restrict__ B, int n_out, int n0, bool store_r, float (&acc)[4][4]) {
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+        for (int d0 = 0; d0 < D; d0 += kTileD) {
+            __syncthreads();
+            const float4 av = load_a(kind, d0, store_r);
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + lrow < n_out) bv = __ldg(reinterpret_cast<const float4*>(B + (size_t)(n0 + lrow) * D + d0 + lc4));
+            *reinterpret_cast<float4*>(xs + lrow * kTileLD + lc4) = av;
+            *reinterpret_cast<float4*>(cs + lrow * kTileLD + lc4) = bv;
+            __syncthreads();
+#pragma unroll
+            for (int d = 0; d < kTileD; d += 4) {
+                float4 xa[4], cb[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) xa[a] = *reinterpret_cast<const float4*>(xs + (ti + 16 * a) * kTileLD + d);
+#pragma unroll
+                for (int b = 0; b < 4; b++) cb[b] = *reinterpret_cast<const float4*>(cs + (tj + 16 * b) * kTileLD + d);
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        acc[a][b] = fmaf(xa[a].x, cb[b].x, acc[a][b]); acc[a][b] = fmaf(xa[a].y, cb[b].y, acc[a][b]);
+                        acc[a][b] = fmaf(xa[a].z, cb[b].z, acc[a][b]); acc[a][b] = fmaf(xa[a].w, cb[b].w, acc[a][b]);
+                    }
+            }
+        }
+    };
+
+    float acc[4][4];
+    if (p.wx) {          // u[b][e] = Wx[e] . xhat[b]
+        for (int e0 = 0; e0 < De; e0 += kTileN) {
+            tile_gemm(0, p.wx, De, e0, false, acc);
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int row = ti + 16 * a;
+                if (row < nrow)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int e = e0 + tj + 16 * b;
+                        if (e < De) p.u[(b0 + row) * De + e] = acc[a][b];
+                    }
+            }
+        }
+    }
+    if (!p.sub_cb) {     // no ranking in this launch: r still has to be written (A == 0 scoring reads it)
+        if (p.r)
+            for (int d0 = 0; d0 < D; d0 += kTileD) load_a(1, d0, true);
+        return;
+    }
+    // |r|^2 of the block's rows: 4 threads per row, same element order for every candidate of the row
+    {
+        float s = 0.f;
+        if (lrow < nrow) {
+            const int64_t b = b0 + lrow;
+            for (int d = (tid & 3); d < D; d += 4) {
+                float xn = p.x[(b / p.F) * D + d];
+                if (p.mean) xn -= p.mean[d];
+                xn /= p.inv_std;
+                const float r = xn - (p.step0 ? 0.f : p.xhat[b * D + d]);
+                s = fmaf(r, r, s);
+            }
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if ((tid & 3) == 0) anorm_s[lrow] = s;
+    }
+    for (int k0 = 0; k0 < K; k0 += kTileN) {
+        tile_gemm(1, p.sub_cb, K, k0, k0 == 0, acc);       // (the first pass also writes r; anorm_s is ordered by its barriers)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int k = k0 + tj + 16 * b;
+            if (k < K) {
+                const float bn = __ldg(p.sub_norm + k);
+#pragma unroll
+                for (int a = 0; a < 4; a++) dpre[(ti + 16 * a) * K + k] = (anorm_s[ti + 16 * a] + bn) - 2.f * acc[a][b];
+            }
+        }
     }
     __syncthreads();
-
-    if (p.wx_t) {   // u[b][e] = sum_d Wx[e][d] * xhat[b][d]
-        for (int e = tid; e < De; e += kPrepThreads) {
-            float acc[kPrepRows];
+    // the A smallest per row, ascending, ties to the lower index (torch.topk(largest=False) order)
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = warp; i < nrow; i += kPrepThreads / 32) {
+        const int64_t b = b0 + i;
+        float vals[8];
 #pragma unroll
-            for (int i = 0; i < kPrepRows; i++) acc[i] = 0.f;
-            for (int d = 0; d < D; d += 4) {
-                const float w0 = __ldg(p.wx_t + (size_t)(d + 0) * De + e), w1 = __ldg(p.wx_t + (size_t)(d + 1) * De + e);
-                const float w2 = __ldg(p.wx_t + (size_t)(d + 2) * De + e), w3 = __ldg(p.wx_t + (size_t)(d + 3) * De + e);
-#pragma unroll
-                for (int i = 0; i < kPrepRows; i++) {
-                    const float4 xv = *reinterpret_cast<const float4*>(xs + i * D + d);
-                    acc[i] = fmaf(w0, xv.x, acc[i]); acc[i] = fmaf(w1, xv.y, acc[i]);
-                    acc[i] = fmaf(w2, xv.z, acc[i]); acc[i] = fmaf(w3, xv.w, acc[i]);
-                }
-            }
-            for (int i = 0; i < nrow; i++) p.u[(b0 + i) * De + e] = acc[i];
+        for (int j = 0; j < 8; j++) {
+            const int k = lane + 32 * j;
+            vals[j] = k < K ? dpre[i * K + k] : FLT_MAX;
         }
-    }
-
-    if (p.sub_cb) {   // dpre[i][k] = ||r_i - S[k]||^2 with S stored transposed [D][K]
-        for (int k = tid; k < K; k += kPrepThreads) {
-            float acc[kPrepRows];
-#pragma unroll
-            for (int i = 0; i < kPrepRows; i++) acc[i] = 0.f;
-            for (int d = 0; d < D; d += 4) {
-                const float s0 = __ldg(p.sub_cb + (size_t)(d + 0) * K + k), s1 = __ldg(p.sub_cb + (size_t)(d + 1) * K + k);
-                const float s2 = __ldg(p.sub_cb + (size_t)(d + 2) * K + k), s3 = __ldg(p.sub_cb + (size_t)(d + 3) * K + k);
-#pragma unroll
-                for (int i = 0; i < kPrepRows; i++) {
-                    const float4 rv = *reinterpret_cast<const float4*>(rs + i * D + d);
-                    const float e0 = rv.x - s0, e1 = rv.y - s1, e2 = rv.z - s2, e3 = rv.w - s3;
-                    acc[i] = fmaf(e0, e0, acc[i]); acc[i] = fmaf(e1, e1, acc[i]);
-                    acc[i] = fmaf(e2, e2, acc[i]); acc[i] = fmaf(e3, e3, acc[i]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < kPrepRows; i++) dpre[i * K + k] = acc[i];
-        }
-        __syncthreads();
-        // the A smallest per row, ascending, ties to the lower index (torch.topk(largest=False) order)
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int i = warp; i < nrow; i += kPrepThreads / 32) {
-            const int64_t b = b0 + i;
-            float vals[8];
+        for (int a = 0; a < p.A; a++) {
+            float bv = FLT_MAX;
+            int bi = 0x7fffffff;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int k = lane + 32 * j;
-                vals[j] = k < K ? dpre[i * K + k] : FLT_MAX;
+                if (k < K && (vals[j] < bv || (vals[j] == bv && k < bi))) { bv = vals[j]; bi = k; }
             }
-            for (int a = 0; a < p.A; a++) {
-                float bv = FLT_MAX;
-                int bi = 0x7fffffff;
+            warp_argmin(bv, bi);
+            if (bi >= K) bi = 0;   // all-NaN row: stay in range
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int k = lane + 32 * j;
-                    if (k < K && (vals[j] < bv || (vals[j] == bv && k < bi))) { bv = vals[j]; bi = k; }
-                }
-                warp_argmin(bv, bi);
-                if (bi >= K) bi = 0;   // all-NaN row: stay in range
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    if (lane + 32 * j == bi) vals[j] = FLT_MAX;
-                if (!p.step0) {
-                    if (lane == 0) p.idx[b * p.A + a] = (uint8_t)bi;
-                } else {
-                    // first step: beam a of vector b starts at codeword bi of C_0 (row-major copy in xhat = p.xhat)
-                    if (lane == 0) p.hist_out[(b * p.A + a) * p.M] = (uint8_t)bi;
-                    for (int d = lane; d < D; d += 32)
-                        p.xhat_out[(b * p.A + a) * D + d] = __ldg(p.xhat + (size_t)bi * D + d);
-                }
+            for (int j = 0; j < 8; j++)
+                if (lane + 32 * j == bi) vals[j] = FLT_MAX;
+            if (!p.step0) {
+                if (lane == 0) p.idx[b * p.A + a] = (uint8_t)bi;
+            } else {
+                // first step: beam a of vector b starts at codeword bi of C_0 (row-major, = the ranking codebook)
+                if (lane == 0) p.hist_out[(b * p.A + a) * p.M] = (uint8_t)bi;
+                for (int d = lane; d < D; d += 32)
+                    p.xhat_out[(b * p.A + a) * D + d] = __ldg(p.sub_cb + (size_t)bi * D + d);
             }
         }
     }
@@ -165,7 +217,7 @@ __global__ void __launch_bounds__(256) qb_select_kernel(const SelectParams p) {
 
 // ---- IVF first step: tiled fp32 "GEMM + arg-min".  Block = 64 vectors; centroids in tiles of 64, D in chunks of 16; thread
 // (ti, tj) of a 16 x 16 grid owns vectors ti + 16 a and centroids tj + 16 b (a, b < 4): 16 dot products in registers.
-constexpr int kIvfVB = 64, kIvfCT = 64, kIvfDC = 16, kIvfLD = kIvfDC + 4;   // +4 floats: rows 16 B apart in bank space
+constexpr int kIvfVB = kPrepRows, kIvfCT = kTileN, kIvfDC = kTileD, kIvfLD = kTileLD;   // +4 floats: rows 16 B apart in bank space
 
 __global__ void __launch_bounds__(256) qb_ivf_assign_kernel(const IvfParams p) {
     __shared__ __align__(16) float xs[kIvfVB * kIvfLD];
@@ -305,8 +357,8 @@ __global__ void qb_affine_kernel(const float* __restrict__ in, float* __restrict
 
 cudaError_t launch_prep(const PrepParams& p, cudaStream_t stream) {
     if (p.n_beams <= 0) return cudaSuccess;
-    if (p.K > 256 || p.D % 4) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)(2 * kPrepRows * p.D + kPrepRows * p.K) * sizeof(float);
+    if (p.K > 256 || p.D % 16) return cudaErrorInvalidValue;
+    const size_t smem = p.sub_cb ? (size_t)kPrepRows * p.K * sizeof(float) : 0;
     static size_t attr_set = 0;
     if (smem > 48 * 1024 && smem > attr_set) {
         cudaError_t e = cudaFuncSetAttribute(qb_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

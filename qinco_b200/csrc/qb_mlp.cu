@@ -4,23 +4,25 @@
 // (reference qinco/model/qinco_base.py:262-280 = in_proj, QConcat :60-64, L x QBlockFFN :93-97, out_proj, skip;
 // the distance of :343-345 and the x-hat update of :363-369) with ONE persistent kernel:
 //
-//   warps 0-3  epilogue: thread t owns row t of the tile == TMEM lane t.
-//              init    e0 = T_m[code] + u_b  -> fp32 into the TMEM residual accumulator (tcgen05.st)
+//   warps 0-7  epilogue (two warpgroups): thread (lane quarter q = warp % 4, lane) owns row 32 q + lane of BOTH tiles in
+//              flight == TMEM lane; the two warps of a lane quarter split every column range.
+//              init    e0 = T_m[code] + u_b  -> fp32 into the TMEM residual accumulator (tcgen05.st.x32)
 //                                             -> fp16 into the A_E operand tile in shared memory
-//              H-epi   relu(Hacc) -> packed fp16 written back IN PLACE into TMEM (A operand of the down-projection)
+//              H-epi   relu(Hacc) -> packed fp16 written back IN PLACE into TMEM (A operand of the down-projection),
+//                      handed to the issuer in two K halves
 //              E-epi   Eacc -> fp16 -> A_E                               (per residual block)
 //              final   score: dist = ||r_b - o||^2 (fp32)   apply: xhat_out = xhat_b + o
-//              (TMEM reads are latency-bound, ~130 cycles per tcgen05.ld: every phase keeps the next load in flight
-//               while it converts the current one; table rows are fetched 64 columns at a time, all loads up front)
-//   warp 4     producer: streams the pre-packed fp16 weight slabs with cp.async.bulk (TMA) into an mbarrier ring
-//   warp 5     MMA issuer: walks the op list (qb_plan.h, in the kernel-parameter constant bank) and issues
-//              tcgen05.mma (M=128, kind::f16, fp32 accumulate in TMEM): up-projection A from shared memory,
+//   warp 8     producer: streams the pre-packed fp16 weight slabs with cp.async.bulk (TMA) into an mbarrier ring
+//   warp 9-10  MMA issuers, one per tile slot: walk the op list (qb_plan.h, in the kernel-parameter constant bank) and
+//              issue tcgen05.mma (M=128, kind::f16, fp32 accumulate in TMEM): up-projection A from shared memory,
 //              down-projection A from TMEM; completion is signalled with tcgen05.commit
+//   warp 11    idle (completes the service warpgroup for setmaxnreg)
 //
-// Warps 4 and 5 run converged and only predicate the asynchronous instructions with elect.sync, so descriptors stay
-// in uniform registers (no per-MMA divergence handling).  The fp32 residual stream never leaves TMEM; activations
-// never touch HBM.  When a tile needs <= 256 TMEM columns two CTAs share an SM (plan.ctas_per_sm): one CTA's table
-// gathers and distance epilogue overlap the other CTA's MMAs.
+// The service warps run converged and only predicate the asynchronous instructions with elect.sync, so descriptors stay
+// in uniform registers.  An issuing warp retires ~1 instruction per 6.5 cycles, which makes the issuer's SASS instruction
+// count (not the tensor pipe) the first bound: see mma_slab / the issuer loop.  The fp32 residual stream never leaves
+// TMEM; activations never touch HBM.  kPair = true is the cta_group::2 variant (one M=256 MMA over a CTA pair, half of
+// every weight slab per CTA); DESIGN.md section 5.1 has the measurements behind each of these choices.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -81,17 +83,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ uint64_t globaltimer() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -115,24 +106,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
     }
 }
 
-// Busy-polling wait (mbarrier.test_wait never suspends the thread): for the single-warp roles whose wake-up latency is on
-// the critical path.
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, uint32_t* err_flag, uint32_t code) {
-    uint32_t spins = 0;
-    uint64_t t0 = 0;
-    while (!mbar_test_wait(bar, parity)) {
-        if ((++spins & 0xffffu) == 0) {
-            const uint64_t now = globaltimer();
-            if (t0 == 0) t0 = now;
-            if (now - t0 > 4000000000ull) {
-                if (err_flag) atomicExch(err_flag, code);
-                __threadfence_system();
-                __trap();
-            }
-        }
-    }
-}
-
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -147,29 +120,6 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// D[tmem] (+)= A[smem] . B[smem]^T, M=128, kind::f16 (fp16 inputs, fp32 accumulate)
-__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :
-        : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem]^T  (A: 128 lanes x 8 columns of packed fp16 pairs per K=16)
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        :
-        : "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
 }
 
 // ---- CTA pair (cta_group::2): one M=256 MMA spans the two CTAs of a cluster; each CTA holds its own 128 rows of A and
@@ -198,27 +148,6 @@ __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
                  "h"((uint16_t)3)
                  : "memory");
 }
-__device__ __forceinline__ void tc_mma_ss_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :
-        : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        :
-        : "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
 // One K=16 MMA whose operand descriptors advance in place (low descriptor word += step; the address field never carries
 // into the LBO field).  Written so that ptxas keeps everything in uniform registers: 5 instructions per MMA when
 // unrolled.  kPairI selects cta_group::2.
@@ -276,15 +205,6 @@ __device__ __forceinline__ void mma_slab(int nk, uint32_t d, uint32_t& a, uint32
     }
 }
 
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE ("interleave") canonical layout
-//   ((8,m),(8,2)) : ((16 B, SBO), (2 B, LBO))      (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::K>)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;   // descriptor version 1 (sm_100)
-    return d;                 // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
-}
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
 __device__ __forceinline__ uint32_t umma_idesc(uint32_t n, uint32_t m = QB_TILE_M) {
     return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
@@ -362,14 +282,6 @@ __device__ __forceinline__ float lds1(uint32_t addr) {
 }
 __device__ __forceinline__ void sts1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-// same load, but pinned in program order (asm volatile): for operands that should be fetched just in time from L1
-// instead of being hoisted by the compiler into a long-lived register block
-__device__ __forceinline__ float4 ldg4_jit(const float* p) {
-    float4 v;
-    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Loads nc (16 or 32) fp32 accumulator columns; the caller waits.  With nc == 16 the upper half is zeroed so that no
@@ -1146,10 +1058,8 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
         if (pair) grid = (grid + 1) & ~1;                      // whole pairs; a peer without work of its own follows its leader
         if (pair && grid > n_sm) grid = n_sm & ~1;
     }
-    static const int exp_bits = getenv("QB_EXP") ? atoi(getenv("QB_EXP")) : 0;
     auto launch = [&](const MlpParams& q0) {
         MlpParams q = q0;
-        q.exp = exp_bits;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((unsigned)grid);
