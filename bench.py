@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the QINCo2 encode hot path on B200 (contract: see the task brief / DESIGN.md section "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2a16|c3|c3a0|q1] [--n VECTORS_PER_GPU]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2a16|c3|c3a0|c4|c5|q1|livf|c5pw] [--n VECTORS_PER_GPU]
     python bench.py --impl reference ...      # the reference's PyTorch-CPU path (oracle/torch_port.py) on the host cores
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
@@ -34,6 +34,8 @@ WORKLOADS = {
     "c2a16": dict(name="QINCo2-S 8x8 K=256 d=128 A=16 beam=1", cfg=dict(D=128, M=8, K=256, L=2, de=128, dh=256, A=16, B=1, qinco1_mode=False), n=1_000_000),
     "c3": dict(name="QINCo2-L 8x8 K=256 d=128 A=16 beam=16", cfg=dict(D=128, M=8, K=256, L=16, de=384, dh=384, A=16, B=16, qinco1_mode=False), n=100_000),
     "c3a0": dict(name="QINCo2-L 8x8 K=256 d=128 A=0 beam=16", cfg=dict(D=128, M=8, K=256, L=16, de=384, dh=384, A=0, B=16, qinco1_mode=False), n=8_192),
+    "c4": dict(name="QINCo2-L 16x8 K=256 d=96 (Deep1B shape) A=16 beam=16", cfg=dict(D=96, M=16, K=256, L=16, de=384, dh=384, A=16, B=16, qinco1_mode=False), n=50_000),
+    "c5": dict(name="QINCo2-L 8x8 K=256 d=768 (Contriever shape) A=16 beam=32", cfg=dict(D=768, M=8, K=256, L=16, de=384, dh=384, A=16, B=32, qinco1_mode=False), n=50_000),
     "livf": dict(name="IVF-QINCo2-L 8x8 K=256 d=128 A=16 beam=16, IVF 65536 centroids", cfg=dict(D=128, M=8, K=256, L=16, de=384, dh=384, A=16, B=16, qinco1_mode=False, ivf_K=65536), n=50_000),
     "q1": dict(name="QINCo1 8x8 K=256 d=128 L=16 beam=1", cfg=dict(D=128, M=8, K=256, L=16, de=128, dh=256, A=0, B=1, qinco1_mode=True), n=200_000),
 }

@@ -70,14 +70,19 @@ __global__ void __launch_bounds__(kPrepThreads) qb_prep_kernel(const PrepParams 
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
-        for (int d0 = 0; d0 < D; d0 += kTileD) {
-            __syncthreads();
-            const float4 av = load_a(kind, d0, store_r);
+        // the next chunk's global loads are issued before the current chunk's FMAs (register double buffering)
+        auto load_b = [&](int d0) {
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (n0 + lrow < n_out) bv = __ldg(reinterpret_cast<const float4*>(B + (size_t)(n0 + lrow) * D + d0 + lc4));
+            return bv;
+        };
+        float4 av = load_a(kind, 0, store_r), bv = load_b(0);
+        for (int d0 = 0; d0 < D; d0 += kTileD) {
+            __syncthreads();
             *reinterpret_cast<float4*>(xs + lrow * kTileLD + lc4) = av;
             *reinterpret_cast<float4*>(cs + lrow * kTileLD + lc4) = bv;
             __syncthreads();
+            if (d0 + kTileD < D) { av = load_a(kind, d0 + kTileD, store_r); bv = load_b(d0 + kTileD); }
 #pragma unroll
             for (int d = 0; d < kTileD; d += 4) {
                 float4 xa[4], cb[4];
@@ -253,24 +258,33 @@ __global__ void __launch_bounds__(256) qb_ivf_assign_kernel(const IvfParams p) {
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+        // 64 rows x 16 columns per chunk: one float4 of x and one of the centroids per thread, the next chunk's loads in
+        // flight while the current chunk's FMAs run
+        const int row = tid >> 2, c4 = (tid & 3) * 4;
+        auto load_x = [&](int d0) {
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v0 + row < p.n) {
+                xv = *reinterpret_cast<const float4*>(p.x + (v0 + row) * D + d0 + c4);
+                if (p.mean) {
+                    const float4 m = *reinterpret_cast<const float4*>(p.mean + d0 + c4);
+                    xv.x -= m.x; xv.y -= m.y; xv.z -= m.z; xv.w -= m.w;
+                }
+                xv.x /= p.std_div; xv.y /= p.std_div; xv.z /= p.std_div; xv.w /= p.std_div;
+            }
+            return xv;
+        };
+        auto load_c = [&](int d0) {
+            float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + row < p.ivf_K) cv = __ldg(reinterpret_cast<const float4*>(p.cent + (size_t)(k0 + row) * D + d0 + c4));
+            return cv;
+        };
+        float4 xv = load_x(0), cv = load_c(0);
         for (int d0 = 0; d0 < D; d0 += kIvfDC) {
             __syncthreads();
-            {   // 64 rows x 16 columns each: one float4 per thread per tile
-                const int row = tid >> 2, c4 = (tid & 3) * 4;
-                float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), cv = xv;
-                if (v0 + row < p.n) {
-                    xv = *reinterpret_cast<const float4*>(p.x + (v0 + row) * D + d0 + c4);
-                    if (p.mean) {
-                        const float4 m = *reinterpret_cast<const float4*>(p.mean + d0 + c4);
-                        xv.x -= m.x; xv.y -= m.y; xv.z -= m.z; xv.w -= m.w;
-                    }
-                    xv.x /= p.std_div; xv.y /= p.std_div; xv.z /= p.std_div; xv.w /= p.std_div;
-                }
-                if (k0 + row < p.ivf_K) cv = __ldg(reinterpret_cast<const float4*>(p.cent + (size_t)(k0 + row) * D + d0 + c4));
-                *reinterpret_cast<float4*>(xs + row * kIvfLD + c4) = xv;
-                *reinterpret_cast<float4*>(cs + row * kIvfLD + c4) = cv;
-            }
+            *reinterpret_cast<float4*>(xs + row * kIvfLD + c4) = xv;
+            *reinterpret_cast<float4*>(cs + row * kIvfLD + c4) = cv;
             __syncthreads();
+            if (d0 + kIvfDC < D) { xv = load_x(d0 + kIvfDC); cv = load_c(d0 + kIvfDC); }
 #pragma unroll
             for (int d = 0; d < kIvfDC; d += 4) {
                 float4 xa[4], cb[4];
