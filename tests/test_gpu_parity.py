@@ -314,3 +314,29 @@ def test_ivf_assign_large_matches_oracle():
         assert np.all(np.abs(d[rows, codes[0][~same]] - d[rows, ref[~same]]) <= 1e-4 * d[rows, ref[~same]])
     finally:
         model._h.close()
+
+
+@pytest.mark.parametrize("shape", [
+    dict(D=768, M=3, K=256, L=2, de=384, dh=384, A=16, B=32, qinco1_mode=False),      # Contriever shape (BASELINE config 5)
+    dict(D=96, M=6, K=256, L=2, de=384, dh=384, A=16, B=16, qinco1_mode=False),       # Deep1B shape (BASELINE config 4)
+])
+def test_baseline_config_shapes_vs_oracle(shape):
+    """The wide-beam shapes of BASELINE configs 4 / 5 (fewer steps and blocks so the numpy oracle stays fast):
+    out_proj chunks over D = 768, beam 32, D = 96 with de = 384."""
+    from qinco_b200.model import QINCo
+    cfg = synth.make_cfg(None, **shape)
+    w = synth.make_weights(cfg, seed=17, n_train=2048, kmeans_iters=1)
+    x = synth.make_data(96, cfg["D"], seed=23)
+    ref_codes, ref_xhat = orc.encode(cfg, w, x)
+    model = QINCo(cfg, w, device="cuda:0")
+    try:
+        codes = model(torch.from_numpy(x).cuda(), step="encode").cpu().numpy()
+        dec = model(torch.from_numpy(ref_codes).cuda(), step="decode").cpu().numpy()
+        model.synchronize()
+        assert rel_mse(dec, orc.decode(cfg, w, ref_codes)) <= DEC_TOL
+        agree = float((codes == ref_codes).all(0).mean())
+        mse_ours, mse_ref = orc.mse(x, orc.decode(cfg, w, codes)), orc.mse(x, ref_xhat)
+        print(f"\n{shape['D']}: identical vectors {agree:.3f} mse ours {mse_ours:.5f} ref {mse_ref:.5f}")
+        assert agree >= 0.8 and abs(mse_ours - mse_ref) <= ENC_TOL_SMALL * mse_ref
+    finally:
+        model._h.close()
