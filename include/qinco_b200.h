@@ -99,6 +99,11 @@ int qb_encode_ivf(qb_model* m, const float* x_dev, int64_t n, int normalize, int
                   float* xhat_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 int qb_decode_ivf(qb_model* m, const int32_t* ivf_codes_dev, const uint8_t* codes_dev, int64_t n, int denormalize,
                   float* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* ... and their host-buffer variants (the loop of encode_database, qinco/search/search_tasks.py:107-116, for IVF models) */
+int qb_encode_ivf_host(qb_model* m, const float* x_host, int64_t n, int normalize, int32_t* ivf_codes_host, uint8_t* codes_host,
+                       float* xhat_host);
+int qb_decode_ivf_host(qb_model* m, const int32_t* ivf_codes_host, const uint8_t* codes_host, int64_t n, int denormalize,
+                       float* out_host);
 
 /* Host-buffer variants = the batch loops of qinco_v1/codec_qinco.py:25-46 and :54-72 (H2D, encode/decode, D2H per
  * chunk, through pinned staging owned by the model).  xhat_host may be NULL. */

@@ -23,7 +23,7 @@ SYMBOLS = ["qb_version", "qb_last_error", "qb_model_create", "qb_model_destroy",
            "qb_decode_workspace_bytes", "qb_encode", "qb_decode", "qb_encode_host", "qb_decode_host", "qb_check",
            "qb_launch_count", "qb_timing_enable", "qb_timing_read", "qb_model_info", "qb_debug_step", "qb_plan_export", "qb_plan_pack", "qb_plan_tables",
            "qb_pairwise_create", "qb_pairwise_destroy", "qb_pairwise_decode", "qb_pairwise_check", "qb_pairwise_launch_count",
-           "qb_pairwise_last_error", "qb_encode_ivf", "qb_decode_ivf"]
+           "qb_pairwise_last_error", "qb_encode_ivf", "qb_decode_ivf", "qb_encode_ivf_host", "qb_decode_ivf_host"]
 
 _fpp = C.POINTER(C.POINTER(C.c_float))
 
@@ -85,6 +85,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.qb_decode.argtypes = [vp, vp, i64, C.c_int, vp, vp, sz, vp]
     lib.qb_encode_ivf.argtypes = [vp, vp, i64, C.c_int, vp, vp, vp, vp, sz, vp]
     lib.qb_decode_ivf.argtypes = [vp, vp, vp, i64, C.c_int, vp, vp, sz, vp]
+    lib.qb_encode_ivf_host.argtypes = [vp, vp, i64, C.c_int, vp, vp, vp]
+    lib.qb_decode_ivf_host.argtypes = [vp, vp, vp, i64, C.c_int, vp]
     lib.qb_encode_host.argtypes = [vp, vp, i64, C.c_int, vp, vp]
     lib.qb_decode_host.argtypes = [vp, vp, i64, C.c_int, vp]
     lib.qb_check.argtypes = [vp]
@@ -213,6 +215,25 @@ class Handle:
 
     def decode_ivf(self, ivf_ptr, codes_ptr, n, denormalize, out_ptr, ws_ptr, ws_bytes, stream):
         check(self._lib.qb_decode_ivf(self._h, ivf_ptr, codes_ptr, n, int(denormalize), out_ptr, ws_ptr, ws_bytes, stream))
+
+    def encode_ivf_host(self, x: np.ndarray, normalize: bool, want_xhat: bool = False):
+        """IVF models, host buffers: -> (ivf codes int32 [n], codes uint8 [n, M], xhat or None)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[0]
+        ivf = np.empty((n,), np.int32)
+        codes = np.empty((n, self.M), np.uint8)
+        xhat = np.empty((n, self.D), np.float32) if want_xhat else None
+        check(self._lib.qb_encode_ivf_host(self._h, x.ctypes.data, n, int(normalize), ivf.ctypes.data, codes.ctypes.data,
+                                           xhat.ctypes.data if want_xhat else None))
+        return ivf, codes, xhat
+
+    def decode_ivf_host(self, ivf: np.ndarray, codes: np.ndarray, denormalize: bool) -> np.ndarray:
+        ivf = np.ascontiguousarray(ivf, dtype=np.int32)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        out = np.empty((codes.shape[0], self.D), np.float32)
+        check(self._lib.qb_decode_ivf_host(self._h, ivf.ctypes.data, codes.ctypes.data, codes.shape[0], int(denormalize),
+                                           out.ctypes.data))
+        return out
 
     def encode_host(self, x: np.ndarray, normalize: bool, want_xhat: bool = False):
         x = _f32(x)

@@ -36,6 +36,7 @@ def build_parser():
     g.add_argument("--float16", default=False, action="store_true", help="accepted for compatibility (operands are always fp16)")
     g.add_argument("--A", type=int, default=None, help="v2: override the number of pre-selected candidates")
     g.add_argument("--B", type=int, default=None, help="v2: override the beam width")
+    g.add_argument("--ivf_centroids", default=None, help="v2 IVF models: .npy of the (normalised) IVF centroids, like cfg.ivf_centroids")
     return ap
 
 
@@ -45,10 +46,12 @@ def main(argv=None):
     assert args.encode ^ args.decode, "one of encode or decode must be selected"
     print("loading model", args.model)
     if args.v2:
-        cfg, sd = io.load_v2_checkpoint(args.model, dict(A=args.A, B=args.B))
+        cfg, sd = io.load_v2_checkpoint(args.model, dict(A=args.A, B=args.B), ivf_centroids=args.ivf_centroids)
+        ivf = bool(cfg.get("ivf_K"))
         model = QINCo(cfg, sd, device=args.device)
         M, K, D = cfg["M"], cfg["K"], cfg["D"]
     else:
+        ivf = False
         sd, db_scale = io.load_v1_checkpoint(args.model)
         model = codec.QINCoV1(sd, db_scale=db_scale, device=args.device)
         print("  database normalization factor", model.db_scale)
@@ -57,12 +60,16 @@ def main(argv=None):
         print("reading", args.i)
         x = io.read_vectors(args.i)
         print(f"encoding intput vectors of size {x.shape}")
-        if args.v2:
+        if args.v2 and ivf:      # [n, M + 1]: column 0 is the IVF code, like model(batch, step="encode").T
+            ivf_codes, codes_u8, _ = model._h.encode_ivf_host(np.ascontiguousarray(x, np.float32), normalize=True)
+            codes = np.concatenate([ivf_codes.astype(np.int64)[:, None], codes_u8.astype(np.int64)], axis=1)
+        elif args.v2:
             codes_u8, _ = model._h.encode_host(np.ascontiguousarray(x, np.float32), normalize=True)
             codes = codes_u8.astype(np.int64)
         else:
             codes = codec.encode(model, x, bs=args.batch_size, is_float16=args.float16)
         if args.raw:
+            assert not ivf, "--raw packs M * ceil(log2 K) bits per vector: not defined for IVF codes"
             print(f"Packing result of size {codes.shape} to {M} * {int(np.ceil(np.log2(K)))} bits")
             io.write_raw_codes(args.o, codes, K)
         elif args.v2 and args.o.endswith(".npz"):
@@ -81,7 +88,9 @@ def main(argv=None):
         else:
             raise RuntimeError("unrecognized format")
         print(f"Decoding intput codes of size {codes.shape}")
-        if args.v2:
+        if args.v2 and ivf:
+            y = model._h.decode_ivf_host(codes[:, 0].astype(np.int32), codes[:, 1:].astype(np.uint8), denormalize=True)
+        elif args.v2:
             if codes.size and (codes.min() < 0 or codes.max() >= K):
                 raise IndexError(f"codes out of range [0, {K})")
             y = model._h.decode_host(codes.astype(np.uint8), denormalize=True)

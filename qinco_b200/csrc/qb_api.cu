@@ -66,6 +66,8 @@ struct HostSlot {
     float* x_dev = nullptr;
     uint8_t* codes_dev = nullptr;
     float* out_dev = nullptr;
+    int32_t* ivf_pin = nullptr;   // IVF models: the int32 IVF codes of the chunk
+    int32_t* ivf_dev = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
     int64_t pending_i0 = -1, pending_n = 0;
 };
@@ -390,6 +392,10 @@ int ensure_host_staging(qb_model* m, bool decode) {
         QB_CUDA(cudaMalloc((void**)&s.x_dev, (size_t)nc * m->D * 4));
         QB_CUDA(cudaMalloc((void**)&s.out_dev, (size_t)nc * m->D * 4));
         QB_CUDA(cudaMalloc((void**)&s.codes_dev, (size_t)nc * m->M));
+        if (m->ivf_K) {
+            QB_CUDA(cudaHostAlloc((void**)&s.ivf_pin, (size_t)nc * 4, cudaHostAllocDefault));
+            QB_CUDA(cudaMalloc((void**)&s.ivf_dev, (size_t)nc * 4));
+        }
         QB_CUDA(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
         QB_CUDA(cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
         QB_CUDA(cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
@@ -519,6 +525,8 @@ int qb_model_destroy(qb_model* m) {
         if (s.x_dev) cudaFree(s.x_dev);
         if (s.out_dev) cudaFree(s.out_dev);
         if (s.codes_dev) cudaFree(s.codes_dev);
+        if (s.ivf_pin) cudaFreeHost(s.ivf_pin);
+        if (s.ivf_dev) cudaFree(s.ivf_dev);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_comp) cudaEventDestroy(s.ev_comp);
         if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
@@ -622,8 +630,8 @@ int qb_check(qb_model* m) {
 }
 
 // Pipelined host loops: chunk i is copied in on one stream while chunk i-1 computes and chunk i-2 copies out.
-static int host_loop(qb_model* m, bool enc, const float* x_host, const uint8_t* codes_in, int64_t n, int flag,
-                     uint8_t* codes_out, float* out_host) {
+static int host_loop(qb_model* m, bool enc, const float* x_host, const int32_t* ivf_in, const uint8_t* codes_in, int64_t n,
+                     int flag, int32_t* ivf_out, uint8_t* codes_out, float* out_host) {
     QB_CUDA(cudaSetDevice(m->device));
     int rc = ensure_host_staging(m, !enc);
     if (rc) return rc;
@@ -634,6 +642,7 @@ static int host_loop(qb_model* m, bool enc, const float* x_host, const uint8_t* 
         QB_CUDA(cudaEventSynchronize(s.ev_d2h));
         if (enc) {
             std::memcpy(codes_out + s.pending_i0 * M, s.codes_pin, (size_t)s.pending_n * M);
+            if (ivf_out) std::memcpy(ivf_out + s.pending_i0, s.ivf_pin, (size_t)s.pending_n * 4);
             if (out_host) std::memcpy(out_host + s.pending_i0 * D, s.out_pin, (size_t)s.pending_n * D * 4);
         } else {
             std::memcpy(out_host + s.pending_i0 * D, s.out_pin, (size_t)s.pending_n * D * 4);
@@ -652,19 +661,25 @@ static int host_loop(qb_model* m, bool enc, const float* x_host, const uint8_t* 
         } else {
             std::memcpy(s.codes_pin, codes_in + i0 * M, (size_t)c * M);
             QB_CUDA(cudaMemcpyAsync(s.codes_dev, s.codes_pin, (size_t)c * M, cudaMemcpyHostToDevice, m->s_h2d));
+            if (ivf_in) {
+                std::memcpy(s.ivf_pin, ivf_in + i0, (size_t)c * 4);
+                QB_CUDA(cudaMemcpyAsync(s.ivf_dev, s.ivf_pin, (size_t)c * 4, cudaMemcpyHostToDevice, m->s_h2d));
+            }
         }
         QB_CUDA(cudaEventRecord(s.ev_h2d, m->s_h2d));
         QB_CUDA(cudaStreamWaitEvent(m->s_comp, s.ev_h2d, 0));
         if (enc)
-            rc = qb_encode(m, s.x_dev, c, flag, s.codes_dev, out_host ? s.out_dev : nullptr, m->host_ws, m->host_ws_bytes,
-                           m->s_comp);
+            rc = encode_impl(m, s.x_dev, c, flag, m->ivf_K ? s.ivf_dev : nullptr, s.codes_dev, out_host ? s.out_dev : nullptr,
+                             m->host_ws, m->host_ws_bytes, m->s_comp);
         else
-            rc = qb_decode(m, s.codes_dev, c, flag, s.out_dev, m->host_ws, m->host_ws_bytes, m->s_comp);
+            rc = decode_impl(m, m->ivf_K ? s.ivf_dev : nullptr, s.codes_dev, c, flag, s.out_dev, m->host_ws, m->host_ws_bytes,
+                             m->s_comp);
         if (rc) return rc;
         QB_CUDA(cudaEventRecord(s.ev_comp, m->s_comp));
         QB_CUDA(cudaStreamWaitEvent(m->s_d2h, s.ev_comp, 0));
         if (enc) {
             QB_CUDA(cudaMemcpyAsync(s.codes_pin, s.codes_dev, (size_t)c * M, cudaMemcpyDeviceToHost, m->s_d2h));
+            if (ivf_out) QB_CUDA(cudaMemcpyAsync(s.ivf_pin, s.ivf_dev, (size_t)c * 4, cudaMemcpyDeviceToHost, m->s_d2h));
             if (out_host)
                 QB_CUDA(cudaMemcpyAsync(s.out_pin, s.out_dev, (size_t)c * D * 4, cudaMemcpyDeviceToHost, m->s_d2h));
         } else {
@@ -684,7 +699,18 @@ int qb_encode_host(qb_model* m, const float* x_host, int64_t n, int normalize, u
     if (n < 0) return fail(QB_ERR_INVALID, "n < 0");
     if (n == 0) return QB_OK;
     if (!x_host || !codes_host) return fail(QB_ERR_INVALID, "NULL buffer");
-    return host_loop(m, true, x_host, nullptr, n, normalize, codes_host, xhat_host);
+    if (m->ivf_K) return fail(QB_ERR_INVALID, "IVF model: use qb_encode_ivf_host");
+    return host_loop(m, true, x_host, nullptr, nullptr, n, normalize, nullptr, codes_host, xhat_host);
+}
+
+int qb_encode_ivf_host(qb_model* m, const float* x_host, int64_t n, int normalize, int32_t* ivf_codes_host, uint8_t* codes_host,
+                       float* xhat_host) {
+    if (!m) return fail(QB_ERR_INVALID, "model is NULL");
+    if (n < 0) return fail(QB_ERR_INVALID, "n < 0");
+    if (!m->ivf_K) return fail(QB_ERR_INVALID, "not an IVF model: use qb_encode_host");
+    if (n == 0) return QB_OK;
+    if (!x_host || !codes_host || !ivf_codes_host) return fail(QB_ERR_INVALID, "NULL buffer");
+    return host_loop(m, true, x_host, nullptr, nullptr, n, normalize, ivf_codes_host, codes_host, xhat_host);
 }
 
 int qb_decode_host(qb_model* m, const uint8_t* codes_host, int64_t n, int denormalize, float* out_host) {
@@ -694,7 +720,22 @@ int qb_decode_host(qb_model* m, const uint8_t* codes_host, int64_t n, int denorm
     if (!codes_host || !out_host) return fail(QB_ERR_INVALID, "NULL buffer");
     for (int64_t i = 0; i < n * m->M; i++)
         if (codes_host[i] >= m->K) return fail(QB_ERR_INVALID, "code out of range [0,K)");
-    return host_loop(m, false, nullptr, codes_host, n, denormalize, nullptr, out_host);
+    if (m->ivf_K) return fail(QB_ERR_INVALID, "IVF model: use qb_decode_ivf_host");
+    return host_loop(m, false, nullptr, nullptr, codes_host, n, denormalize, nullptr, nullptr, out_host);
+}
+
+int qb_decode_ivf_host(qb_model* m, const int32_t* ivf_codes_host, const uint8_t* codes_host, int64_t n, int denormalize,
+                       float* out_host) {
+    if (!m) return fail(QB_ERR_INVALID, "model is NULL");
+    if (n < 0) return fail(QB_ERR_INVALID, "n < 0");
+    if (!m->ivf_K) return fail(QB_ERR_INVALID, "not an IVF model: use qb_decode_host");
+    if (n == 0) return QB_OK;
+    if (!ivf_codes_host || !codes_host || !out_host) return fail(QB_ERR_INVALID, "NULL buffer");
+    for (int64_t i = 0; i < n * m->M; i++)
+        if (codes_host[i] >= m->K) return fail(QB_ERR_INVALID, "code out of range [0,K)");
+    for (int64_t i = 0; i < n; i++)
+        if (ivf_codes_host[i] < 0 || ivf_codes_host[i] >= m->ivf_K) return fail(QB_ERR_INVALID, "IVF code out of range [0,ivf_K)");
+    return host_loop(m, false, nullptr, ivf_codes_host, codes_host, n, denormalize, nullptr, nullptr, out_host);
 }
 
 int64_t qb_launch_count(const qb_model* m) { return m ? m->launches : 0; }

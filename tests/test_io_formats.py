@@ -120,3 +120,29 @@ def test_cli_round_trip(tmp_path):
     cli.main(["--decode", "--v2", "--model", m2, "--i", str(tmp_path / "db.npz"), "--o", str(tmp_path / "y2.npy")])
     y2 = np.load(str(tmp_path / "y2.npy"))
     assert y2.shape == (300, 32) and ((y2 - x) ** 2).sum() < (x ** 2).sum()
+
+
+@pytest.mark.gpu
+def test_cli_ivf_round_trip(tmp_path):
+    """IVF-QINCo through the CLI: centroids from a separate .npy (cfg.ivf_centroids), codes [n, M + 1] with the IVF code in
+    column 0 (like model(batch, step="encode").T), host-buffer entry points qb_encode_ivf_host / qb_decode_ivf_host."""
+    from oracle import qinco_oracle as orc
+    from qinco_b200 import cli
+    cfg = synth.make_cfg(None, D=32, M=3, K=64, L=1, de=32, dh=32, A=8, B=4, ivf_K=120)
+    w = synth.make_weights(cfg, seed=7, n_train=1024, kmeans_iters=1)
+    x = synth.make_data(257, 32, seed=4)
+    xin, cent, ck = str(tmp_path / "x.npy"), str(tmp_path / "cent.npy"), str(tmp_path / "ivf.pt")
+    np.save(xin, x)
+    np.save(cent, w["steps.0.ivf_centroids.weight"])
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in w.items() if k != "steps.0.ivf_centroids.weight"}
+    torch.save({"model": sd, "parameters": {"K": 64, "M": 3, "de": 32, "dh": 32, "L": 1, "A": 8, "B": 4, "ivf_in_use": True,
+                                             "ivf_K": 120, "qinco1_mode": False}, "data_dim": 32}, ck)
+    cli.main(["--encode", "--v2", "--model", ck, "--ivf_centroids", cent, "--i", xin, "--o", str(tmp_path / "db.npz")])
+    codes, meta = io.load_encoded_db(str(tmp_path / "db.npz"))
+    assert codes.shape == (257, 4) and codes[:, 0].max() < 120 and codes[:, 1:].max() < 64
+    ref_codes, _ = orc.encode(cfg, w, x)
+    assert (codes.T == ref_codes).all(0).mean() >= 0.8
+    cli.main(["--decode", "--v2", "--model", ck, "--ivf_centroids", cent, "--i", str(tmp_path / "db.npz"), "--o", str(tmp_path / "y.npy")])
+    y = np.load(str(tmp_path / "y.npy"))
+    ref = orc.decode(cfg, w, codes.T)
+    assert ((y - ref) ** 2).sum() / (ref ** 2).sum() <= 1e-4
