@@ -13,7 +13,16 @@ namespace {
 
 constexpr int kPrepThreads = 256;
 constexpr int kPrepRows = 64;                 // (vector, beam) rows per block
-constexpr int kTileN = 64, kTileD = 16, kTileLD = kTileD + 4;   // output tile, D chunk, padded shared-memory row
+constexpr int kTileN = 64, kTileD = 32, kTileLD = kTileD + 4;   // output tile, D chunk, padded shared-memory row
+constexpr int kTileF4 = kPrepRows * kTileD / 4 / kPrepThreads;   // float4 loads per thread and operand tile (2)
+
+// Two fp32 FMAs per instruction (Blackwell FFMA2): acc.{x,y} += a.{x,y} * b.{x,y}.  The tile GEMMs below pair the even and
+// the odd dimensions of a dot product, which need no operand shuffling (the pairs are the halves of the float4 loads).
+__device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(reinterpret_cast<uint64_t&>(acc))
+        : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+}
 
 // lexicographic (value, index) minimum across the warp
 __device__ __forceinline__ void warp_argmin(float& v, int& i) {
@@ -28,7 +37,7 @@ __device__ __forceinline__ void warp_argmin(float& v, int& i) {
 // Beam preparation for one step (reference: QincoSubstep.get_distances_for_codes / select_code_candidates,
 // qinco_base.py:114-121; the hoisted half of QConcat, :60-64: Wcat[:, De:] . xhat; for step 0 the first lines of
 // QINCoInferenceEncoder.forward, qinco_inference.py:239-246).  Two register-tiled fp32 "GEMMs" per block of 64 rows, both
-// in the shape of the IVF kernel below (16 x 16 threads, 4 x 4 dot products each, D in chunks of 16 through shared memory):
+// in the shape of the IVF kernel below (16 x 16 threads, 4 x 4 dot products each, D in chunks of 32 through shared memory):
 //   u[b][e]    = xhat_b . Wx[e]                                     (written straight from registers)
 //   dpre[b][k] = (|r_b|^2 + |S_k|^2) - 2 r_b . S_k                  (the reference's approx_pairwise_distance form,
 //                utils.py:336-346, which is what it uses for > 32 rows) -> shared memory -> top-A per row
@@ -41,14 +50,18 @@ __global__ void __launch_bounds__(kPrepThreads) qb_prep_kernel(const PrepParams 
     const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
     const int64_t b0 = (int64_t)blockIdx.x * kPrepRows;
     const int nrow = (int)min((int64_t)kPrepRows, p.n_beams - b0);
-    const int lrow = tid >> 2, lc4 = (tid & 3) * 4;          // this thread's float4 of a 64 x 16 chunk
+    const int lrow = tid >> 2;                                // row of this thread in the 4-threads-per-row norm pass
+    // float4 number i (< kTileF4) of this thread in a 64 x kTileD chunk: row, first column
+    auto f4_row = [&](int i) { return (tid + i * kPrepThreads) / (kTileD / 4); };
+    auto f4_col = [&](int i) { return ((tid + i * kPrepThreads) % (kTileD / 4)) * 4; };
 
-    // one float4 of row lrow, columns d0 + lc4 ..: the beam's xhat (kind 0) or its residual r = xn - xhat (kind 1)
-    auto load_a = [&](int kind, int d0, bool store_r) {
+    // one float4 of a row, columns d0 + c4 ..: the beam's xhat (kind 0) or its residual r = xn - xhat (kind 1);
+    // columns past D (D is a multiple of 16, the chunk is 32 wide) read as zero
+    auto load_a = [&](int kind, int d0, bool store_r, int row, int c4) {
         float4 xh = make_float4(0.f, 0.f, 0.f, 0.f), r = xh;
-        if (lrow < nrow) {
-            const int64_t b = b0 + lrow;
-            const int d = d0 + lc4;
+        if (row < nrow && d0 + c4 < D) {
+            const int64_t b = b0 + row;
+            const int d = d0 + c4;
             if (!p.step0) xh = *reinterpret_cast<const float4*>(p.xhat + b * D + d);
             if (kind == 1) {
                 float4 xn = *reinterpret_cast<const float4*>(p.x + (b / p.F) * D + d);
@@ -66,23 +79,35 @@ __global__ void __launch_bounds__(kPrepThreads) qb_prep_kernel(const PrepParams 
     };
     // acc[a][b] = A-row (ti + 16 a) . B-row (n0 + tj + 16 b) over all of D; B is [n_out][D] row-major
     auto tile_gemm = [&](int kind, const float* __restrict__ B, int n_out, int n0, bool store_r, float (&acc)[4][4]) {
+        float2 acc2[4][4];      // (sum over even dimensions, sum over odd dimensions)
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+            for (int b = 0; b < 4; b++) acc2[a][b] = make_float2(0.f, 0.f);
         // the next chunk's global loads are issued before the current chunk's FMAs (register double buffering)
-        auto load_b = [&](int d0) {
+        auto load_b = [&](int d0, int row, int c4) {
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n0 + lrow < n_out) bv = __ldg(reinterpret_cast<const float4*>(B + (size_t)(n0 + lrow) * D + d0 + lc4));
+            if (n0 + row < n_out && d0 + c4 < D) bv = __ldg(reinterpret_cast<const float4*>(B + (size_t)(n0 + row) * D + d0 + c4));
             return bv;
         };
-        float4 av = load_a(kind, 0, store_r), bv = load_b(0);
+        float4 av[kTileF4], bv[kTileF4];
+#pragma unroll
+        for (int i = 0; i < kTileF4; i++) { av[i] = load_a(kind, 0, store_r, f4_row(i), f4_col(i)); bv[i] = load_b(0, f4_row(i), f4_col(i)); }
         for (int d0 = 0; d0 < D; d0 += kTileD) {
             __syncthreads();
-            *reinterpret_cast<float4*>(xs + lrow * kTileLD + lc4) = av;
-            *reinterpret_cast<float4*>(cs + lrow * kTileLD + lc4) = bv;
+#pragma unroll
+            for (int i = 0; i < kTileF4; i++) {
+                *reinterpret_cast<float4*>(xs + f4_row(i) * kTileLD + f4_col(i)) = av[i];
+                *reinterpret_cast<float4*>(cs + f4_row(i) * kTileLD + f4_col(i)) = bv[i];
+            }
             __syncthreads();
-            if (d0 + kTileD < D) { av = load_a(kind, d0 + kTileD, store_r); bv = load_b(d0 + kTileD); }
+            if (d0 + kTileD < D) {
+#pragma unroll
+                for (int i = 0; i < kTileF4; i++) {
+                    av[i] = load_a(kind, d0 + kTileD, store_r, f4_row(i), f4_col(i));
+                    bv[i] = load_b(d0 + kTileD, f4_row(i), f4_col(i));
+                }
+            }
 #pragma unroll
             for (int d = 0; d < kTileD; d += 4) {
                 float4 xa[4], cb[4];
@@ -94,11 +119,15 @@ __global__ void __launch_bounds__(kPrepThreads) qb_prep_kernel(const PrepParams 
                 for (int a = 0; a < 4; a++)
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
-                        acc[a][b] = fmaf(xa[a].x, cb[b].x, acc[a][b]); acc[a][b] = fmaf(xa[a].y, cb[b].y, acc[a][b]);
-                        acc[a][b] = fmaf(xa[a].z, cb[b].z, acc[a][b]); acc[a][b] = fmaf(xa[a].w, cb[b].w, acc[a][b]);
+                        ffma2(acc2[a][b], make_float2(xa[a].x, xa[a].y), make_float2(cb[b].x, cb[b].y));
+                        ffma2(acc2[a][b], make_float2(xa[a].z, xa[a].w), make_float2(cb[b].z, cb[b].w));
                     }
             }
         }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b] = acc2[a][b].x + acc2[a][b].y;
     };
 
     float acc[4][4];
@@ -119,7 +148,9 @@ __global__ void __launch_bounds__(kPrepThreads) qb_prep_kernel(const PrepParams 
     }
     if (!p.sub_cb) {     // no ranking in this launch: r still has to be written (A == 0 scoring reads it)
         if (p.r)
-            for (int d0 = 0; d0 < D; d0 += kTileD) load_a(1, d0, true);
+            for (int d0 = 0; d0 < D; d0 += kTileD)
+#pragma unroll
+                for (int i = 0; i < kTileF4; i++) load_a(1, d0, true, f4_row(i), f4_col(i));
         return;
     }
     // |r|^2 of the block's rows: 4 threads per row, same element order for every candidate of the row
@@ -152,36 +183,60 @@ __global__ void __launch_bounds__(kPrepThreads) qb_prep_kernel(const PrepParams 
         }
     }
     __syncthreads();
-    // the A smallest per row, ascending, ties to the lower index (torch.topk(largest=False) order)
+    // the A smallest per row, ascending, ties to the lower index (torch.topk(largest=False) order).  A warp ranks FOUR of
+    // its rows at a time: the butterfly reductions of the rows are independent, so their shuffle latencies overlap.
     const int warp = tid >> 5, lane = tid & 31;
-    for (int i = warp; i < nrow; i += kPrepThreads / 32) {
-        const int64_t b = b0 + i;
-        float vals[8];
+    constexpr int kRG = 4, kWarps = kPrepThreads / 32;
+    for (int i0 = warp; i0 < nrow; i0 += kWarps * kRG) {
+        float vals[kRG][8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int k = lane + 32 * j;
-            vals[j] = k < K ? dpre[i * K + k] : FLT_MAX;
-        }
-        for (int a = 0; a < p.A; a++) {
-            float bv = FLT_MAX;
-            int bi = 0x7fffffff;
+        for (int g = 0; g < kRG; g++) {
+            const int i = i0 + g * kWarps;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int k = lane + 32 * j;
-                if (k < K && (vals[j] < bv || (vals[j] == bv && k < bi))) { bv = vals[j]; bi = k; }
+                vals[g][j] = (i < nrow && k < K) ? dpre[i * K + k] : FLT_MAX;
             }
-            warp_argmin(bv, bi);
-            if (bi >= K) bi = 0;   // all-NaN row: stay in range
+        }
+        for (int a = 0; a < p.A; a++) {
+            float bv[kRG];
+            int bi[kRG];
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (lane + 32 * j == bi) vals[j] = FLT_MAX;
-            if (!p.step0) {
-                if (lane == 0) p.idx[b * p.A + a] = (uint8_t)bi;
-            } else {
-                // first step: beam a of vector b starts at codeword bi of C_0 (row-major, = the ranking codebook)
-                if (lane == 0) p.hist_out[(b * p.A + a) * p.M] = (uint8_t)bi;
-                for (int d = lane; d < D; d += 32)
-                    p.xhat_out[(b * p.A + a) * D + d] = __ldg(p.sub_cb + (size_t)bi * D + d);
+            for (int g = 0; g < kRG; g++) {
+                bv[g] = FLT_MAX;
+                bi[g] = 0x7fffffff;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int k = lane + 32 * j;
+                    if (k < K && (vals[g][j] < bv[g] || (vals[g][j] == bv[g] && k < bi[g]))) { bv[g] = vals[g][j]; bi[g] = k; }
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int g = 0; g < kRG; g++) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv[g], off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi[g], off);
+                    if (ov < bv[g] || (ov == bv[g] && oi < bi[g])) { bv[g] = ov; bi[g] = oi; }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < kRG; g++) {
+                const int i = i0 + g * kWarps;
+                if (i >= nrow) continue;
+                if (bi[g] >= K) bi[g] = 0;   // all-NaN row: stay in range
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (lane + 32 * j == bi[g]) vals[g][j] = FLT_MAX;
+                const int64_t b = b0 + i;
+                if (!p.step0) {
+                    if (lane == 0) p.idx[b * p.A + a] = (uint8_t)bi[g];
+                } else {
+                    // first step: beam a of vector b starts at codeword bi of C_0 (row-major, = the ranking codebook)
+                    if (lane == 0) p.hist_out[(b * p.A + a) * p.M] = (uint8_t)bi[g];
+                    for (int d = lane; d < D; d += 32)
+                        p.xhat_out[(b * p.A + a) * D + d] = __ldg(p.sub_cb + (size_t)bi[g] * D + d);
+                }
             }
         }
     }
@@ -220,7 +275,7 @@ __global__ void __launch_bounds__(256) qb_select_kernel(const SelectParams p) {
     }
 }
 
-// ---- IVF first step: tiled fp32 "GEMM + arg-min".  Block = 64 vectors; centroids in tiles of 64, D in chunks of 16; thread
+// ---- IVF first step: tiled fp32 "GEMM + arg-min".  Block = 64 vectors; centroids in tiles of 64, D in chunks of 32; thread
 // (ti, tj) of a 16 x 16 grid owns vectors ti + 16 a and centroids tj + 16 b (a, b < 4): 16 dot products in registers.
 constexpr int kIvfVB = kPrepRows, kIvfCT = kTileN, kIvfDC = kTileD, kIvfLD = kTileLD;   // +4 floats: rows 16 B apart in bank space
 
@@ -253,17 +308,18 @@ __global__ void __launch_bounds__(256) qb_ivf_assign_kernel(const IvfParams p) {
 #pragma unroll
     for (int a = 0; a < 4; a++) { bv[a] = FLT_MAX; bi[a] = 0x7fffffff; }
     for (int k0 = 0; k0 < p.ivf_K; k0 += kIvfCT) {
-        float acc[4][4];
+        float2 acc2[4][4];      // (even dimensions, odd dimensions) of each dot product: FFMA2
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
-        // 64 rows x 16 columns per chunk: one float4 of x and one of the centroids per thread, the next chunk's loads in
+            for (int b = 0; b < 4; b++) acc2[a][b] = make_float2(0.f, 0.f);
+        // 64 rows x 32 columns per chunk: two float4 of x and two of the centroids per thread, the next chunk's loads in
         // flight while the current chunk's FMAs run
-        const int row = tid >> 2, c4 = (tid & 3) * 4;
-        auto load_x = [&](int d0) {
+        auto f4_row = [&](int i) { return (tid + i * 256) / (kIvfDC / 4); };
+        auto f4_col = [&](int i) { return ((tid + i * 256) % (kIvfDC / 4)) * 4; };
+        auto load_x = [&](int d0, int row, int c4) {
             float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (v0 + row < p.n) {
+            if (v0 + row < p.n && d0 + c4 < D) {
                 xv = *reinterpret_cast<const float4*>(p.x + (v0 + row) * D + d0 + c4);
                 if (p.mean) {
                     const float4 m = *reinterpret_cast<const float4*>(p.mean + d0 + c4);
@@ -273,18 +329,29 @@ __global__ void __launch_bounds__(256) qb_ivf_assign_kernel(const IvfParams p) {
             }
             return xv;
         };
-        auto load_c = [&](int d0) {
+        auto load_c = [&](int d0, int row, int c4) {
             float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k0 + row < p.ivf_K) cv = __ldg(reinterpret_cast<const float4*>(p.cent + (size_t)(k0 + row) * D + d0 + c4));
+            if (k0 + row < p.ivf_K && d0 + c4 < D) cv = __ldg(reinterpret_cast<const float4*>(p.cent + (size_t)(k0 + row) * D + d0 + c4));
             return cv;
         };
-        float4 xv = load_x(0), cv = load_c(0);
+        float4 xv[kTileF4], cv[kTileF4];
+#pragma unroll
+        for (int i = 0; i < kTileF4; i++) { xv[i] = load_x(0, f4_row(i), f4_col(i)); cv[i] = load_c(0, f4_row(i), f4_col(i)); }
         for (int d0 = 0; d0 < D; d0 += kIvfDC) {
             __syncthreads();
-            *reinterpret_cast<float4*>(xs + row * kIvfLD + c4) = xv;
-            *reinterpret_cast<float4*>(cs + row * kIvfLD + c4) = cv;
+#pragma unroll
+            for (int i = 0; i < kTileF4; i++) {
+                *reinterpret_cast<float4*>(xs + f4_row(i) * kIvfLD + f4_col(i)) = xv[i];
+                *reinterpret_cast<float4*>(cs + f4_row(i) * kIvfLD + f4_col(i)) = cv[i];
+            }
             __syncthreads();
-            if (d0 + kIvfDC < D) { xv = load_x(d0 + kIvfDC); cv = load_c(d0 + kIvfDC); }
+            if (d0 + kIvfDC < D) {
+#pragma unroll
+                for (int i = 0; i < kTileF4; i++) {
+                    xv[i] = load_x(d0 + kIvfDC, f4_row(i), f4_col(i));
+                    cv[i] = load_c(d0 + kIvfDC, f4_row(i), f4_col(i));
+                }
+            }
 #pragma unroll
             for (int d = 0; d < kIvfDC; d += 4) {
                 float4 xa[4], cb[4];
@@ -296,8 +363,8 @@ __global__ void __launch_bounds__(256) qb_ivf_assign_kernel(const IvfParams p) {
                 for (int a = 0; a < 4; a++)
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
-                        acc[a][b] = fmaf(xa[a].x, cb[b].x, acc[a][b]); acc[a][b] = fmaf(xa[a].y, cb[b].y, acc[a][b]);
-                        acc[a][b] = fmaf(xa[a].z, cb[b].z, acc[a][b]); acc[a][b] = fmaf(xa[a].w, cb[b].w, acc[a][b]);
+                        ffma2(acc2[a][b], make_float2(xa[a].x, xa[a].y), make_float2(cb[b].x, cb[b].y));
+                        ffma2(acc2[a][b], make_float2(xa[a].z, xa[a].w), make_float2(cb[b].z, cb[b].w));
                     }
             }
         }
@@ -308,7 +375,7 @@ __global__ void __launch_bounds__(256) qb_ivf_assign_kernel(const IvfParams p) {
                 const float bn = __ldg(p.cnorm + k);
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
-                    const float dist = (anorm_s[ti + 16 * a] + bn) - 2.f * acc[a][b];   // utils.py:346
+                    const float dist = (anorm_s[ti + 16 * a] + bn) - 2.f * (acc2[a][b].x + acc2[a][b].y);   // utils.py:346
                     if (dist < bv[a] || (dist == bv[a] && k < bi[a])) { bv[a] = dist; bi[a] = k; }
                 }
             }
