@@ -146,3 +146,21 @@ def test_cli_ivf_round_trip(tmp_path):
     y = np.load(str(tmp_path / "y.npy"))
     ref = orc.decode(cfg, w, codes.T)
     assert ((y - ref) ** 2).sum() / (ref ** 2).sum() <= 1e-4
+
+
+def test_cfg_normalisation_accepts_reference_style_objects():
+    """model.normalize_cfg: plain dicts and objects shaped like the reference's SharedCfgState (qinco/utils.py:16-40),
+    with and without an IVF first step (cfg.ivf_in_use, cfg._M_ivf = M + 1; qinco/qinco_tasks.py:378-383)."""
+    from types import SimpleNamespace
+    from qinco_b200.model import normalize_cfg
+    ref = SimpleNamespace(_D=96, M=16, _M_ivf=16, K=256, L=16, de=384, dh=384, A=16, B=32, qinco1_mode=False,
+                          ivf_in_use=False, ivf_K=1048576, _ivf_book=None)
+    assert normalize_cfg(ref) == dict(D=96, M=16, K=256, L=16, de=384, dh=384, A=16, B=32, qinco1_mode=False)
+    ref.ivf_in_use, ref._M_ivf, ref._ivf_book = True, 17, object()
+    got = normalize_cfg(ref)
+    assert got["M"] == 16 and got["ivf_K"] == 1048576
+    d = normalize_cfg(dict(D=128, M=8, K=256, L=2, de=None, dh=256, A=0, B=1, qinco1_mode=True))
+    assert d["de"] == 128 and "ivf_K" not in d
+    assert normalize_cfg(dict(D=128, M=8, K=256, L=2, de=128, dh=256, ivf_K=4096))["ivf_K"] == 4096
+    with pytest.raises(ValueError):
+        normalize_cfg(dict(M=8, K=256, L=2, dh=256))
