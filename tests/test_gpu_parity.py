@@ -340,3 +340,78 @@ def test_baseline_config_shapes_vs_oracle(shape):
         assert agree >= 0.8 and abs(mse_ours - mse_ref) <= ENC_TOL_SMALL * mse_ref
     finally:
         model._h.close()
+
+
+def test_one_step_random_shapes_vs_oracle():
+    """qb_debug_step (prep + the tcgen05 MLP kernel in apply mode) on a dozen random legal shapes: odd multiples of 16,
+    with / without projections and outer skip, ragged row counts."""
+    from qinco_b200.model import QINCo
+    rng = np.random.default_rng(77)
+    tried = 0
+    while tried < 12:
+        D = int(rng.choice([16, 32, 48, 64, 96, 128, 192]))
+        de = int(rng.choice([D, 16 * int(rng.integers(1, 25))]))
+        dh = 16 * int(rng.integers(1, 25))
+        L = int(rng.integers(0, 4))
+        K = int(rng.choice([16, 64, 100, 256]))
+        cfg = synth.make_cfg(None, D=D, M=2, K=K, L=L, de=de, dh=dh, A=0, B=1, qinco1_mode=bool(rng.integers(0, 2)))
+        w = synth.make_weights(cfg, seed=int(rng.integers(1, 1000)), n_train=max(256, K), kmeans_iters=1)
+        try:
+            model = QINCo(cfg, w, device="cuda:0")
+        except Exception as e:     # shapes the planner refuses must say why
+            assert "TMEM" in str(e) or "shared memory" in str(e), (cfg, str(e))
+            continue
+        tried += 1
+        try:
+            n = int(rng.integers(1, 700))
+            xhat = rng.standard_normal((n, D), dtype=np.float32)
+            codes = rng.integers(0, K, size=n).astype(np.uint8)
+            ref = xhat + orc.step_mlp(cfg, w, 1, w["steps.1.codebook.weight"][codes], xhat)
+            xt, ct = torch.from_numpy(xhat).cuda(), torch.from_numpy(codes).cuda()
+            out = torch.empty_like(xt)
+            ws = torch.empty(n * de * 4 + 512, dtype=torch.uint8, device="cuda")
+            model._h.debug_step(1, xt.data_ptr(), ct.data_ptr(), n, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                torch.cuda.current_stream().cuda_stream)
+            model.synchronize()
+            err = rel_mse(out.cpu().numpy(), ref)
+            assert err <= STEP_TOL, (cfg, n, err)
+        finally:
+            model._h.close()
+
+
+def test_encode_random_configs_vs_oracle():
+    """Whole encode / decode on random small configurations (odd K, D, de, dh; A in {0, 3, 8}; beams 1..6; 2..5 steps;
+    sometimes an IVF first step): codes mostly identical to the fp32 oracle, MSE within tolerance, decode within 1e-4."""
+    from qinco_b200.model import QINCo
+    rng = np.random.default_rng(4242)
+    for it in range(10):
+        D = int(rng.choice([16, 32, 48, 96]))
+        de = int(rng.choice([D, 16 * int(rng.integers(1, 13))]))
+        K = int(rng.choice([16, 50, 64, 256]))
+        A = int(rng.choice([0, 3, 8]))
+        B = int(rng.integers(1, 7))
+        A = min(A, K)
+        if A and A * 1 < B:            # a beam step needs at least B candidates: keep A*F_in >= B for every step
+            A = B
+        kw = dict(D=D, M=int(rng.integers(2, 6)), K=K, L=int(rng.integers(0, 3)), de=de, dh=16 * int(rng.integers(1, 9)),
+                  A=A, B=min(B, K), qinco1_mode=bool(rng.integers(0, 2)))
+        if it % 3 == 2:
+            kw["ivf_K"] = int(rng.integers(5, 300))
+        cfg = synth.make_cfg(None, **kw)
+        w = synth.make_weights(cfg, seed=100 + it, n_train=1024, kmeans_iters=1, data_mean=0.1 * it, data_std=1.0 + 0.1 * it)
+        n = int(rng.integers(1, 130))
+        x = synth.make_data(n, D, seed=it, mean=0.1 * it, std=1.0 + 0.1 * it)
+        xn = (x - w["data_mean"]) / np.float32(w["data_std"])
+        ref_codes, ref_xhat = orc.encode(cfg, w, xn)
+        model = QINCo(cfg, w, device="cuda:0")
+        try:
+            c = model(torch.from_numpy(x).cuda(), step="encode").cpu().numpy()
+            dec = model(torch.from_numpy(ref_codes).cuda(), step="decode").cpu().numpy()
+            model.synchronize()
+            assert c.shape == ref_codes.shape
+            assert rel_mse(dec, orc.forward(cfg, w, ref_codes, "decode")) <= DEC_TOL, cfg
+            agree = float((c == ref_codes).all(0).mean())
+            mse_ours, mse_ref = orc.mse(xn, orc.decode(cfg, w, c)), orc.mse(xn, ref_xhat)
+            assert agree >= 0.7 and abs(mse_ours - mse_ref) <= 1e-2 * mse_ref, (cfg, n, agree, mse_ours, mse_ref)
+        finally:
+            model._h.close()

@@ -228,3 +228,43 @@ def test_op_list_replay_matches_oracle(lib, name, opts):
     ref = xhat + orc.step_mlp(cfg, w, 1, w["steps.1.codebook.weight"][codes], xhat)
     rel = float(((got - ref) ** 2).sum() / (ref ** 2).sum())
     assert rel <= 1e-6, rel   # only the fp16 rounding of activations separates them (weights are fp16-exact)
+
+
+def test_planner_replay_on_random_shapes(lib):
+    """Property test: for random legal shapes (multiples of 16, with and without projections / skip / pre-selection
+    irrelevant here) the planner's op list + the packer's blob replay to the oracle's MLP.  Seeded, ~25 shapes."""
+    rng = np.random.default_rng(2024)
+    done = 0
+    for _ in range(60):
+        D = int(rng.choice([16, 32, 48, 64, 96, 128, 192]))
+        de = int(rng.choice([D, D, 16 * int(rng.integers(1, 25))]))
+        dh = 16 * int(rng.integers(1, 25))
+        L = int(rng.integers(0, 4))
+        K = int(rng.choice([16, 64, 100, 256]))
+        q1 = bool(rng.integers(0, 2))
+        opts = [int(rng.choice([0, 64, 128])), int(rng.choice([0, 1])), int(rng.choice([0, 8192, 16384, 32768])), 0,
+                int(rng.choice([0, 32, 64]))]
+        cfg = synth.make_cfg(None, D=D, M=2, K=K, L=L, de=de, dh=dh, A=0, B=1, qinco1_mode=q1)
+        o = (C.c_int32 * 5)(*opts)
+        plan_raw = (C.c_int32 * 32)()
+        ops = np.zeros(256, OP_DTYPE)
+        n_ops = lib.qb_plan_export(D, de, dh, L, K, int(q1), o, plan_raw, 32, ops.ctypes.data_as(C.c_void_p), 256)
+        if n_ops < 0:          # shapes the planner refuses (e.g. de too wide for TMEM) must be refused consistently
+            assert de + 32 > 512 or n_ops in (-1, -2)
+            continue
+        plan, ops = dict(zip(PLAN_FIELDS, list(plan_raw))), ops[:n_ops]
+        assert plan["smem_total"] + 15 * 1024 <= 227 * 1024 and plan["n_tiles"] * plan["tmem_tile_cols"] <= 512
+        w = synth.make_weights(cfg, seed=int(rng.integers(1, 1000)), n_train=max(256, K), kmeans_iters=1, fp16_exact=True)
+        blob = pack(lib, cfg, w, 1, plan, opts)
+        T, CB, WxT = tables(lib, cfg, w, 1)
+        n = 16
+        codes = rng.integers(0, K, n)
+        xhat = rng.standard_normal((n, D), dtype=np.float32)
+        got = replay(plan, ops, blob, T, CB, WxT, codes, xhat)
+        ref = xhat + orc.step_mlp(cfg, w, 1, w["steps.1.codebook.weight"][codes], xhat)
+        rel = float(((got - ref) ** 2).sum() / (ref ** 2).sum())
+        assert rel <= 1e-6, (cfg, opts, rel)
+        done += 1
+        if done >= 25:
+            break
+    assert done >= 15
