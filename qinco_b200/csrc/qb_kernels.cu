@@ -440,11 +440,17 @@ cudaError_t launch_prep(const PrepParams& p, cudaStream_t stream) {
     if (p.n_beams <= 0) return cudaSuccess;
     if (p.K > 256 || p.D % 16) return cudaErrorInvalidValue;
     const size_t smem = p.sub_cb ? (size_t)kPrepRows * p.K * sizeof(float) : 0;
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(qb_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) {       // the attribute is per device: remember what each one was raised to
+        static size_t attr_set[64] = {0};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        attr_set = smem;
+        if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+        if (smem > attr_set[dev]) {
+            e = cudaFuncSetAttribute(qb_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_set[dev] = smem;
+        }
     }
     const int64_t grid = (p.n_beams + kPrepRows - 1) / kPrepRows;
     qb_prep_kernel<<<(unsigned)grid, kPrepThreads, smem, stream>>>(p);
