@@ -330,12 +330,14 @@ def main():
     gathered = torch.empty((world * n, cfg["M"]), dtype=torch.uint8, device=dev) if world > 1 else None
 
     ivf = bool(cfg.get("ivf_K"))
-    if ivf:      # the CPU port has no IVF step; decode / e2e blocks use the plain entry points
-        args.no_cpu_baseline = args.no_e2e = args.no_decode = True
+    if ivf:      # the decode / e2e blocks below use the plain (non-IVF) entry points
+        args.no_e2e = args.no_decode = True
+
+    last_ivf = [None]
 
     def step():
         if ivf:
-            _, codes, _ = model.encode_ivf_u8(x_dev, normalize=True, want_xhat=False)
+            last_ivf[0], codes, _ = model.encode_ivf_u8(x_dev, normalize=True, want_xhat=False)
         else:
             codes, _ = model.encode_u8(x_dev, normalize=True, want_xhat=False)
         if world > 1:
@@ -458,6 +460,8 @@ def main():
             # parity on the same sample (decode MSE vs ref; encode MSE of our codes decoded by the reference arithmetic)
             xs = x_host[:n_s].numpy()
             ours = codes[:n_s].cpu().numpy().T.astype(np.int64)
+            if ivf:      # the reference's code matrix has the IVF code as row 0
+                ours = np.concatenate([last_ivf[0][:n_s].cpu().numpy().astype(np.int64)[None, :], ours])
             dec_ours = model.decode(torch.from_numpy(ref_codes).to(dev)).cpu().numpy()
             dec_ref = port.decode(ref_codes).numpy()
             mse_ref = float(((xs - ref_xhat) ** 2).sum(1).mean())

@@ -52,8 +52,9 @@ class TorchPort:
     @torch.no_grad()
     def decode(self, codes_MB):
         codes_MB = torch.as_tensor(codes_MB).long()
-        xhat = self.w["steps.0.codebook.weight"][codes_MB[0]].clone()
-        for m in range(1, self.cfg["M"]):
+        ivf = bool(self.cfg.get("ivf_K"))                # IVFBook.decode (qinco_base.py:176-183): centroid lookup
+        xhat = self.w["steps.0.ivf_centroids.weight" if ivf else "steps.0.codebook.weight"][codes_MB[0]].clone()
+        for m in range(1, self.cfg["M"] + (1 if ivf else 0)):
             xhat = xhat + self.step_mlp(m, self.w[f"steps.{m}.codebook.weight"][codes_MB[m]], xhat)
         return xhat
 
@@ -67,14 +68,22 @@ class TorchPort:
             parts = [self.encode(x[i:i + bs], max_rows) for i in range(0, len(x), bs)]
             return torch.cat([p[0] for p in parts], 1), torch.cat([p[1] for p in parts])
         n = len(x)
-        F1 = B if M > 1 else 1
-        d0 = self.pairwise(x, self.w["steps.0.codebook.weight"])
-        c0 = d0.topk(F1, dim=-1, largest=False).indices if F1 > 1 else d0.argmin(-1, keepdim=True)
-        xhat = self.w["steps.0.codebook.weight"][c0]     # [n, F, D]
+        ivf = bool(cfg.get("ivf_K"))
+        if ivf:                                          # IVFBook.quantize (qinco_base.py:146-163): arg-min, one beam
+            M = M + 1                                    # cfg._M_ivf
+            c0 = self.pairwise(x, self.w["steps.0.ivf_centroids.weight"]).argmin(-1, keepdim=True)
+            xhat = self.w["steps.0.ivf_centroids.weight"][c0]
+        else:
+            F1 = B if M > 1 else 1
+            d0 = self.pairwise(x, self.w["steps.0.codebook.weight"])
+            c0 = d0.topk(F1, dim=-1, largest=False).indices if F1 > 1 else d0.argmin(-1, keepdim=True)
+            xhat = self.w["steps.0.codebook.weight"][c0]     # [n, F, D]
         hist = c0.unsqueeze(0)                           # [m, n, F]
+        A_cfg = A
         for m in range(1, M):
             F_in, F_out = xhat.shape[1], (B if m < M - 1 else 1)
             cb = self.w[f"steps.{m}.codebook.weight"]
+            A = max(A_cfg, B) if (A_cfg > 0 and ivf and m == 1) else A_cfg      # QincoSubstep._n_codes (qinco_base.py:108-112)
             if A > 0:
                 r = (x.unsqueeze(1) - xhat).reshape(n * F_in, D)
                 idx = self.pairwise(r, self.w[f"steps.{m}.substep.codebook.weight"]).topk(A, -1, largest=False).indices

@@ -87,7 +87,7 @@ def test_edge_cases():
     np.testing.assert_array_equal(c[0], d.argmin(1))
 
 
-@pytest.mark.parametrize("name", GOLDEN_V2)
+@pytest.mark.parametrize("name", GOLDEN_V2 + GOLDEN_IVF)
 def test_torch_port_matches_reference(name, golden_loader):
     """oracle/torch_port.py (the timed CPU baseline) returns the reference's codes on every fixture."""
     from oracle.torch_port import TorchPort
