@@ -21,7 +21,7 @@ class OracleModel:
     """Reference call surface (model(x, step="encode") -> LongTensor [M, n]) on top of the CPU oracle."""
 
     def __init__(self, cfg, w):
-        self.cfg, self.w, self.M = cfg, w, cfg["M"]
+        self.cfg, self.w, self.M, self.ivf_K = cfg, w, cfg["M"], cfg.get("ivf_K", 0)
 
     def __call__(self, x, step="encode"):
         assert step == "encode"
@@ -34,15 +34,22 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n, out_dir):
+def _cfg(ivf):
+    return synth.make_cfg(None, D=16, M=3, K=32, L=1, de=16, dh=16, A=4, B=2, **({"ivf_K": 300} if ivf else {}))
+
+
+def _worker(rank, world, port, n, out_dir, ivf=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    cfg = synth.make_cfg(None, D=16, M=3, K=32, L=1, de=16, dh=16, A=4, B=2)
+    cfg = _cfg(ivf)
     w = synth.make_weights(cfg, seed=5, n_train=512, kmeans_iters=1)
     x = torch.from_numpy(synth.make_data(n, 16, seed=9))
     s, e = shard.shard_range(n, rank, world)
     codes = shard.encode_sharded(OracleModel(cfg, w), x[s:e], n, batch=7)
+    if ivf:
+        np.save(os.path.join(out_dir, f"ivf_{rank}.npy"), codes[0].numpy())
+        codes = codes[1]
     np.save(os.path.join(out_dir, f"codes_{rank}.npy"), codes.numpy())
     dist.barrier()
     dist.destroy_process_group()
@@ -70,3 +77,18 @@ def test_encode_sharded_matches_single_process(tmp_path, world, n):
         got = np.load(tmp_path / f"codes_{r}.npy")
         assert got.dtype == np.uint8 and got.shape == (n, cfg["M"])
         np.testing.assert_array_equal(got, ref)      # every rank ends with the full, identical code matrix
+
+
+def test_encode_sharded_ivf_model(tmp_path):
+    """IVF-QINCo: the int32 IVF codes travel as four extra byte columns of the one all-gather."""
+    world, n = 2, 23
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n, str(tmp_path), True), nprocs=world, join=True)
+    cfg = _cfg(True)
+    w = synth.make_weights(cfg, seed=5, n_train=512, kmeans_iters=1)
+    ref = orc.forward(cfg, w, synth.make_data(n, 16, seed=9), "encode")
+    for r in range(world):
+        ivf, codes = np.load(tmp_path / f"ivf_{r}.npy"), np.load(tmp_path / f"codes_{r}.npy")
+        assert ivf.dtype == np.int32 and ivf.shape == (n,) and codes.shape == (n, cfg["M"])
+        np.testing.assert_array_equal(ivf, ref[0])
+        np.testing.assert_array_equal(codes, ref[1:].T.astype(np.uint8))
