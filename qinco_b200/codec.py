@@ -70,6 +70,63 @@ class QINCoV1:
     forward = encode
 
 
+class PQQINCoV1:
+    """PQ-QINCo (reference qinco_v1/model_qinco.py:185-234): the vector is cut into consecutive sub-vectors, each with
+    its own QINCo1 quantizer and db_scale; an optional OPQ rotation is applied before / undone after.  A thin loop over
+    `QINCoV1` sub-quantizers: all quantisation work stays in the CUDA kernels, the rotation is one torch matmul."""
+
+    def __init__(self, sub_quantizers, opq_matrix=None):
+        self.db_scale = 1                    # set per sub-quantizer, like the reference
+        self.sub_quantizers = list(sub_quantizers)
+        self.device = self.sub_quantizers[0].device
+        self.opq_matrix = None if opq_matrix is None else torch.as_tensor(np.asarray(opq_matrix, np.float32)).to(self.device)
+        self.d = self.D = sum(q.d for q in self.sub_quantizers)
+        self.M = sum(q.M for q in self.sub_quantizers)
+        self.K = self.sub_quantizers[0].K
+
+    def parameters(self):
+        return self.sub_quantizers[0].parameters()
+
+    def eval(self):
+        return self
+
+    def half(self):
+        return self
+
+    @torch.no_grad()
+    def encode(self, x):
+        """x [bs, D] -> (codes [bs, sum M] int64, xhat [bs, D])   (model_qinco.py:203-221)."""
+        x = x.float().to(self.device)
+        d0, codes, xhat = 0, [], torch.zeros_like(x)
+        if self.opq_matrix is not None:
+            x = x @ self.opq_matrix.T
+        for q in self.sub_quantizers:
+            d1 = d0 + q.d
+            code, xhat_sub = q.encode((x[:, d0:d1] / q.db_scale).contiguous())
+            codes.append(code)
+            xhat[:, d0:d1] = xhat_sub * q.db_scale
+            d0 = d1
+        if self.opq_matrix is not None:
+            xhat = xhat @ self.opq_matrix
+        return torch.cat(codes, 1), xhat
+
+    @torch.no_grad()
+    def decode(self, codes):
+        """codes [bs, sum M] -> x [bs, D]   (model_qinco.py:223-234)."""
+        codes = torch.as_tensor(codes).to(self.device)
+        c0, xs = 0, []
+        for q in self.sub_quantizers:
+            c1 = c0 + q.M
+            xs.append(q.decode(codes[:, c0:c1].contiguous()) * q.db_scale)
+            c0 = c1
+        x = torch.cat(xs, 1)
+        if self.opq_matrix is not None:
+            x = x @ self.opq_matrix
+        return x
+
+    forward = encode
+
+
 def encode(model, x, bs, is_float16=False, verbose=True):
     """numpy [N, D] float32 -> numpy [N, M] int64; prints the reference's progress/MSE lines (codec_qinco.py:25-46)."""
     t0 = time.time()
