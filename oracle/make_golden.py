@@ -44,6 +44,12 @@ CASES = {
     "proj_a8_b4":     (dict(D=96, M=4, K=256, L=3, de=192, dh=160, A=8, B=4, qinco1_mode=False), 40, (0.25, 1.5), 24),
     "q1_l4":          (dict(D=128, M=4, K=256, L=4, de=128, dh=256, A=0, B=1, qinco1_mode=True), 32, (0.0, 1.0), 25),
     "l_a16_b16":      (dict(D=128, M=4, K=256, L=4, de=384, dh=384, A=16, B=16, qinco1_mode=False), 16, (0.0, 1.0), 26),
+    # the BASELINE configurations at FULL depth (L = 16, all M steps), 64 rows each: QINCo1 preset (config 1), QINCo2-L
+    # 8x8 beam 16 (config 3), the Deep1B shape 16x8 d=96 (config 4), the Contriever shape d=768 beam 32 (config 5)
+    "full_q1":        (dict(D=128, M=8, K=256, L=16, de=128, dh=256, A=0, B=1, qinco1_mode=True), 64, (0.0, 1.0), 41),
+    "full_l_b16":     (dict(D=128, M=8, K=256, L=16, de=384, dh=384, A=16, B=16, qinco1_mode=False), 64, (0.0, 1.0), 42),
+    "full_deep_m16":  (dict(D=96, M=16, K=256, L=16, de=384, dh=384, A=16, B=16, qinco1_mode=False), 64, (0.0, 1.0), 43),
+    "full_contr_b32": (dict(D=768, M=8, K=256, L=16, de=384, dh=384, A=16, B=32, qinco1_mode=False), 64, (0.0, 1.0), 44),
     # IVF-QINCo: step 0 = arg-min over ivf_K centroids, then M implicit-codebook steps; codes [M+1, n]
     "ivf_a8_b4":      (dict(D=32, M=3, K=64, L=2, de=32, dh=48, A=8, B=4, qinco1_mode=False, ivf_K=200), 96, (0.25, 1.5), 31),
     "ivf_a4_b8":      (dict(D=32, M=3, K=64, L=1, de=48, dh=32, A=4, B=8, qinco1_mode=False, ivf_K=77), 64, (0.0, 1.0), 32),
