@@ -110,7 +110,20 @@ int qb_decode_ivf_host(qb_model* m, const int32_t* ivf_codes_host, const uint8_t
 int qb_encode_host(qb_model* m, const float* x_host, int64_t n, int normalize, uint8_t* codes_host, float* xhat_host);
 int qb_decode_host(qb_model* m, const uint8_t* codes_host, int64_t n, int denormalize, float* out_host);
 
+/* Code-matrix conversions at the reference's tensor surface, on the device and asynchronous on `stream`.
+ * qb_codes_pack: the [S, n] integer matrix the reference passes to decode (qinco_base.py:447-449; S = M, or M + 1 with the
+ * IVF code in row 0; uint8 / int32 / int64 elements -- the IVF search passes a transposed int32 view, search_tasks.py:428-445,
+ * hence the two element strides) -> codes_dev uint8 [n, M] (+ ivf_codes_dev int32 [n] for IVF models, else NULL).  Codes
+ * outside [0, K) / [0, ivf_K) set the device error word (0x10 / 0x20, reported once by qb_check) and are clamped: the
+ * counterpart of the device-side index assert the reference's codebook lookup would raise.
+ * qb_codes_unpack: uint8 [n, M] (+ int32 [n]) -> contiguous int64 [S, n], what encode returns (qinco_base.py:480-485). */
+int qb_codes_pack(qb_model* m, const void* codes_MB_dev, int elem_bytes, int64_t stride_row, int64_t stride_col, int64_t n,
+                  uint8_t* codes_dev, int32_t* ivf_codes_dev, void* stream);
+int qb_codes_unpack(qb_model* m, const uint8_t* codes_dev, const int32_t* ivf_codes_dev, int64_t n, int64_t* codes_MB_dev,
+                    void* stream);
+
 /* Reads the device-side error word (set by a kernel before it traps, or by an out-of-range code); 0 when clean.
+ * An out-of-range-code report is cleared once returned (the kernels clamp and finish); a time-out is fatal and stays.
  * Cheap (one host read of mapped memory); call it after synchronising the stream. */
 int qb_check(qb_model* m);
 

@@ -23,7 +23,7 @@ SYMBOLS = ["qb_version", "qb_last_error", "qb_model_create", "qb_model_destroy",
            "qb_decode_workspace_bytes", "qb_encode", "qb_decode", "qb_encode_host", "qb_decode_host", "qb_check",
            "qb_launch_count", "qb_timing_enable", "qb_timing_read", "qb_model_info", "qb_debug_step", "qb_plan_export", "qb_plan_pack", "qb_plan_tables",
            "qb_pairwise_create", "qb_pairwise_destroy", "qb_pairwise_decode", "qb_pairwise_check", "qb_pairwise_launch_count",
-           "qb_pairwise_last_error", "qb_encode_ivf", "qb_decode_ivf", "qb_encode_ivf_host", "qb_decode_ivf_host"]
+           "qb_pairwise_last_error", "qb_encode_ivf", "qb_decode_ivf", "qb_encode_ivf_host", "qb_decode_ivf_host", "qb_codes_pack", "qb_codes_unpack"]
 
 _fpp = C.POINTER(C.POINTER(C.c_float))
 
@@ -89,6 +89,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.qb_decode_ivf_host.argtypes = [vp, vp, vp, i64, C.c_int, vp]
     lib.qb_encode_host.argtypes = [vp, vp, i64, C.c_int, vp, vp]
     lib.qb_decode_host.argtypes = [vp, vp, i64, C.c_int, vp]
+    lib.qb_codes_pack.argtypes = [vp, vp, C.c_int, i64, i64, i64, vp, vp, vp]
+    lib.qb_codes_unpack.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.qb_check.argtypes = [vp]
     lib.qb_launch_count.argtypes = [vp]
     lib.qb_launch_count.restype = i64
@@ -250,6 +252,12 @@ class Handle:
         out = np.empty((n, self.D), np.float32)
         check(self._lib.qb_decode_host(self._h, codes.ctypes.data, n, int(denormalize), out.ctypes.data))
         return out
+
+    def codes_pack(self, src_ptr, elem_bytes, stride_row, stride_col, n, codes_ptr, ivf_ptr, stream):
+        check(self._lib.qb_codes_pack(self._h, src_ptr, elem_bytes, stride_row, stride_col, n, codes_ptr, ivf_ptr, stream))
+
+    def codes_unpack(self, codes_ptr, ivf_ptr, n, dst_ptr, stream):
+        check(self._lib.qb_codes_unpack(self._h, codes_ptr, ivf_ptr, n, dst_ptr, stream))
 
     def debug_step(self, step, xhat_ptr, codes_ptr, n, out_ptr, ws_ptr, ws_bytes, stream):
         check(self._lib.qb_debug_step(self._h, step, xhat_ptr, codes_ptr, n, out_ptr, ws_ptr, ws_bytes, stream))

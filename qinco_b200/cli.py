@@ -25,10 +25,10 @@ def build_parser():
     g.add_argument("--encode", default=False, action="store_true")
     g.add_argument("--decode", default=False, action="store_true")
     g = ap.add_argument_group("files")
-    g.add_argument("--model", default="", help="QINCo model to use")
-    g.add_argument("--i", required=True, help="input vectors (npy or fvecs/bvecs format) / codes")
+    g.add_argument("--model", default="", help="checkpoint: v1 state-dict file (or pickled module with --unsafe-pickle), v2 save_model dict with --v2")
+    g.add_argument("--i", required=True, help="--encode: vectors (.npy / .fvecs / .bvecs); --decode: codes (.npy, raw, or .npz database)")
     g.add_argument("--o", required=True, help="output (npy, raw, or .npz encoded database with --v2)")
-    g.add_argument("--raw", default=False, action="store_true", help="codes are in raw format (no header)")
+    g.add_argument("--raw", default=False, action="store_true", help="codes as headerless bit strings (M * ceil(log2 K) bits per vector)")
     g.add_argument("--v2", default=False, action="store_true", help="QINCo2 checkpoint (save_model dict) instead of a v1 module")
     g = ap.add_argument_group("computation options")
     g.add_argument("--batch_size", default=4096, type=int)
@@ -36,15 +36,17 @@ def build_parser():
     g.add_argument("--float16", default=False, action="store_true", help="accepted for compatibility (operands are always fp16)")
     g.add_argument("--A", type=int, default=None, help="v2: override the number of pre-selected candidates")
     g.add_argument("--B", type=int, default=None, help="v2: override the beam width")
+    g.add_argument("--unsafe-pickle", dest="unsafe_pickle", default=False, action="store_true",
+                   help="v1: also accept a pickled nn.Module checkpoint (read through a restricted unpickler)")
     g.add_argument("--ivf_centroids", default=None, help="v2 IVF models: .npy of the (normalised) IVF centroids, like cfg.ivf_centroids")
     return ap
 
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
-    print("args:", args)
+    print("arguments:", vars(args))
     assert args.encode ^ args.decode, "one of encode or decode must be selected"
-    print("loading model", args.model)
+    print("model file:", args.model)
     if args.v2:
         cfg, sd = io.load_v2_checkpoint(args.model, dict(A=args.A, B=args.B), ivf_centroids=args.ivf_centroids)
         ivf = bool(cfg.get("ivf_K"))
@@ -52,14 +54,13 @@ def main(argv=None):
         M, K, D = cfg["M"], cfg["K"], cfg["D"]
     else:
         ivf = False
-        sd, db_scale = io.load_v1_checkpoint(args.model)
-        model = codec.QINCoV1(sd, db_scale=db_scale, device=args.device)
-        print("  database normalization factor", model.db_scale)
+        model = io.load_v1_model(args.model, device=args.device, allow_pickled_module=args.unsafe_pickle)
+        print("  db_scale of the model:", model.db_scale)
         M, K, D = model.M, model.K, model.D
     if args.encode:
-        print("reading", args.i)
+        print("input vectors:", args.i)
         x = io.read_vectors(args.i)
-        print(f"encoding intput vectors of size {x.shape}")
+        print(f"encoding {x.shape[0]} vectors of dimension {x.shape[1]}")
         if args.v2 and ivf:      # [n, M + 1]: column 0 is the IVF code, like model(batch, step="encode").T
             ivf_codes, codes_u8, _ = model._h.encode_ivf_host(np.ascontiguousarray(x, np.float32), normalize=True)
             codes = np.concatenate([ivf_codes.astype(np.int64)[:, None], codes_u8.astype(np.int64)], axis=1)
@@ -70,15 +71,15 @@ def main(argv=None):
             codes = codec.encode(model, x, bs=args.batch_size, is_float16=args.float16)
         if args.raw:
             assert not ivf, "--raw packs M * ceil(log2 K) bits per vector: not defined for IVF codes"
-            print(f"Packing result of size {codes.shape} to {M} * {int(np.ceil(np.log2(K)))} bits")
+            print(f"bit-packing codes {codes.shape}: {M} x {int(np.ceil(np.log2(K)))} bits per vector")
             io.write_raw_codes(args.o, codes, K)
         elif args.v2 and args.o.endswith(".npz"):
             io.save_encoded_db(args.o, [codes], K=K, M=M, D=D)
         else:
-            print(f"Storing result of size {codes.shape} in {args.o}")
+            print(f"writing codes {codes.shape} to {args.o}")
             np.save(args.o, codes)
     else:
-        print("reading", args.i)
+        print("input codes:", args.i)
         if args.raw:
             codes = io.read_raw_codes(args.i, M, K)
         elif args.i.endswith(".npz"):
@@ -87,7 +88,7 @@ def main(argv=None):
             codes = np.load(args.i)
         else:
             raise RuntimeError("unrecognized format")
-        print(f"Decoding intput codes of size {codes.shape}")
+        print(f"decoding {codes.shape[0]} codes of {codes.shape[1]} columns")
         if args.v2 and ivf:
             y = model._h.decode_ivf_host(codes[:, 0].astype(np.int32), codes[:, 1:].astype(np.uint8), denormalize=True)
         elif args.v2:
@@ -96,7 +97,7 @@ def main(argv=None):
             y = model._h.decode_host(codes.astype(np.uint8), denormalize=True)
         else:
             y = codec.decode(model, codes, bs=args.batch_size, is_float16=args.float16)
-        print(f"Storing result of size {y.shape} in {args.o}")
+        print(f"writing vectors {y.shape} to {args.o}")
         np.save(args.o, y)
     torch.cuda.synchronize()
 

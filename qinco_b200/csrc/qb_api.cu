@@ -338,7 +338,7 @@ int decode_chunk(qb_model* m, const int32_t* ivf_codes, const uint8_t* codes, in
         QB_CUDA(timed_launch(m, KIND_OTHER, n, st, [&] {
             return qb::launch_decode_init(m->cb0, codes, n, M, D, m->K, (M == 1 && !affine) ? out : xh[cur], m->err_dev, st);
         }));
-    if (M == 1 && affine)
+    if (M == 1 && affine && !m->ivf_K)     // (an IVF model with M == 1 still has one MLP step, which applies the affine)
         QB_CUDA(timed_launch(m, KIND_OTHER, n, st, [&] { return qb::launch_affine(xh[cur], out, n, D, scale, shift, st); }));
     for (int step = 1; step < S; step++) {
         const StepDev& s = m->steps[step];
@@ -367,12 +367,17 @@ int decode_chunk(qb_model* m, const int32_t* ivf_codes, const uint8_t* codes, in
 }
 
 int check_device_flag(qb_model* m) {
-    const uint32_t e = *reinterpret_cast<volatile uint32_t*>(m->err_host);
+    volatile uint32_t* word = reinterpret_cast<volatile uint32_t*>(m->err_host);
+    const uint32_t e = *word;
     if (e) {
-        char buf[160];
+        char buf[200];
         snprintf(buf, sizeof(buf),
-                 "device-side failure, err word 0x%x (0x10: code out of range; 0x1xx/0x2xx/0x3xx/0x4xx: barrier wait "
-                 "time-out in producer/MMA/ring/epilogue)", e);
+                 "device-side failure, err word 0x%x (0x10: code out of range [0,K); 0x20: IVF code out of range; "
+                 "0x1xx/0x2xx/0x3xx/0x4xx: barrier wait time-out in producer/MMA/ring/epilogue)", e);
+        // Out-of-range codes are the caller's input error: the kernels clamp them and run to completion, so the word is
+        // reported ONCE and cleared -- later calls on the model are good again.  Time-outs precede a trap: the context is
+        // gone and the word stays.
+        if (e == 0x10u || e == 0x20u) *word = 0;
         return fail(QB_ERR_KERNEL, buf);
     }
     return QB_OK;
@@ -421,7 +426,8 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
     int ndev = 0;
     QB_CUDA(cudaGetDeviceCount(&ndev));
     if (d->device < 0 || d->device >= ndev) return fail(QB_ERR_INVALID, "device ordinal out of range");
-    QB_CUDA(cudaSetDevice(d->device));
+    qb::DeviceGuard guard(d->device);       // the caller's current device is restored on every exit
+    QB_CUDA(guard.err);
     cudaDeviceProp prop;
     QB_CUDA(cudaGetDeviceProperties(&prop, d->device));
     if (prop.major != 10)
@@ -516,7 +522,7 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
 
 int qb_model_destroy(qb_model* m) {
     if (!m) return QB_OK;
-    cudaSetDevice(m->device);
+    qb::DeviceGuard guard(m->device);
     for (void* p : m->dev_allocs) cudaFree(p);
     for (auto& s : m->slot) {
         if (s.x_pin) cudaFreeHost(s.x_pin);
@@ -567,7 +573,8 @@ static int encode_impl(qb_model* m, const float* x_dev, int64_t n, int normalize
     nc = std::min<int64_t>(nc, default_chunk(m));
     if (nc < 1) return fail(QB_ERR_WORKSPACE, "workspace too small for one vector; see qb_encode_workspace_bytes");
     if (nc >= 128) nc = nc / 128 * 128;
-    QB_CUDA(cudaSetDevice(m->device));
+    qb::DeviceGuard guard(m->device);
+    QB_CUDA(guard.err);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     for (int64_t i0 = 0; i0 < n; i0 += nc) {
         const int64_t c = std::min(nc, n - i0);
@@ -602,7 +609,8 @@ static int decode_impl(qb_model* m, const int32_t* ivf_codes_dev, const uint8_t*
     nc = std::min<int64_t>(nc, default_chunk(m) * 16);
     if (nc < 1) return fail(QB_ERR_WORKSPACE, "workspace too small for one vector; see qb_decode_workspace_bytes");
     if (nc >= 128) nc = nc / 128 * 128;
-    QB_CUDA(cudaSetDevice(m->device));
+    qb::DeviceGuard guard(m->device);
+    QB_CUDA(guard.err);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     for (int64_t i0 = 0; i0 < n; i0 += nc) {
         const int64_t c = std::min(nc, n - i0);
@@ -630,9 +638,30 @@ int qb_check(qb_model* m) {
 }
 
 // Pipelined host loops: chunk i is copied in on one stream while chunk i-1 computes and chunk i-2 copies out.
+static int host_loop_body(qb_model* m, bool enc, const float* x_host, const int32_t* ivf_in, const uint8_t* codes_in, int64_t n,
+                          int flag, int32_t* ivf_out, uint8_t* codes_out, float* out_host);
+
+// Error exits leave copies in flight and staging slots marked pending: drain the three streams and forget the slots, so
+// the next call on this model cannot copy a stale chunk into ITS caller's buffers.
 static int host_loop(qb_model* m, bool enc, const float* x_host, const int32_t* ivf_in, const uint8_t* codes_in, int64_t n,
                      int flag, int32_t* ivf_out, uint8_t* codes_out, float* out_host) {
-    QB_CUDA(cudaSetDevice(m->device));
+    qb::DeviceGuard guard(m->device);
+    QB_CUDA(guard.err);
+    const int rc = host_loop_body(m, enc, x_host, ivf_in, codes_in, n, flag, ivf_out, codes_out, out_host);
+    if (rc != QB_OK) {
+        const std::string keep = g_err;
+        if (m->s_h2d) cudaStreamSynchronize(m->s_h2d);
+        if (m->s_comp) cudaStreamSynchronize(m->s_comp);
+        if (m->s_d2h) cudaStreamSynchronize(m->s_d2h);
+        cudaGetLastError();
+        for (auto& s : m->slot) s.pending_i0 = -1;
+        g_err = keep;
+    }
+    return rc;
+}
+
+static int host_loop_body(qb_model* m, bool enc, const float* x_host, const int32_t* ivf_in, const uint8_t* codes_in, int64_t n,
+                          int flag, int32_t* ivf_out, uint8_t* codes_out, float* out_host) {
     int rc = ensure_host_staging(m, !enc);
     if (rc) return rc;
     const int64_t nc = m->host_chunk;
@@ -738,6 +767,37 @@ int qb_decode_ivf_host(qb_model* m, const int32_t* ivf_codes_host, const uint8_t
     return host_loop(m, false, nullptr, ivf_codes_host, codes_host, n, denormalize, nullptr, nullptr, out_host);
 }
 
+int qb_codes_pack(qb_model* m, const void* codes_MB_dev, int elem_bytes, int64_t stride_row, int64_t stride_col, int64_t n,
+                  uint8_t* codes_dev, int32_t* ivf_codes_dev, void* stream) {
+    if (!m) return fail(QB_ERR_INVALID, "model is NULL");
+    if (n < 0) return fail(QB_ERR_INVALID, "n < 0");
+    if (n == 0) return QB_OK;
+    if (!codes_MB_dev || !codes_dev) return fail(QB_ERR_INVALID, "NULL buffer");
+    if ((m->ivf_K > 0) != (ivf_codes_dev != nullptr)) return fail(QB_ERR_INVALID, "ivf_codes_dev must be given exactly for IVF models");
+    if (elem_bytes != 1 && elem_bytes != 4 && elem_bytes != 8) return fail(QB_ERR_INVALID, "codes must be uint8, int32 or int64");
+    qb::DeviceGuard guard(m->device);
+    QB_CUDA(guard.err);
+    m->launches++;
+    QB_CUDA(qb::launch_codes_pack(codes_MB_dev, elem_bytes, stride_row, stride_col, n, m->M, m->K, m->ivf_K, codes_dev,
+                                  ivf_codes_dev, m->err_dev, reinterpret_cast<cudaStream_t>(stream)));
+    return QB_OK;
+}
+
+int qb_codes_unpack(qb_model* m, const uint8_t* codes_dev, const int32_t* ivf_codes_dev, int64_t n, int64_t* codes_MB_dev,
+                    void* stream) {
+    if (!m) return fail(QB_ERR_INVALID, "model is NULL");
+    if (n < 0) return fail(QB_ERR_INVALID, "n < 0");
+    if (n == 0) return QB_OK;
+    if (!codes_MB_dev || !codes_dev) return fail(QB_ERR_INVALID, "NULL buffer");
+    if ((m->ivf_K > 0) != (ivf_codes_dev != nullptr)) return fail(QB_ERR_INVALID, "ivf_codes_dev must be given exactly for IVF models");
+    qb::DeviceGuard guard(m->device);
+    QB_CUDA(guard.err);
+    m->launches++;
+    QB_CUDA(qb::launch_codes_unpack(codes_dev, ivf_codes_dev, n, m->M, m->ivf_K ? 1 : 0, codes_MB_dev,
+                                    reinterpret_cast<cudaStream_t>(stream)));
+    return QB_OK;
+}
+
 int64_t qb_launch_count(const qb_model* m) { return m ? m->launches : 0; }
 
 int qb_timing_enable(qb_model* m, int on) {
@@ -748,7 +808,8 @@ int qb_timing_enable(qb_model* m, int on) {
 
 int qb_timing_read(qb_model* m, double* ms_out, int64_t* launches_out, int64_t* rows_out, int n_kinds) {
     if (!m || !ms_out || !launches_out || !rows_out) return fail(QB_ERR_INVALID, "NULL argument");
-    QB_CUDA(cudaSetDevice(m->device));
+    qb::DeviceGuard guard(m->device);
+    QB_CUDA(guard.err);
     for (int k = 0; k < n_kinds; k++) { ms_out[k] = 0; launches_out[k] = 0; rows_out[k] = 0; }
     for (auto& t : m->timed) {
         QB_CUDA(cudaEventSynchronize(t.b));
@@ -780,7 +841,8 @@ int qb_debug_step(qb_model* m, int step, const float* xhat_dev, const uint8_t* c
     if (step < 1 || step >= m->S) return fail(QB_ERR_INVALID, "step out of range (MLP steps are 1..S-1)");
     if (n <= 0) return QB_OK;
     if (workspace_bytes < (size_t)n * m->De * 4 + 256) return fail(QB_ERR_WORKSPACE, "workspace too small (n*de*4+256)");
-    QB_CUDA(cudaSetDevice(m->device));
+    qb::DeviceGuard guard(m->device);
+    QB_CUDA(guard.err);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     float* u = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(workspace_dev), 256));
     const StepDev& s = m->steps[step];

@@ -7,6 +7,23 @@
 
 namespace qb {
 
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards: no entry point of the
+// library changes the process's current device behind the caller's back (multi-GPU callers keep allocating where they were).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;       // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 enum { QB_MODE_SCORE = 0, QB_MODE_APPLY = 1 };
 enum { QB_TRACE_EVENTS = 2048 };
 
@@ -108,6 +125,15 @@ cudaError_t launch_ivf_lookup(const float* cent, const int32_t* ivf_codes, int64
 // xhat[v] = C_0[codes[v*M]]  (decode start, qinco_base.py:447-452 with step 0 = plain codebook lookup)
 cudaError_t launch_decode_init(const float* cb0, const uint8_t* codes, int64_t n, int M, int D, int K, float* xhat,
                                uint32_t* err_flag, cudaStream_t stream);
+// Code-matrix conversions at the reference's surface (qinco_base.py:447-449, :480-485): the reference moves codes as
+// [S, n] integer matrices (S = M, or M + 1 with the IVF code in row 0; int64 from encode, int32 from the search's re-ranking
+// loop, search_tasks.py:428-445), the kernels as uint8 [n, M] (+ int32 [n] IVF codes).  `pack` range-checks on the device
+// (err word 0x10 / 0x20, the offending code is clamped) so the Python surface needs no reduction kernels and no host sync.
+cudaError_t launch_codes_pack(const void* codes_MB, int elem_bytes, int64_t stride_row, int64_t stride_col, int64_t n, int M,
+                              int K, int ivf_K, uint8_t* codes_u8, int32_t* ivf, uint32_t* err_flag, cudaStream_t stream);
+cudaError_t launch_codes_unpack(const uint8_t* codes_u8, const int32_t* ivf, int64_t n, int M, int has_ivf, int64_t* codes_MB,
+                                cudaStream_t stream);
+
 // out[i] = in[i]*scale + shift[i % D]
 cudaError_t launch_affine(const float* in, float* out, int64_t n, int D, float scale, const float* shift,
                           cudaStream_t stream);

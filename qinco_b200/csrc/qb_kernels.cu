@@ -434,7 +434,60 @@ __global__ void qb_affine_kernel(const float* __restrict__ in, float* __restrict
     out[t] = fmaf(in[t], scale, shift ? shift[t % D] : 0.f);
 }
 
+// [S, n] integer code matrix (any strides, int32 / int64) -> uint8 [n, M] (+ int32 [n] IVF codes), range-checked
+template <typename T>
+__global__ void qb_codes_pack_kernel(const T* __restrict__ src, int64_t stride_row, int64_t stride_col, int64_t n, int M, int K,
+                                     int ivf_K, uint8_t* __restrict__ codes, int32_t* __restrict__ ivf, uint32_t* err_flag) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int row0 = ivf_K ? 1 : 0;
+    if (ivf_K) {
+        long long c = (long long)src[v * stride_col];
+        if (c < 0 || c >= ivf_K) { atomicExch(err_flag, 0x20u); c = 0; }
+        ivf[v] = (int32_t)c;
+    }
+    for (int m = 0; m < M; m++) {
+        long long c = (long long)src[(int64_t)(m + row0) * stride_row + v * stride_col];
+        if (c < 0 || c >= K) { atomicExch(err_flag, 0x10u); c = 0; }
+        codes[v * M + m] = (uint8_t)c;
+    }
+}
+
+// uint8 [n, M] (+ int32 [n]) -> contiguous int64 [S, n]; a thread owns one vector, the stores of a warp are coalesced per row
+__global__ void qb_codes_unpack_kernel(const uint8_t* __restrict__ codes, const int32_t* __restrict__ ivf, int64_t n, int M,
+                                       int has_ivf, int64_t* __restrict__ dst) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    if (has_ivf) dst[v] = (int64_t)ivf[v];
+    for (int m = 0; m < M; m++) dst[(int64_t)(m + has_ivf) * n + v] = (int64_t)codes[v * M + m];
+}
+
 }  // namespace
+
+cudaError_t launch_codes_pack(const void* codes_MB, int elem_bytes, int64_t stride_row, int64_t stride_col, int64_t n, int M,
+                              int K, int ivf_K, uint8_t* codes_u8, int32_t* ivf, uint32_t* err_flag, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (elem_bytes == 8)
+        qb_codes_pack_kernel<long long><<<grid, 256, 0, stream>>>((const long long*)codes_MB, stride_row, stride_col, n, M, K, ivf_K,
+                                                                   codes_u8, ivf, err_flag);
+    else if (elem_bytes == 4)
+        qb_codes_pack_kernel<int32_t><<<grid, 256, 0, stream>>>((const int32_t*)codes_MB, stride_row, stride_col, n, M, K, ivf_K,
+                                                                codes_u8, ivf, err_flag);
+    else if (elem_bytes == 1)
+        qb_codes_pack_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)codes_MB, stride_row, stride_col, n, M, K, ivf_K,
+                                                                codes_u8, ivf, err_flag);
+    else
+        return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_codes_unpack(const uint8_t* codes_u8, const int32_t* ivf, int64_t n, int M, int has_ivf, int64_t* codes_MB,
+                                cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    qb_codes_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(codes_u8, ivf, n, M, has_ivf, codes_MB);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_prep(const PrepParams& p, cudaStream_t stream) {
     if (p.n_beams <= 0) return cudaSuccess;

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/qinco_b200.h"
+#include "qb_dev.h"
 
 namespace {
 
@@ -120,7 +121,7 @@ int qb_pairwise_create(const qb_pairwise_desc* d, qb_pairwise** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || d->device < 0 || d->device >= ndev)
         return pw_fail(QB_ERR_CUDA, "no usable CUDA device (there is no CPU fallback)");
-    cudaSetDevice(d->device);
+    qb::DeviceGuard guard(d->device);       // the caller's current device is restored on exit
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess || prop.major != 10)
         return pw_fail(QB_ERR_CUDA, "this library is built for sm_100a only");
@@ -166,7 +167,7 @@ int qb_pairwise_create(const qb_pairwise_desc* d, qb_pairwise** out) {
 
 int qb_pairwise_destroy(qb_pairwise* h) {
     if (!h) return QB_OK;
-    cudaSetDevice(h->device);
+    qb::DeviceGuard guard(h->device);
     if (h->table) cudaFree(h->table);
     if (h->ivf_map) cudaFree(h->ivf_map);
     if (h->err_host) cudaFreeHost(h->err_host);
@@ -180,7 +181,7 @@ int qb_pairwise_decode(qb_pairwise* h, const uint8_t* codes_dev, const int32_t* 
     if (n < 0) return pw_fail(QB_ERR_INVALID, "n < 0");
     if (n == 0) return QB_OK;
     if (!codes_dev || !ivf_codes_dev || !out_dev) return pw_fail(QB_ERR_INVALID, "NULL buffer");
-    cudaSetDevice(h->device);
+    qb::DeviceGuard guard(h->device);
     PwParams p;
     std::memset(&p, 0, sizeof(p));
     p.D4 = h->D / 4; p.M = h->M; p.K = h->K; p.Mt = h->Mt; p.ivf_K = h->ivf_K; p.n = n;

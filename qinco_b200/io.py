@@ -89,15 +89,84 @@ def load_v2_checkpoint(path: str, overrides: dict | None = None, ivf_centroids: 
     return cfg, sd
 
 
-def load_v1_checkpoint(path: str):
-    """-> (state dict of numpy arrays, db_scale) from a pickled v1 module or a state-dict file."""
+class _SafeV1Unpickler:
+    """pickle-module stand-in for `torch.load(..., pickle_module=...)`: unpickles a whole v1 `nn.Module`
+    (qinco_v1/codec_qinco.py:112 loads checkpoints that way) WITHOUT importing the reference and without executing
+    arbitrary pickle code: the classes of reference qinco_v1/model_qinco.py map to inert `nn.Module` stubs, only torch /
+    numpy / collections names are resolvable, everything else is refused."""
+    import pickle as _pickle
+
+    _V1_CLASSES = ("QINCo", "QINCoStep", "PQ_QINCo")
+    _ALLOWED_PREFIXES = ("torch", "collections", "numpy")
+    _ALLOWED_BUILTINS = ("set", "frozenset", "slice", "range", "complex", "bytearray", "list", "dict", "tuple", "int", "float", "bool", "str")
+
+    class Unpickler(_pickle.Unpickler):
+        def find_class(self, module, name):
+            import builtins
+            import importlib
+
+            import torch
+            if module in ("model_qinco", "qinco_v1.model_qinco") and name in _SafeV1Unpickler._V1_CLASSES:
+                return type(name, (torch.nn.Module,), {"_qb_v1_kind": name})
+            if module in ("builtins", "__builtin__") and name in _SafeV1Unpickler._ALLOWED_BUILTINS:
+                return getattr(builtins, name)
+            if module.split(".")[0] in _SafeV1Unpickler._ALLOWED_PREFIXES and not name.startswith("__"):
+                return getattr(importlib.import_module(module), name)
+            raise _SafeV1Unpickler._pickle.UnpicklingError(f"refusing to unpickle {module}.{name} from a v1 checkpoint")
+
+    @staticmethod
+    def load(f, **kw):
+        return _SafeV1Unpickler.Unpickler(f, **kw).load()
+
+    Pickler = _pickle.Pickler
+    __name__ = "qinco_b200.io._SafeV1Unpickler"
+
+
+def _load_v1_object(path: str, allow_pickled_module: bool):
     import torch
-    obj = torch.load(str(path), map_location="cpu", weights_only=False)
+    try:
+        return torch.load(str(path), map_location="cpu", weights_only=True)
+    except Exception as e:
+        if not allow_pickled_module:
+            raise RuntimeError(
+                f"{path} is not a plain state-dict file ({type(e).__name__}).  Pickled v1 nn.Module checkpoints (what the "
+                "reference's codec loads) are only read on request: pass allow_pickled_module=True / --unsafe-pickle; they go "
+                "through a restricted unpickler that maps model_qinco.{QINCo,QINCoStep,PQ_QINCo} to inert stubs") from e
+    return torch.load(str(path), map_location="cpu", weights_only=False, pickle_module=_SafeV1Unpickler)
+
+
+def load_v1_checkpoint(path: str, allow_pickled_module: bool = False):
+    """-> (state dict of numpy arrays, db_scale) of a plain v1 QINCo from a state-dict file ({"state_dict", "db_scale"} or
+    the bare dict) or, on request, a pickled v1 module.  PQ-QINCo and IVF v1 modules are not a single state dict: use
+    `load_v1_model`, which says so."""
+    obj = _load_v1_object(path, allow_pickled_module)
     if hasattr(obj, "state_dict"):
-        return {k: _np(v) for k, v in obj.state_dict().items()}, float(getattr(obj, "db_scale", 1.0))
-    if isinstance(obj, dict) and "state_dict" in obj:
-        return {k: _np(v) for k, v in obj["state_dict"].items()}, float(obj.get("db_scale", 1.0))
-    return {k: _np(v) for k, v in obj.items()}, 1.0
+        kind = getattr(obj, "_qb_v1_kind", type(obj).__name__)
+        if kind != "QINCo":
+            raise ValueError(f"{path} holds a pickled {kind}; load_v1_checkpoint reads plain QINCo models (use load_v1_model)")
+        sd, scale = {k: _np(v) for k, v in obj.state_dict().items()}, float(getattr(obj, "db_scale", 1.0))
+    elif isinstance(obj, dict) and "state_dict" in obj:
+        sd, scale = {k: _np(v) for k, v in obj["state_dict"].items()}, float(obj.get("db_scale", 1.0))
+    else:
+        sd, scale = {k: _np(v) for k, v in obj.items()}, 1.0
+    if "codebook0.weight" not in sd:
+        what = "a PQ-QINCo" if any(k.startswith("sub_quantizer_") for k in sd) else "an unsupported v1 model"
+        raise ValueError(f"{path}: state dict of {what} (no codebook0.weight); use load_v1_model for PQ-QINCo")
+    return sd, scale
+
+
+def load_v1_model(path: str, device="cuda:0", allow_pickled_module: bool = False):
+    """-> a ready `codec.QINCoV1`, or a `codec.PQQINCoV1` when the file holds a pickled PQ_QINCo (sub-quantizers with their
+    own db_scale and an optional OPQ matrix, reference qinco_v1/model_qinco.py:185-201)."""
+    from . import codec
+    obj = _load_v1_object(path, allow_pickled_module)
+    if hasattr(obj, "state_dict") and getattr(obj, "_qb_v1_kind", "") == "PQ_QINCo":
+        subs = [codec.QINCoV1({k: _np(v) for k, v in q.state_dict().items()}, db_scale=float(getattr(q, "db_scale", 1.0)),
+                              device=device) for q in obj.sub_quantizers]
+        opq = getattr(obj, "opq_matrix", None)
+        return codec.PQQINCoV1(subs, opq_matrix=None if opq is None else _np(opq))
+    sd, scale = load_v1_checkpoint(path, allow_pickled_module)
+    return codec.QINCoV1(sd, db_scale=scale, device=device)
 
 
 # ---------------------------------------------------------------------------------------------- encoded databases (v2)

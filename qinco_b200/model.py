@@ -13,8 +13,6 @@ tables and distances and use fp16 only for the tensor-core operands.
 """
 from __future__ import annotations
 
-from types import SimpleNamespace
-
 import numpy as np
 import torch
 
@@ -64,6 +62,36 @@ def _to_numpy_state(sd) -> dict:
     return out
 
 
+class _Weight:
+    """`.weight` holder with the look of an nn.Embedding / nn.Linear: the tensor is put on the model's device on first use."""
+
+    def __init__(self, owner, key):
+        self._owner, self._key, self._t = owner, key, None
+
+    @property
+    def weight(self):
+        if self._t is None or self._t.device != self._owner.device:
+            self._t = torch.from_numpy(self._owner._weights[self._key]).to(self._owner.device)
+        return self._t
+
+
+class _StepView:
+    """What callers reach through `model.qinco_model.steps[m]`: the IVF search's re-ranking stage reads
+    `steps[0].ivf_centroids.weight` (reference qinco/search/search_tasks.py:449; modules of qinco_base.py:128-146,
+    :229-260).  Read-only views of the loaded state dict -- the kernels use their own packed copies."""
+
+    _NAMES = {"codebook": "codebook.weight", "ivf_centroids": "ivf_centroids.weight", "in_proj": "in_proj.weight",
+              "out_proj": "out_proj.weight"}
+
+    def __init__(self, owner, m):
+        for attr, key in self._NAMES.items():
+            if f"steps.{m}.{key}" in owner._weights:
+                setattr(self, attr, _Weight(owner, f"steps.{m}.{key}"))
+        if f"steps.{m}.substep.codebook.weight" in owner._weights:
+            self.substep = type("Substep", (), {})()
+            self.substep.codebook = _Weight(owner, f"steps.{m}.substep.codebook.weight")
+
+
 class QINCo:
     """B200 drop-in for the encode/decode surface of the reference model objects (see module docstring)."""
 
@@ -84,7 +112,7 @@ class QINCo:
         self._weights = None
         self._ws = None
         self.qinco_model = self            # callers reach through the wrapper for `.qinco_model.steps[0]`
-        self.steps = SimpleNamespace()
+        self.steps = []                    # filled by load_state_dict: one _StepView per quantisation step
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -128,6 +156,7 @@ class QINCo:
         w.setdefault("data_mean", np.zeros(self.D, np.float32))
         w.setdefault("data_std", np.array(1.0, np.float32))
         self._weights = w
+        self.steps = [_StepView(self, m) for m in range(self.M_ivf)]
         self.build()
 
     def _expected_keys(self):
@@ -242,33 +271,38 @@ class QINCo:
                                    ws.numel(), stream)
         return out
 
-    def _split_ivf(self, codes_MB):
-        """[M + 1, n] integer codes (row 0 = IVF code) -> (int32 [n], uint8 [n, M]) on the device."""
+    def _pack_codes(self, codes_MB):
+        """[M_ivf, n] integer codes (int64 / int32 / uint8, any strides; row 0 = IVF code for IVF models) ->
+        (uint8 [n, M], int32 [n] or None) with ONE library kernel: no torch reductions, no host sync.  Out-of-range codes
+        are flagged by that kernel and surface as IndexError from `synchronize()` (the reference's codebook lookup fails
+        the same asynchronous way on a GPU)."""
         if not isinstance(codes_MB, torch.Tensor):
             codes_MB = torch.as_tensor(np.asarray(codes_MB))
         if codes_MB.dim() != 2 or codes_MB.shape[0] != self.M_ivf:
-            raise AssertionError(f"codes must be [M_ivf={self.M_ivf}, n], got {tuple(codes_MB.shape)}")   # qinco_base.py:449
-        codes_MB = codes_MB.to(self.device)
-        ivf, rest = codes_MB[0], codes_MB[1:]
-        if ivf.numel() and (int(ivf.min()) < 0 or int(ivf.max()) >= self.ivf_K):
-            raise IndexError(f"IVF codes out of range [0, {self.ivf_K})")
-        if rest.numel() and (int(rest.min()) < 0 or int(rest.max()) >= self.K):
-            raise IndexError(f"codes out of range [0, {self.K})")
-        return ivf.to(torch.int32).contiguous(), rest.t().contiguous().to(torch.uint8)
+            raise AssertionError(f"codes must be [{self.M_ivf}, n], got {tuple(codes_MB.shape)}")          # qinco_base.py:449
+        if codes_MB.dtype not in (torch.int64, torch.int32, torch.uint8):
+            codes_MB = codes_MB.long()
+        if codes_MB.device != self.device:
+            codes_MB = codes_MB.to(self.device)
+        n = codes_MB.shape[1]
+        codes = torch.empty((n, self.M), dtype=torch.uint8, device=self.device)
+        ivf = torch.empty((n,), dtype=torch.int32, device=self.device) if self.ivf_K else None
+        if n:
+            with torch.cuda.device(self.device):
+                self._h.codes_pack(codes_MB.data_ptr(), codes_MB.element_size(), codes_MB.stride(0), codes_MB.stride(1), n,
+                                   codes.data_ptr(), ivf.data_ptr() if ivf is not None else None,
+                                   torch.cuda.current_stream().cuda_stream)
+        return codes, ivf
 
-    @staticmethod
-    def _join_ivf(ivf_i32, codes_u8):
-        return torch.cat([ivf_i32.long()[None, :], codes_u8.t().long()], dim=0).contiguous()
-
-    def _codes_to_u8(self, codes_MB):
-        if not isinstance(codes_MB, torch.Tensor):
-            codes_MB = torch.as_tensor(np.asarray(codes_MB))
-        if codes_MB.dim() != 2 or codes_MB.shape[0] != self.M:
-            raise AssertionError(f"codes must be [M={self.M}, n], got {tuple(codes_MB.shape)}")   # qinco_base.py:449
-        codes_MB = codes_MB.to(self.device)
-        if codes_MB.numel() and (int(codes_MB.min()) < 0 or int(codes_MB.max()) >= self.K):
-            raise IndexError(f"codes out of range [0, {self.K})")
-        return codes_MB.t().contiguous().to(torch.uint8)
+    def _unpack_codes(self, codes_u8, ivf_i32=None):
+        """(uint8 [n, M], int32 [n] or None) -> LongTensor [M_ivf, n], the reference's layout (qinco_base.py:480-485)."""
+        n = codes_u8.shape[0]
+        out = torch.empty((self.M_ivf, n), dtype=torch.int64, device=self.device)
+        if n:
+            with torch.cuda.device(self.device):
+                self._h.codes_unpack(codes_u8.data_ptr(), ivf_i32.data_ptr() if ivf_i32 is not None else None, n,
+                                     out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return out
 
     # ---- the reference surface ------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -276,16 +310,17 @@ class QINCo:
         """Normalised space: x [n, D] -> (codes LongTensor [M_ivf, n], xhat [n, D])   (qinco_base.py:454-485)."""
         if self.ivf_K:
             ivf, codes, xhat = self.encode_ivf_u8(x_target_BD, normalize=False, want_xhat=True)
-            return self._join_ivf(ivf, codes), xhat
+            return self._unpack_codes(codes, ivf), xhat
         codes, xhat = self.encode_u8(x_target_BD, normalize=False, want_xhat=True)
-        return codes.t().contiguous().long(), xhat
+        return self._unpack_codes(codes), xhat
 
     @torch.no_grad()
     def decode(self, codes_MB):
         """Normalised space: codes [M_ivf, n] (int64/int32/uint8) -> xhat [n, D] fp32   (qinco_base.py:447-452)."""
+        codes, ivf = self._pack_codes(codes_MB)
         if self.ivf_K:
-            return self.decode_ivf_u8(*self._split_ivf(codes_MB), denormalize=False)
-        return self.decode_u8(self._codes_to_u8(codes_MB), denormalize=False)
+            return self.decode_ivf_u8(ivf, codes, denormalize=False)
+        return self.decode_u8(codes, denormalize=False)
 
     @torch.no_grad()
     def forward(self, x_in, *args, step="train", **kwargs):
@@ -296,19 +331,26 @@ class QINCo:
         if step == "encode":                                                          # :532-534
             if self.ivf_K:
                 ivf, codes, _ = self.encode_ivf_u8(x_in, normalize=True, want_xhat=False)
-                return self._join_ivf(ivf, codes)
+                return self._unpack_codes(codes, ivf)
             codes, _ = self.encode_u8(x_in, normalize=True, want_xhat=False)
-            return codes.t().contiguous().long()
+            return self._unpack_codes(codes)
+        codes, ivf = self._pack_codes(x_in)                                           # :536-537
         if self.ivf_K:
-            return self.decode_ivf_u8(*self._split_ivf(x_in), denormalize=True)
-        return self.decode_u8(self._codes_to_u8(x_in), denormalize=True)              # :536-537
+            return self.decode_ivf_u8(ivf, codes, denormalize=True)
+        return self.decode_u8(codes, denormalize=True)
 
     __call__ = forward
 
     def synchronize(self):
-        """Wait for outstanding work and surface device-side failures."""
+        """Wait for outstanding work and surface device-side failures: out-of-range codes raise IndexError (what the
+        reference's codebook lookup raises), anything else the library's error."""
         torch.cuda.synchronize(self.device)
-        self._h.check()
+        try:
+            self._h.check()
+        except _lib.QbError as e:
+            if "err word 0x10 " in str(e) or "err word 0x20 " in str(e):
+                raise IndexError(f"codes out of range [0, {self.K})" + (f" or IVF codes out of range [0, {self.ivf_K})" if self.ivf_K else "")) from e
+            raise
 
     @property
     def launch_count(self):

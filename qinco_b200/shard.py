@@ -12,6 +12,28 @@ import torch
 import torch.distributed as dist
 
 
+def reference_shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Rows [start, end) of rank `rank` exactly as `encode_database` cuts them (search_tasks.py:103-104): floor(n / world)
+    rows per rank, the last rank also takes the remainder -- what the part files of task=encode must contain."""
+    per = n // world
+    return per * rank, (per * (rank + 1) if rank < world - 1 else n)
+
+
+def _model_has_ivf(model) -> bool:
+    """IVF-QINCo or not, for our model (`ivf_K`) and for anything with the reference's surface: the reference model
+    carries it in its cfg (`cfg.ivf_in_use`, qinco_base.py:428) and has NO `ivf_K` attribute of its own."""
+    if getattr(model, "ivf_K", 0):
+        return True
+    cfg = getattr(model, "cfg", None)
+    if cfg is None:
+        return False
+    get = cfg.get if isinstance(cfg, dict) else (lambda k, d=None: getattr(cfg, k, d))
+    try:
+        return bool(get("ivf_in_use", False)) or (isinstance(cfg, dict) and bool(cfg.get("ivf_K")))
+    except Exception:
+        return False
+
+
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     """Rows [start, end) of rank `rank`: contiguous, ceil(n / world) per rank, the tail ranks may get fewer or none."""
     per = -(-n // world) if world > 0 else n
@@ -35,8 +57,8 @@ def encode_sharded(model, x_local: torch.Tensor, n_total: int, batch: int = 1 <<
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     start, end = shard_range(n_total, rank, world)
     assert x_local.shape[0] == end - start, f"rank {rank}: expected {end - start} local rows, got {x_local.shape[0]}"
-    ivf = bool(getattr(model, "ivf_K", 0))
-    M = int(model.M)
+    ivf = _model_has_ivf(model)
+    M = None                      # uint8 code columns per vector (without the IVF code); known after the first batch
     parts = []
     for i0 in range(0, len(x_local), batch):
         xb = x_local[i0:i0 + batch]
@@ -45,12 +67,23 @@ def encode_sharded(model, x_local: torch.Tensor, n_total: int, batch: int = 1 <<
         elif hasattr(model, "encode_u8") and not ivf:
             iv, (codes, _) = None, model.encode_u8(xb, normalize=True, want_xhat=False)
         else:
-            c = model(xb, step="encode")                       # [M (+1), n] int64
+            c = model(xb, step="encode")                       # [M (+1), n] int64, row 0 = the IVF code of an IVF model
+            rest = c[1:] if ivf else c
+            # never truncate: a K > 256 model or an undetected IVF row must fail loudly, not wrap modulo 256
+            if rest.numel() and (int(rest.min()) < 0 or int(rest.max()) > 255):
+                raise ValueError("codes outside [0, 256): not a K <= 256 QINCo code matrix (is this an IVF model whose "
+                                 "cfg does not say ivf_in_use?)")
+            if ivf and c.shape[1] and (int(c[0].min()) < 0 or int(c[0].max()) >= 2 ** 31):
+                raise ValueError("IVF codes do not fit int32")
             iv = c[0].to(torch.int32).contiguous() if ivf else None
-            codes = (c[1:] if ivf else c).t().contiguous().to(torch.uint8)
+            codes = rest.t().contiguous().to(torch.uint8)
+        M = codes.shape[1] if M is None else M
+        assert codes.shape[1] == M
         if ivf:      # little-endian bytes of the int32 IVF code as columns M .. M+3
             codes = torch.cat([codes, iv.contiguous().view(torch.uint8).reshape(-1, 4)], dim=1)
         parts.append(codes)
+    if M is None:                 # no local rows: the width comes from the model (the reference's `model.M` is cfg._M_ivf,
+        M = int(model.M) - (1 if (ivf and not hasattr(model, "ivf_K")) else 0)     # i.e. it counts the IVF row)
     width = M + (4 if ivf else 0)
     local = torch.cat(parts) if parts else torch.empty((0, width), dtype=torch.uint8, device=x_local.device)
     if gather and world > 1:

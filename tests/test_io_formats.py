@@ -164,3 +164,59 @@ def test_cfg_normalisation_accepts_reference_style_objects():
     assert normalize_cfg(dict(D=128, M=8, K=256, L=2, de=128, dh=256, ivf_K=4096))["ivf_K"] == 4096
     with pytest.raises(ValueError):
         normalize_cfg(dict(M=8, K=256, L=2, dh=256))
+
+
+def test_v1_pickled_module_goes_through_the_restricted_unpickler(tmp_path):
+    """A pickled v1 nn.Module (what reference qinco_v1/codec_qinco.py:112 loads) is refused by default, read on request
+    without the reference on sys.path, and a pickle that names anything else is rejected."""
+    import pickle
+    import sys
+    import types
+    cfg = synth.make_cfg(None, D=16, M=3, K=32, L=2, de=16, dh=32, A=0, B=1, qinco1_mode=True)
+    w = synth.make_weights(cfg, seed=3, n_train=512, kmeans_iters=1)
+    v1 = synth.to_v1_state(cfg, w)
+    fake = types.ModuleType("model_qinco")                 # stands in for the reference's module while pickling
+
+    class QINCoStep(torch.nn.Module):
+        pass
+
+    class QINCo(torch.nn.Module):
+        pass
+
+    for cls in (QINCoStep, QINCo):
+        cls.__module__, cls.__qualname__ = "model_qinco", cls.__name__
+        setattr(fake, cls.__name__, cls)
+    sys.modules["model_qinco"] = fake
+    try:
+        model = QINCo()
+        model.codebook0 = torch.nn.Embedding(32, 16)
+        for m in range(1, 3):
+            step = QINCoStep()
+            step.codebook = torch.nn.Embedding(32, 16)
+            step.MLPconcat = torch.nn.Linear(32, 16)
+            for l in range(2):
+                step.add_module(f"residual_block{l}", torch.nn.Sequential(torch.nn.Linear(16, 32, bias=False), torch.nn.ReLU(),
+                                                                          torch.nn.Linear(32, 16, bias=False)))
+            model.add_module(f"step{m}", step)
+        model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in v1.items()})
+        model.db_scale = 3.25
+        path = str(tmp_path / "v1_module.pt")
+        torch.save(model, path)
+    finally:
+        del sys.modules["model_qinco"]
+    with pytest.raises(RuntimeError, match="allow_pickled_module"):
+        io.load_v1_checkpoint(path)
+    sd, scale = io.load_v1_checkpoint(path, allow_pickled_module=True)
+    assert scale == 3.25 and set(sd) == set(v1)
+    for k in v1:
+        np.testing.assert_array_equal(sd[k], v1[k])
+
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, ("echo pwned > /dev/null",))
+
+    bad = str(tmp_path / "evil.pt")
+    torch.save({"state_dict": Evil()}, bad)
+    with pytest.raises(pickle.UnpicklingError):
+        io.load_v1_checkpoint(bad, allow_pickled_module=True)
