@@ -125,21 +125,232 @@ def make_model_inputs(wl, n, rank):
     return cfg, w, x
 
 
-def cpu_port_rate(cfg, w, x_np, budget_s=12.0):
-    """Reference PyTorch-CPU encode (oracle/torch_port.py) on a bounded sample: (vec/s, sample size, codes, xhat, threads)."""
+def contract_sample(cfg):
+    """SURVEY.md section 8(d) "Parity subsets": the first 10 000 rows for the small models (S / QINCo1), 1 024 for QINCo2-L."""
+    return 1024 if cfg["de"] >= 384 else 10000
+
+
+def cpu_port_rate(cfg, w, x_np):
+    """Reference PyTorch-CPU encode + decode (oracle/torch_port.py) on the contract's parity sample:
+    (encode vec/s, sample size, codes, xhat, threads, port, decode vec/s)."""
     import torch
     from oracle.torch_port import TorchPort
     threads = os.cpu_count() or 1
     port = TorchPort(cfg, w, threads=threads)
-    probe = min(len(x_np), 256)
-    t0 = time.perf_counter()
-    port.encode(x_np[:probe])
-    rate0 = probe / (time.perf_counter() - t0)
-    n = int(min(len(x_np), max(256, min(8192, rate0 * budget_s)) // 64 * 64))
+    n = min(len(x_np), contract_sample(cfg))
+    port.encode(x_np[:min(n, 64)])                       # thread-pool / allocator warm-up
     t0 = time.perf_counter()
     codes, xhat = port.encode(x_np[:n])
     dt = time.perf_counter() - t0
-    return n / dt, n, codes.numpy(), xhat.numpy(), torch.get_num_threads(), port
+    t0 = time.perf_counter()
+    port.decode(codes)
+    dt_dec = time.perf_counter() - t0
+    return n / dt, n, codes.numpy(), xhat.numpy(), torch.get_num_threads(), port, n / dt_dec
+
+
+def parity_block(cfg, model, port, xs, ours, ref_codes, ref_xhat, dev):
+    """decode MSE vs the reference on ITS codes; encode MSE of OUR codes decoded with the reference arithmetic."""
+    import torch
+    dec_ours = model.decode(torch.from_numpy(ref_codes).to(dev)).cpu().numpy()
+    dec_ref = port.decode(ref_codes).numpy()
+    d_ref = ((xs - ref_xhat) ** 2).sum(1).astype(np.float64)
+    d_ours = ((xs - port.decode(ours).numpy()) ** 2).sum(1).astype(np.float64)
+    same = (ours == ref_codes).all(0)
+    delta = (d_ours - d_ref)[~same]
+    return {"sample": int(len(xs)),
+            "decode_rel_mse_vs_ref": float(((dec_ours - dec_ref) ** 2).sum() / (dec_ref ** 2).sum()),
+            "encode_mse_ref": float(d_ref.mean()), "encode_mse_ours": float(d_ours.mean()),
+            "encode_mse_rel_diff": float(abs(d_ours.mean() - d_ref.mean()) / d_ref.mean()),
+            "vectors_with_identical_codes": float(same.mean()),
+            "differing_vectors_mean_delta_over_mse": float(delta.mean() / d_ref.mean()) if len(delta) else 0.0,
+            "differing_vectors_sem_over_mse": float(delta.std(ddof=1) / np.sqrt(len(delta)) / d_ref.mean()) if len(delta) > 1 else 0.0}
+
+
+def decode_flops_per_vector(cfg):
+    """hoisted form, per vector: (M - 1) x (the MLP of one candidate + u = Wx . xhat)"""
+    D_, De_, Dh_, L_, M_ = cfg["D"], cfg["de"], cfg["dh"], cfg["L"], cfg["M"]
+    return 2 * (M_ - 1 + (1 if cfg.get("ivf_K") else 0)) * (2 * L_ * De_ * Dh_ + (D_ * De_ if De_ != D_ else 0) + D_ * De_)
+
+
+def timed_encode(model, x_dev, steps, warmup, local, sample_clocks=True):
+    """`warmup` untimed + `steps` timed encode passes over x_dev (resident): (ms total, kinds, launches, clocks, codes)."""
+    import torch
+    h = model._h
+    for _ in range(warmup):
+        model.encode_u8(x_dev, normalize=True, want_xhat=False)
+    torch.cuda.synchronize()
+    h.timing_read()
+    h.timing_enable(True)
+    l0 = h.launch_count
+    sampler = ClockSampler(local) if sample_clocks else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        codes, _ = model.encode_u8(x_dev, normalize=True, want_xhat=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    kinds = h.timing_read()
+    h.timing_enable(False)
+    return ms, kinds, h.launch_count - l0, clocks, codes
+
+
+def score_roofline(cfg, kinds, peaks):
+    ms_score, n_score, rows_score = kinds["mlp_score"]
+    fl = flops_min_per_candidate(cfg)
+    achieved = rows_score * fl / (ms_score * 1e-3) / 1e12 if ms_score > 0 else 0.0
+    return {"bound": "tensor", "kernel": "qb_mlp_kernel (score)", "achieved": achieved, "peak": peaks["tflops"],
+            "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "peak_source": peaks["source"], "launches": int(n_score),
+            "avg_launch_ms": ms_score / max(n_score, 1), "flops_per_row": fl, "rows_per_launch": rows_score / max(n_score, 1),
+            "kernel_share_of_step": ms_score / max(sum(v[0] for v in kinds.values()), 1e-9)}
+
+
+def block_beam16(args, local, dev):
+    """BASELINE config 3 (QINCo2-L 8x8, A=16, beam 16) beside the beam-1 headline: value, roofline, parity, clocks."""
+    import torch
+    from qinco_b200.model import QINCo
+    wl = WORKLOADS["c3"]
+    n = args.beam16_n
+    cfg, w, x_host = make_model_inputs(wl, n, 0)
+    model = QINCo(cfg, w, device=dev)
+    x_dev = x_host.to(dev)
+    k = 3
+    ms, kinds, launches, clocks, codes = timed_encode(model, x_dev, k, 1, local)
+    peaks = load_peaks()
+    out = {"workload": wl["name"], "vectors_per_step": n, "steps": k, "warmup": 1, "value": n * k / (ms * 1e-3), "unit": UNIT,
+           "ms_per_step": ms / k, "gpu_launches": int(launches), "flops_min_per_vector": encode_flops_min_per_vector(cfg),
+           "tflops_whole_step": n * k / (ms * 1e-3) * encode_flops_min_per_vector(cfg) / 1e12,
+           "roofline": score_roofline(cfg, kinds, peaks), "kernel_ms_per_step": {kk: v[0] / k for kk, v in kinds.items()},
+           "clocks": clocks}
+    if not args.no_cpu_baseline:
+        rate, n_s, ref_codes, ref_xhat, threads, port, dec_rate = cpu_port_rate(cfg, w, x_host[:contract_sample(cfg)].numpy())
+        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "decode_value": dec_rate,
+                               "sample": f"first {n_s} vectors, oracle/torch_port.py"}
+        ours = codes[:n_s].cpu().numpy().T.astype(np.int64)
+        out["parity"] = parity_block(cfg, model, port, x_host[:n_s].numpy(), ours, ref_codes, ref_xhat, dev)
+    model.synchronize()
+    model._h.close()
+    return out
+
+
+def block_torch_gpu(cfg, w, x_host, dev, n_sample):
+    """The reference's operator sequence run by PyTorch on THIS GPU (oracle/torch_port.py, device=cuda): fp32, and all-fp16
+    like the reference's own GPU wrapper (qinco_inference.py:303-317).  Timed with CUDA events after one warm-up pass."""
+    import torch
+    from oracle.torch_port import TorchPort
+    out = {"sample": f"first {n_sample} vectors of the workload, candidate rows processed in chunks of 2^22",
+           "what": "oracle/torch_port.py on cuda:0 (torch Linear/cat/bmm/topk launches per step, no hoisting)"}
+    xs = x_host[:n_sample]
+    for name, dt in (("fp32", torch.float32), ("fp16", torch.float16)):
+        try:
+            port = TorchPort(cfg, w, device=dev, dtype=dt)
+            port.encode(xs[:4096], max_rows=1 << 22)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            codes, xhat = port.encode(xs, max_rows=1 << 22)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            port.decode(codes)
+            d1.record()
+            torch.cuda.synchronize()
+            out[name] = {"value": n_sample / (ms * 1e-3), "unit": UNIT, "decode_value": n_sample / (d0.elapsed_time(d1) * 1e-3),
+                         "encode_mse": float(((xs.to(dev).float() - xhat.float()) ** 2).sum(1).mean().item())}
+            del port
+            torch.cuda.empty_cache()
+        except Exception as e:          # an out-of-memory torch path must not take the bench line down
+            out[name] = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
+    return out
+
+
+def block_c1(args, dev):
+    """BASELINE config 1: QINCo1 8x8 d=128, 10 000 vectors, encode AND decode, with the reference's own protocol
+    (compute_MSE, qinco_tasks.py:98-145: batches of 1024, a forced host read closing each timer; us per vector), on the host
+    cores (PyTorch-CPU port of the reference) and through the B200 path (same protocol, and codec.encode/decode bs=4096)."""
+    import io as _io
+    import torch
+    from oracle.torch_port import TorchPort
+    from qinco_b200 import codec, tasks
+    from qinco_b200.model import QINCo
+    wl = WORKLOADS["q1"]
+    n = args.c1_rows
+    cfg, w, x_host = make_model_inputs(wl, n, 0)
+    xs = x_host.numpy()
+    threads = os.cpu_count() or 1
+    port = TorchPort(cfg, w, threads=threads)
+    port.forward(xs[:64], "encode")
+    t_enc = t_dec = 0.0
+    codes_ref, dec_ref = [], []
+    for i0 in range(0, n, 1024):
+        b = xs[i0:i0 + 1024]
+        t0 = time.time()
+        c = port.forward(b, "encode")
+        _ = float(c[-1].reshape(-1)[-1])
+        t1 = time.time()
+        xh = port.forward(c, "decode")
+        _ = float(xh.reshape(-1)[-1])
+        t2 = time.time()
+        t_enc += t1 - t0
+        t_dec += t2 - t1
+        codes_ref.append(c.numpy())
+        dec_ref.append(xh.numpy())
+    codes_ref, dec_ref = np.concatenate(codes_ref, 1), np.concatenate(dec_ref)
+    out = {"workload": "QINCo1 8x8 K=256 d=128 L=16 beam=1, 10k synthetic fp32 vectors (BASELINE config 1)", "vectors": n,
+           "batch": 1024,
+           "cpu": {"kind": "port", "cores": torch.get_num_threads(), "encode_us_per_vector": t_enc / n * 1e6,
+                   "decode_us_per_vector": t_dec / n * 1e6, "encode_vectors_per_s": n / t_enc, "decode_vectors_per_s": n / t_dec,
+                   "mse": float(((xs - dec_ref) ** 2).sum(1).mean())}}
+    model = QINCo(cfg, w, device=dev)
+    res = tasks.compute_MSE(model, xs, 1024, dev, timed=False, out=lambda *a, **k: None)
+    out["b200_same_protocol"] = {"encode_us_per_vector": res["t_encode"] / n * 1e6, "decode_us_per_vector": res["t_decode"] / n * 1e6,
+                                 "encode_vectors_per_s": n / res["t_encode"], "decode_vectors_per_s": n / res["t_decode"],
+                                 "mse": res["MSE"], "api": "model(batch, step=...) per 1024-row batch with a host read (tasks.compute_MSE)"}
+    ours = model(x_host.to(dev), step="encode").cpu().numpy()
+    out["parity"] = parity_block(cfg, model, port, xs, ours, codes_ref, port.decode(codes_ref).numpy(), dev)
+    model.synchronize()
+    model._h.close()
+    v1 = codec.QINCoV1(cfg=cfg, weights=w, db_scale=1.0, device=dev)
+    codec.encode(v1, xs[:4096], bs=4096, verbose=False)
+    t0 = time.time()
+    c1 = codec.encode(v1, xs, bs=4096, verbose=False)
+    t1 = time.time()
+    y1 = codec.decode(v1, c1, bs=4096, verbose=False)
+    t2 = time.time()
+    out["b200_codec_qinco"] = {"encode_us_per_vector": (t1 - t0) / n * 1e6, "decode_us_per_vector": (t2 - t1) / n * 1e6,
+                               "mse": float(((xs - y1) ** 2).sum(1).mean()), "codes_equal_model_path": bool(np.array_equal(c1.T, ours)),
+                               "api": "codec.encode / codec.decode (numpy in, numpy out, bs=4096)"}
+    v1._m._h.close()
+    return out
+
+
+def block_small_batch(model, x_dev, dev):
+    """What every caller of the reference does: cfg.batch = 1024 rows per call, then a sync (search_tasks.py:107-116)."""
+    import torch
+    out = {}
+    for bs in (1024, 4096):
+        xb = x_dev[:bs].contiguous()
+        for _ in range(3):
+            c = model(xb, step="encode")
+            model(c, step="decode")
+        torch.cuda.synchronize()
+        k = 20
+        t0 = time.perf_counter()
+        for _ in range(k):
+            c = model(xb, step="encode")
+            _ = float(c[-1].reshape(-1)[-1].cpu())
+        t1 = time.perf_counter()
+        for _ in range(k):
+            y = model(c, step="decode")
+            _ = float(y.reshape(-1)[-1].cpu())
+        t2 = time.perf_counter()
+        out[str(bs)] = {"encode_vectors_per_s": bs * k / (t1 - t0), "encode_ms_per_call": (t1 - t0) / k * 1e3,
+                        "decode_vectors_per_s": bs * k / (t2 - t1), "decode_ms_per_call": (t2 - t1) / k * 1e3}
+    out["api"] = 'model(x, step="encode") / model(codes, step="decode") per call, each closed by a host read'
+    return out
 
 
 def run_reference(args, wl):
@@ -290,6 +501,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the beam16 / torch_gpu_baseline / c1 / small_batch blocks of the default line")
+    ap.add_argument("--beam16-n", type=int, default=100_000, help="vectors per step of the beam16 block (BASELINE config 3)")
+    ap.add_argument("--c1-rows", type=int, default=10_000, help="vectors of the config-1 block (QINCo1, CPU encode + decode)")
     ap.add_argument("--plan-opts", default="", help="kernel planner overrides, e.g. slot_bytes=8192,pair=1,hc=64,max_stage=4 (pair: 0 auto, 1 off, 2 on)")
     args = ap.parse_args()
     if args.workload == "c5pw":
@@ -327,8 +541,7 @@ def main():
     h = model._h
     x_pin = x_host.pin_memory()
     x_dev = x_pin.to(dev, non_blocking=True)
-    gathered = torch.empty((world * n, cfg["M"]), dtype=torch.uint8, device=dev) if world > 1 else None
-
+    from qinco_b200 import shard
     ivf = bool(cfg.get("ivf_K"))
     if ivf:      # the decode / e2e blocks below use the plain (non-IVF) entry points
         args.no_e2e = args.no_decode = True
@@ -336,12 +549,18 @@ def main():
     last_ivf = [None]
 
     def step():
+        """One pass: this rank's rows through the kernels and (N > 1) the ONE all-gather of the uint8 codes, both inside
+        qinco_b200.shard.encode_sharded -- the multi-GPU form of the reference's encode_database."""
+        if world > 1:
+            got = shard.encode_sharded(model, x_dev, world * n, batch=n)
+            codes_all = got[1] if ivf else got
+            if ivf:
+                last_ivf[0] = got[0][rank * n:(rank + 1) * n]
+            return codes_all[rank * n:(rank + 1) * n]
         if ivf:
             last_ivf[0], codes, _ = model.encode_ivf_u8(x_dev, normalize=True, want_xhat=False)
         else:
             codes, _ = model.encode_u8(x_dev, normalize=True, want_xhat=False)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, codes)
         return codes
 
     def barrier():
@@ -391,12 +610,20 @@ def main():
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         dec_ms = float(td.item()) / k_dec
-        D_, De_, Dh_, L_, M_ = cfg["D"], cfg["de"], cfg["dh"], cfg["L"], cfg["M"]
-        dec_flops = 2 * (M_ - 1) * (2 * L_ * De_ * Dh_ + (D_ * De_ if De_ != D_ else 0) + D_ * De_)   # hoisted form, per vector
+        D_, M_ = cfg["D"], cfg["M"]
+        dec_flops = decode_flops_per_vector(cfg)
+        dec_tflops = n / (dec_ms * 1e-3) * dec_flops / 1e12
+        pk = load_peaks()
         dec = {"value": world * n / (dec_ms * 1e-3), "unit": "vectors/s decoded", "ms_per_pass": dec_ms, "passes": k_dec,
-               "tflops": n / (dec_ms * 1e-3) * dec_flops / 1e12, "flops_per_vector": dec_flops,
-               "hbm_gbs_algorithmic": n / (dec_ms * 1e-3) * (4 * D_ + M_) / 1e9,
+               "tflops": dec_tflops, "flops_per_vector": dec_flops,
+               "roofline": {"bound": "tensor", "kernel": "qb_mlp_kernel (decode)", "achieved": dec_tflops, "peak": pk["tflops"],
+                            "unit": "TFLOP/s", "frac": dec_tflops / pk["tflops"], "peak_source": pk["source"],
+                            "hbm_gbs_algorithmic": n / (dec_ms * 1e-3) * (4 * D_ + M_) / 1e9},
+               "gpu_launches_per_pass": None,
                "mse_vs_input": float(((xdec[: min(n, 65536)] - x_dev[: min(n, 65536)]) ** 2).sum(1).mean().item())}
+        l0 = h.launch_count
+        model.decode_u8(codes, denormalize=True)
+        dec["gpu_launches_per_pass"] = int(h.launch_count - l0)
 
     # ---- end to end: pinned host buffers through the C-ABI host call (H2D + encode + D2H inside the timed region)
     e2e = None
@@ -409,6 +636,7 @@ def main():
         for _ in range(k_e2e):
             codes_host, _ = h.encode_host(x_np, normalize=True)
             if world > 1:
+                gathered = torch.empty((world * n, cfg["M"]), dtype=torch.uint8, device=dev)
                 dist.all_gather_into_tensor(gathered, torch.from_numpy(codes_host).to(dev))
         barrier()
         dt = time.perf_counter() - t0
@@ -422,28 +650,21 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
-        ms_score, n_score, rows_score = kinds["mlp_score"]
-        fl_launch = flops_min_per_candidate(cfg)
-        achieved = rows_score * fl_launch / (ms_score * 1e-3) / 1e12 if ms_score > 0 else 0.0
         step_ms = {k: v[0] / args.steps for k, v in kinds.items()}
-        traffic = traffic_of(args.workload)
+        roof = score_roofline(cfg, kinds, peaks)
+        roof["traffic"] = traffic_of(args.workload)
+        roof["hbm_gbs_algorithmic"] = value / world * (4 * cfg["D"] + cfg["M"]) / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands, f32 accumulate/residual/distances", "data": "synthetic",
             "config": {"workload": wl["name"], "vectors_per_gpu_per_step": n, "global_vectors_per_step": world * n,
-                       "sharding": f"rows over {world} rank(s), one NCCL all-gather of uint8 codes per step",
+                       "sharding": f"rows over {world} rank(s), one NCCL all-gather of uint8 codes per step (shard.encode_sharded)",
                        "l2": f"inputs larger than L2 ({n * cfg['D'] * 4 / 2**20:.0f} MiB of vectors per step)"},
             "gpu_launches": int(launches),
             "flops_min_per_vector": encode_flops_min_per_vector(cfg),
             "tflops_whole_step": value / world * encode_flops_min_per_vector(cfg) / 1e12,
-            "roofline": {"bound": "tensor", "kernel": "qb_mlp_kernel (score)", "achieved": achieved, "peak": peaks["tflops"],
-                         "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
-                         "peak_source": peaks["source"], "launches": int(n_score),
-                         "avg_launch_ms": ms_score / max(n_score, 1),
-                         "flops_per_row": fl_launch, "rows_per_launch": rows_score / max(n_score, 1),
-                         "kernel_share_of_step": ms_score / max(sum(v[0] for v in kinds.values()), 1e-9),
-                         "hbm_gbs_algorithmic": value / world * (4 * cfg["D"] + cfg["M"]) / 1e9},
+            "roofline": roof,
             "kernel_ms_per_step": step_ms,
             "clocks": clocks,
         }
@@ -452,25 +673,28 @@ def main():
         if dec:
             out["decode"] = dec
         if world == 1 and not args.no_cpu_baseline:
-            ns = min(n, 8192)
-            rate, n_s, ref_codes, ref_xhat, threads, port = cpu_port_rate(cfg, w, x_host[:ns].numpy())
+            ns = min(n, contract_sample(cfg))
+            rate, n_s, ref_codes, ref_xhat, threads, port, dec_rate = cpu_port_rate(cfg, w, x_host[:ns].numpy())
             out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                   "sample": f"first {n_s} vectors of the workload, oracle/torch_port.py (reference op "
-                                             f"sequence in PyTorch CPU fp32), os.cpu_count()={os.cpu_count()}"}
+                                   "decode": {"value": dec_rate, "unit": "vectors/s decoded"},
+                                   "sample": f"first {n_s} vectors of the workload (the contract's parity sample, SURVEY 8d), "
+                                             f"oracle/torch_port.py (reference op sequence in PyTorch CPU fp32), "
+                                             f"os.cpu_count()={os.cpu_count()}"}
             # parity on the same sample (decode MSE vs ref; encode MSE of our codes decoded by the reference arithmetic)
-            xs = x_host[:n_s].numpy()
             ours = codes[:n_s].cpu().numpy().T.astype(np.int64)
             if ivf:      # the reference's code matrix has the IVF code as row 0
                 ours = np.concatenate([last_ivf[0][:n_s].cpu().numpy().astype(np.int64)[None, :], ours])
-            dec_ours = model.decode(torch.from_numpy(ref_codes).to(dev)).cpu().numpy()
-            dec_ref = port.decode(ref_codes).numpy()
-            mse_ref = float(((xs - ref_xhat) ** 2).sum(1).mean())
-            mse_ours = float(((xs - port.decode(ours).numpy()) ** 2).sum(1).mean())
-            out["parity"] = {"sample": n_s,
-                             "decode_rel_mse_vs_ref": float(((dec_ours - dec_ref) ** 2).sum() / (dec_ref ** 2).sum()),
-                             "encode_mse_ref": mse_ref, "encode_mse_ours": mse_ours,
-                             "encode_mse_rel_diff": abs(mse_ours - mse_ref) / mse_ref,
-                             "vectors_with_identical_codes": float((ours == ref_codes).all(0).mean())}
+            out["parity"] = parity_block(cfg, model, port, x_host[:n_s].numpy(), ours, ref_codes, ref_xhat, dev)
+        if world == 1 and not args.no_extras and args.workload == "c2":
+            out["small_batch"] = block_small_batch(model, x_dev, dev)
+            model.synchronize()
+            model._h.close()
+            del x_dev
+            torch.cuda.empty_cache()
+            out["torch_gpu_baseline"] = block_torch_gpu(cfg, w, x_host, dev, min(n, 65536))
+            out["beam16"] = block_beam16(args, local, dev)
+            if not args.no_cpu_baseline:
+                out["c1"] = block_c1(args, dev)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

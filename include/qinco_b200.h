@@ -148,6 +148,10 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
                    int n_plan_out, void* ops_out, int max_ops);
 int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int32_t* opts5, const float* const* up,
                  const float* const* down, const float* out_proj, uint16_t* blob, int64_t blob_halfs);
+/* ... and the slabs of the decode loop's pre-ops (u = Wx . xhat as fp16 hi/lo MMAs; opts5[3] bit 10 selects that plan);
+ * wx = Wcat[:, De:] as [De][D] rows. */
+int qb_plan_pack_pre(int D, int De, int Dh, int L, int K, int qinco1_mode, const int32_t* opts5, const float* wx, uint16_t* blob,
+                     int64_t blob_halfs);
 int qb_plan_tables(int D, int De, int K, const float* codebook, const float* in_proj, const float* concat_w,
                    const float* concat_b, float* t_blk, float* cb_blk, float* wx_t);
 

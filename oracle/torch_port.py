@@ -11,6 +11,11 @@ any hoisting, `cat` for QConcat, the |a|^2+|b|^2-2ab distance via bmm, topk, gat
   distances       qinco/utils.py:336-346, 377-383
   encode / decode qinco_base.py:447-485;  qinco_inference.py:66-75, 239-254
 It is pinned to the reference by tests/test_oracle_golden.py (identical codes on every committed fixture).
+
+`device="cuda"` runs the SAME operator sequence through PyTorch on the GPU -- the "just run the reference on this box"
+anchor of BASELINE.md section 3 -- in fp32, or with `dtype=torch.float16` in the numerics of the reference's own GPU
+wrapper, which casts the whole model and the input to half (qinco_inference.py:303-317, 343).  bench.py reports it as
+`torch_gpu_baseline`; it is never part of the product path.
 """
 from __future__ import annotations
 
@@ -20,13 +25,14 @@ import torch.nn.functional as F
 
 
 class TorchPort:
-    def __init__(self, cfg: dict, weights: dict, threads: int | None = None):
+    def __init__(self, cfg: dict, weights: dict, threads: int | None = None, device="cpu", dtype=torch.float32):
         self.cfg = cfg
         if threads:
             torch.set_num_threads(threads)
-        self.w = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)) for k, v in weights.items()}
-        self.mean = self.w.get("data_mean", torch.zeros(cfg["D"]))
-        self.std = self.w.get("data_std", torch.tensor(1.0))
+        self.device, self.dtype = torch.device(device), dtype
+        self.w = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(self.device, dtype) for k, v in weights.items()}
+        self.mean = self.w.get("data_mean", torch.zeros(cfg["D"], device=self.device, dtype=dtype))
+        self.std = self.w.get("data_std", torch.tensor(1.0, device=self.device, dtype=dtype))
 
     # f_m(c, xhat): rows [..., D]
     def step_mlp(self, m, c, xhat):
@@ -51,7 +57,7 @@ class TorchPort:
 
     @torch.no_grad()
     def decode(self, codes_MB):
-        codes_MB = torch.as_tensor(codes_MB).long()
+        codes_MB = torch.as_tensor(codes_MB).long().to(self.device)
         ivf = bool(self.cfg.get("ivf_K"))                # IVFBook.decode (qinco_base.py:176-183): centroid lookup
         xhat = self.w["steps.0.ivf_centroids.weight" if ivf else "steps.0.codebook.weight"][codes_MB[0]].clone()
         for m in range(1, self.cfg["M"] + (1 if ivf else 0)):
@@ -62,7 +68,7 @@ class TorchPort:
     def encode(self, x, max_rows=65536):
         cfg = self.cfg
         K, D, M, A, B = cfg["K"], cfg["D"], cfg["M"], cfg["A"], cfg["B"]
-        x = torch.as_tensor(x, dtype=torch.float32)
+        x = torch.as_tensor(x).to(self.device, self.dtype)
         bs = max(1, max_rows // (B * (A or 1)))          # qinco_base.py:456-472 (enc_max_bs // (B * max(A,1)))
         if len(x) > bs:
             parts = [self.encode(x[i:i + bs], max_rows) for i in range(0, len(x), bs)]
@@ -105,5 +111,5 @@ class TorchPort:
 
     def forward(self, x_in, step):
         if step == "encode":
-            return self.encode((torch.as_tensor(x_in, dtype=torch.float32) - self.mean) / self.std)[0]
+            return self.encode((torch.as_tensor(x_in).to(self.device, self.dtype) - self.mean) / self.std)[0]
         return self.decode(x_in) * self.std + self.mean

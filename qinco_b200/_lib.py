@@ -21,7 +21,7 @@ STATUS = {0: "QB_OK", -1: "QB_ERR_INVALID", -2: "QB_ERR_CUDA", -3: "QB_ERR_WORKS
 # every symbol include/qinco_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ["qb_version", "qb_last_error", "qb_model_create", "qb_model_destroy", "qb_encode_workspace_bytes",
            "qb_decode_workspace_bytes", "qb_encode", "qb_decode", "qb_encode_host", "qb_decode_host", "qb_check",
-           "qb_launch_count", "qb_timing_enable", "qb_timing_read", "qb_model_info", "qb_debug_step", "qb_plan_export", "qb_plan_pack", "qb_plan_tables",
+           "qb_launch_count", "qb_timing_enable", "qb_timing_read", "qb_model_info", "qb_debug_step", "qb_plan_export", "qb_plan_pack", "qb_plan_pack_pre", "qb_plan_tables",
            "qb_pairwise_create", "qb_pairwise_destroy", "qb_pairwise_decode", "qb_pairwise_check", "qb_pairwise_launch_count",
            "qb_pairwise_last_error", "qb_encode_ivf", "qb_decode_ivf", "qb_encode_ivf_host", "qb_decode_ivf_host", "qb_codes_pack", "qb_codes_unpack"]
 
@@ -134,7 +134,7 @@ class _PtrArray:
 
 INFO_FIELDS = ["D", "De", "Dh", "L", "K", "has_proj", "skip", "n_ops_block", "n_ops_out", "hc", "n_hchunk", "n_tiles",
                "oc", "n_ochunk", "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes", "n_sm",
-               "default_chunk", "pair"]
+               "default_chunk", "pair", "decode_loop", "loop_n_stage", "loop_smem_total"]
 
 
 class Handle:

@@ -57,6 +57,9 @@ struct StepDev {
     float* wx = nullptr;         // [De][D] = Wcat[:, De:]
     float* sub_cb = nullptr;     // [K][D] pre-selection codebook (A > 0)
     float* sub_norm = nullptr;   // [K] squared row norms of sub_cb
+    // decode loop (one launch walks every step): the same weight blob, extended by the pre-op slabs (u = Wx . xhat)
+    QbStepPlan loop_plan;
+    std::vector<QbOp> loop_ops;
 };
 
 struct HostSlot {
@@ -89,6 +92,7 @@ struct qb_model {
     float* cb0_norm = nullptr; // [K] squared row norms of cb0
     float* mean = nullptr;     // [D]
     std::vector<StepDev> steps;   // index m, entry 0 unused
+    bool loop_ok = false;         // every step has a decode-loop plan (qb_mlp_kernel<.., kLoop>): decode is ONE launch
     uint32_t* err_host = nullptr;   // mapped pinned word written by the kernels before they trap
     uint32_t* err_dev = nullptr;
     int64_t launches = 0;
@@ -330,6 +334,30 @@ int decode_chunk(qb_model* m, const int32_t* ivf_codes, const uint8_t* codes, in
     const bool affine = denormalize && (scale != 1.f || shift);
     int cur = 0;
     const int S = m->S;
+    if (m->loop_ok && S > 1) {
+        // ONE launch: every 128-vector tile walks all S - 1 implicit-codebook steps (qb_mlp_kernel<.., kLoop>), codes read
+        // in the kernel, u = Wx . xhat on the tensor core, the running xhat kept by the rows' own threads in `out`.
+        const StepDev& s1 = m->steps[1];
+        qb::MlpParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.plan = s1.loop_plan;
+        p.n_ops = (int32_t)s1.loop_ops.size();
+        std::memcpy(p.ops, s1.loop_ops.data(), s1.loop_ops.size() * sizeof(QbOp));
+        p.w_blob = s1.w_blob; p.t_blk = s1.t_blk; p.cb_blk = s1.cb_blk;
+        p.err_flag = m->err_dev;
+        p.mode = qb::QB_MODE_APPLY;
+        p.F_in = 1; p.F_out = 1; p.n_rows = n;
+        p.sel_code = codes; p.code_stride = M; p.code_off = m->ivf_K ? 0 : 1;
+        p.xhat_out = out;
+        p.out_scale = scale; p.out_shift = shift;
+        p.n_loop_steps = S - 1;
+        for (int step = 1; step < S; step++)
+            p.loop_steps[step - 1] = qb::QbLoopStep{m->steps[step].w_blob, m->steps[step].t_blk, m->steps[step].cb_blk};
+        if (m->ivf_K) { p.seed_tab = m->ivf_cent; p.seed_K = m->ivf_K; p.seed_codes_i32 = ivf_codes; }
+        else { p.seed_tab = m->cb0; p.seed_K = m->K; }
+        QB_CUDA(timed_launch(m, KIND_APPLY, n * (S - 1), st, [&] { return qb::launch_mlp(p, m->n_sm, st); }));
+        return QB_OK;
+    }
     if (m->ivf_K)
         QB_CUDA(timed_launch(m, KIND_OTHER, n, st, [&] {
             return qb::launch_ivf_lookup(m->ivf_cent, ivf_codes, n, D, m->ivf_K, xh[cur], m->err_dev, st);
@@ -485,8 +513,24 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         std::vector<QbOp> ops;
         std::string err;
         if (qb::make_step_plan(D, De, m->Dh, m->L, K, m->q1, opt, &sd.plan, &ops, &err)) return bail(fail(QB_ERR_INVALID, err));
-        std::vector<uint16_t> blob((size_t)(sd.plan.w_blob_bytes + 1) / 2, 0);
-        if (qb::pack_step_weights(sd.plan, ops, d->up_w ? d->up_w + (size_t)s * m->L : nullptr,
+        // Decode-loop plan: same slab geometry (slot size, H chunk), plus the pre-ops; usable when its block / out_proj
+        // ops are exactly the plain plan's, so both kernels read ONE weight blob.
+        bool loop = !sd.plan.pair && !getenv("QB_NO_DECODE_LOOP");
+        std::vector<QbOp> lops;
+        if (loop) {
+            qb::PlanOptions lo = opt;
+            lo.uop = 1; lo.pair = 1; lo.hc = sd.plan.hc; lo.slot_bytes = sd.plan.slot_bytes;
+            std::string lerr;
+            loop = qb::make_step_plan(D, De, m->Dh, m->L, K, m->q1, lo, &sd.loop_plan, &lops, &lerr) == 0 &&
+                   sd.loop_plan.n_ops_block == sd.plan.n_ops_block && sd.loop_plan.n_ops_out == sd.plan.n_ops_out &&
+                   sd.loop_plan.block_w_bytes == sd.plan.block_w_bytes && lops.size() >= ops.size() &&
+                   std::memcmp(lops.data(), ops.data(), ops.size() * sizeof(QbOp)) == 0;
+        }
+        m->loop_ok = (s == 1) ? loop : (m->loop_ok && loop);
+        const QbStepPlan& pack_plan = loop ? sd.loop_plan : sd.plan;
+        const std::vector<QbOp>& pack_ops = loop ? lops : ops;
+        std::vector<uint16_t> blob((size_t)(pack_plan.w_blob_bytes + 1) / 2, 0);
+        if (qb::pack_step_weights(pack_plan, pack_ops, d->up_w ? d->up_w + (size_t)s * m->L : nullptr,
                                   d->down_w ? d->down_w + (size_t)s * m->L : nullptr,
                                   De != D ? d->out_proj[s] : nullptr, blob.data(), &err))
             return bail(fail(QB_ERR_INVALID, err));
@@ -494,7 +538,8 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         qb::build_tables(D, De, K, d->codebook[s], De != D ? d->in_proj[s] : nullptr, d->concat_w[s], d->concat_b[s],
                          t_blk.data(), cb_blk.data(), wx_t.data());
         sd.ops = ops;
-        if ((rc = dev_upload(m, (const uint8_t*)blob.data(), blob.size() * 2, &sd.w_blob))) return bail(rc);
+        sd.loop_ops = lops;
+        if (loop) max_smem = std::max(max_smem, sd.loop_plan.smem_total);
         if ((rc = dev_upload(m, t_blk.data(), t_blk.size(), &sd.t_blk))) return bail(rc);
         if ((rc = dev_upload(m, cb_blk.data(), cb_blk.size(), &sd.cb_blk))) return bail(rc);
         {   // Wx = Wcat[:, De:] as [De][D] rows (build_tables hands back its transpose)
@@ -502,7 +547,9 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
             for (int e = 0; e < De; e++)
                 for (int dd = 0; dd < D; dd++) wx[(size_t)e * D + dd] = wx_t[(size_t)dd * De + e];
             if ((rc = dev_upload(m, wx.data(), wx.size(), &sd.wx))) return bail(rc);
+            if (loop && qb::pack_pre_weights(sd.loop_plan, lops, wx.data(), blob.data(), &err)) return bail(fail(QB_ERR_INVALID, err));
         }
+        if ((rc = dev_upload(m, (const uint8_t*)blob.data(), blob.size() * 2, &sd.w_blob))) return bail(rc);
         if (m->A > 0) {
             std::vector<float> nrm((size_t)K);
             for (int k = 0; k < K; k++) nrm[k] = row_norm2(d->substep_codebook[s] + (size_t)k * D, D);
@@ -829,7 +876,8 @@ int qb_model_info(const qb_model* m, int step, int32_t* out, int n_out) {
     const QbStepPlan& p = m->steps[step].plan;
     const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk,
                          p.n_tiles, p.oc, p.n_ochunk, p.slot_bytes, p.n_stage, p.smem_total, (int32_t)p.block_w_bytes,
-                         (int32_t)p.w_blob_bytes, m->n_sm, (int32_t)default_chunk(m), p.pair};
+                         (int32_t)p.w_blob_bytes, m->n_sm, (int32_t)default_chunk(m), p.pair, m->loop_ok ? 1 : 0,
+                         m->loop_ok ? m->steps[step].loop_plan.n_stage : 0, m->loop_ok ? m->steps[step].loop_plan.smem_total : 0};
     const int nv = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < n_out && i < nv; i++) out[i] = v[i];
     return nv;

@@ -33,6 +33,13 @@ enum { QB_TRACE_EVENTS = 2048 };
 //   apply: row -> vector v = row / F_out, b = v*F_in + parent[row], code = sel_code[row*code_stride + code_off];
 //          xhat_out[row] = (xhat_in[b] + f_m(C_m[code], xhat_in[b])) * out_scale + out_shift   (qinco_base.py:363-369,
 //          decode :282-290, :447-452)
+// per-step tables of the decode loop (one tile walks all steps inside one launch)
+struct QbLoopStep {
+    const uint8_t* w_blob;
+    const float* t_blk;
+    const float* cb_blk;
+};
+
 struct MlpParams {
     QbStepPlan plan;
     QbOp ops[QB_MAX_OPS];     // the plan's op list; lives in the kernel-parameter constant bank so the MMA / producer
@@ -57,6 +64,16 @@ struct MlpParams {
     float* xhat_out;          // apply: [n_rows, D]
     float out_scale;          // apply
     const float* out_shift;   // apply: [D] or NULL
+    // Decode loop (n_loop_steps > 0, apply mode, F_in = F_out = 1; reference QINCoInferenceDecoder.forward,
+    // qinco_inference.py:66-75): row i starts at seed_tab[seed code] (C_0[codes[i][0]], or the IVF centroid of
+    // seed_codes_i32[i]) and walks loop step s = 0 .. n_loop_steps-1 with code sel_code[i*code_stride + code_off + s];
+    // xhat_out [n_rows, D] holds the running reconstruction between steps (each thread re-reads only what it wrote) and
+    // the result (scaled / shifted at the last step).  plan.n_ops_pre > 0 is required.
+    int32_t n_loop_steps;
+    int32_t seed_K;
+    const float* seed_tab;          // [seed_K][D] row-major
+    const int32_t* seed_codes_i32;  // IVF codes [n_rows], or NULL: the seed code is sel_code[i*code_stride]
+    QbLoopStep loop_steps[QB_MAX_LOOP_STEPS];
     uint32_t* err_flag;       // device word set non-zero when a barrier wait timed out
     unsigned long long* trace;   // debug: per-role event log of CTA 0 ([3][QB_TRACE_EVENTS] of clock<<16 | id), or NULL
 };

@@ -19,6 +19,8 @@ struct PlanOptions {
     int max_stage = 0;    // cap on ring depth (0 = QB_MAX_STAGE)
     int max_slab_k = 0;   // cap on slab K (0 = what fits a slot)
     int smem_budget = 0;  // bytes of dynamic shared memory the kernel may use (0 = 208 KiB)
+    int uop = 0;          // 1: decode-loop plan: pre-ops computing u = Wx . xhat on the tensor core (fp16 hi/lo split), A_E
+                          // buffer sized for [xhat_hi | xhat_lo], no resident tables
 };
 
 uint16_t f32_to_f16(float f);
@@ -29,6 +31,9 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
 
 int pack_step_weights(const QbStepPlan& plan, const std::vector<QbOp>& ops, const float* const* up,
                       const float* const* down, const float* out_proj, uint16_t* blob, std::string* err);
+
+// slabs of the pre-ops (decode-loop plans): wx is Wcat[:, De:] as [De][D] rows
+int pack_pre_weights(const QbStepPlan& plan, const std::vector<QbOp>& ops, const float* wx, uint16_t* blob, std::string* err);
 
 void build_tables(int D, int De, int K, const float* codebook, const float* in_proj, const float* concat_w,
                   const float* concat_b, float* t_blk, float* cb_blk, float* wx_t);

@@ -414,8 +414,9 @@ struct Tracer {
 
 }  // namespace
 
-template <bool kScore, bool kResident, bool kPair>
+template <bool kScore, bool kResident, bool kPair, bool kLoop = false>
 __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_constant__ MlpParams p) {
+    static_assert(!kLoop || (!kScore && !kResident && !kPair), "the decode loop is an apply-mode, single-CTA variant");
     extern __shared__ __align__(1024) uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t bars[2][QB_BAR_COUNT];     // one barrier set per tile slot
     __shared__ __align__(8) uint64_t w_full[QB_MAX_STAGE];
@@ -431,6 +432,15 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     const QbStepPlan& pl = p.plan;
     const int n_ops = pl.n_ops_block + pl.n_ops_out;
     const int NT = pl.n_tiles;
+    // One tile set walks `n_ls` steps (1 outside the decode loop); a step is the phases  -1: pre-ops (decode loop only:
+    // u = Wx . xhat), 0 .. L-1: residual blocks (one shared op list), L: out_proj ops.
+    const int n_ls = kLoop ? p.n_loop_steps : 1;
+    constexpr int kFirstPhase = kLoop ? -1 : 0;
+    auto phase_ops = [&](int ph, int& i0, int& i1, size_t& w_rel) {
+        if (ph < 0) { i0 = n_ops; i1 = n_ops + pl.n_ops_pre; w_rel = 0; }
+        else if (ph < pl.L) { i0 = 0; i1 = pl.n_ops_block; w_rel = (size_t)ph * (size_t)pl.block_w_bytes; }
+        else { i0 = pl.n_ops_block; i1 = n_ops; w_rel = 0; }
+    };
     const int64_t n_tiles = (p.n_rows + QB_TILE_M - 1) / QB_TILE_M;
     // Work units ("sets" of NT tiles).  Default: NT consecutive tiles, sets strided over the CTAs.  Resident mode (score,
     // all 256 codes per beam): CTA index % 4 picks a code quarter hq; a tile is that quarter (64 codes) of TWO consecutive
@@ -536,10 +546,12 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         if (kResident) push_rows(set_first, 0);
         for (int64_t set = set_first; more_sets(set); set += set_stride, kset++) {
             if (kResident) push_rows(set + set_stride, kset + 1);
-            for (int l = 0; l <= pl.L; l++) {
-                const int i0 = (l < pl.L) ? 0 : pl.n_ops_block;
-                const int i1 = (l < pl.L) ? pl.n_ops_block : n_ops;
-                const uint8_t* wbase = p.w_blob + ((l < pl.L) ? (size_t)l * (size_t)pl.block_w_bytes : 0);
+            for (int ls = 0; ls < n_ls; ls++)
+            for (int l = kFirstPhase; l <= pl.L; l++) {
+                int i0, i1;
+                size_t w_rel;
+                phase_ops(l, i0, i1, w_rel);
+                const uint8_t* wbase = (kLoop ? p.loop_steps[ls].w_blob : p.w_blob) + w_rel;
                 for (int i = i0; i < i1; i++) {
                     const QbOp& op = p.ops[i];
                     const uint32_t n_slab = op.n_slab, slab_bytes = op.slab_bytes, last_bytes = op.last_bytes;
@@ -598,9 +610,11 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             const uint32_t tcol = tmem_base + (uint32_t)t * tile_cols;
             const uint32_t ae_lo = ((smem_base + pl.smem_ae[t]) >> 4) & 0x3FFFu;
             for (int64_t set = set_first; more_sets(set); set += set_stride) {
-                for (int l = 0; l <= pl.L; l++) {
-                    const int i0 = (l < pl.L) ? 0 : pl.n_ops_block;
-                    const int i1 = (l < pl.L) ? pl.n_ops_block : n_ops;
+                for (int ls = 0; ls < n_ls; ls++)
+                for (int l = kFirstPhase; l <= pl.L; l++) {
+                    int i0, i1;
+                    size_t w_rel_unused;
+                    phase_ops(l, i0, i1, w_rel_unused);
                     for (int i = i0; i < i1; i++) {
                         const QbOp& op = p.ops[i];          // kernel-parameter bank -> uniform registers
                         const uint32_t n = op.n;
@@ -704,6 +718,213 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             for (int i = 0; i < 16; i++)
                 treg[i] = (e0c + 4 * i < e1c) ? ldg4(tsrc + (size_t)i * K * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        if constexpr (kLoop) {
+            // ============================================================================ decode loop (one launch, all steps)
+            // A tile of 128 vectors walks every quantisation step here; its running reconstruction xhat never leaves the
+            // rows' owner threads: each thread keeps its column range of xhat in xhat_out (re-read by the same thread one
+            // step later, an L1/L2 hit) and hands the NEXT step's MMA operand [xhat_hi | xhat_lo] (fp16 hi/lo split) to the
+            // tensor core through the A_E buffer, where the pre-ops add u = Wx . xhat onto Eacc = T_m[code].
+            uint32_t parl0 = 0, parl1 = 0;
+            auto wait_l = [&](int t, int bar, uint32_t code) {
+                uint32_t& par = t ? parl1 : parl0;
+                mbar_wait(bar_addr(t, bar), (par >> bar) & 1, p.err_flag, code);
+                par ^= 1u << bar;
+                tc_fence_after();
+            };
+            const uint32_t x_lo_chunk = (uint32_t)(D >> 3);        // k-chunk of the first xhat_lo column
+            // n (16 or 32) columns of xhat starting at column c: fp16 hi / lo parts -> A operand k-chunks of tile slot t
+            auto put_operand = [&](int t, int c, int n, const float (&x)[32]) {
+                const uint32_t dst = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (8 * j < n) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const float a = x[8 * j + 2 * k], b = x[8 * j + 2 * k + 1];
+                            const __half2 h = __floats2half2_rn(a, b);
+                            const float2 hf = __half22float2(h);
+                            hi[k] = *reinterpret_cast<const uint32_t*>(&h);
+                            lo[k] = pack_h2(a - hf.x, b - hf.y);
+                        }
+                        st_shared_v4(dst + ((uint32_t)(c >> 3) + j) * kAkcBytes, hi[0], hi[1], hi[2], hi[3]);
+                        st_shared_v4(dst + (x_lo_chunk + (uint32_t)(c >> 3) + j) * kAkcBytes, lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            };
+            // seed: xhat = seed_tab[code0] (C_0[code] or the IVF centroid) over this thread's columns
+            auto seed_tile = [&](int t, int64_t row, bool valid) {
+                int c0 = 0;
+                if (valid) {
+                    if (p.seed_codes_i32) {
+                        c0 = __ldg(p.seed_codes_i32 + row);
+                        if (c0 < 0 || c0 >= p.seed_K) { atomicExch(p.err_flag, 0x20u); c0 = 0; }
+                    } else {
+                        c0 = (int)__ldg(p.sel_code + row * p.code_stride);
+                        if (c0 >= p.seed_K) { atomicExch(p.err_flag, 0x10u); c0 = p.seed_K - 1; }
+                    }
+                }
+                const float* src = p.seed_tab + (size_t)c0 * D;
+                float* xrow = p.xhat_out + row * D;
+#pragma unroll 1
+                for (int c = o0c; c < o1c; c += 32) {
+                    const int n = (o1c - c) >= 32 ? 32 : 16;
+                    float x[32];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float4 v = (4 * i < n) ? ldg4(src + c + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+                        if (valid && 4 * i < n) *reinterpret_cast<float4*>(xrow + c + 4 * i) = v;
+                    }
+                    put_operand(t, c, n, x);
+                }
+            };
+            auto step_code = [&](int64_t row, bool valid, int ls) {
+                int code = 0;
+                if (valid) {
+                    code = (int)__ldg(p.sel_code + row * p.code_stride + p.code_off + ls);
+                    if (code >= K) { atomicExch(p.err_flag, 0x10u); code = K - 1; }
+                }
+                return code;
+            };
+            // init of a step: Eacc <- T_m[code] (fp32); the operand [xhat_hi | xhat_lo] is already in shared memory
+            auto init_loop = [&](int t, int code, const float* t_blk) {
+                const uint32_t tl = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col;
+#pragma unroll 1
+                for (int c = e0c; c < e1c; c += 32) {
+                    const int n = (e1c - c) >= 32 ? 32 : 16;
+                    uint32_t e[32];
+                    const float* base = t_blk + ((size_t)(c >> 2) * K + code) * 4;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float4 v = (4 * i < n) ? ldg4(base + (size_t)i * K * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        e[4 * i] = __float_as_uint(v.x); e[4 * i + 1] = __float_as_uint(v.y);
+                        e[4 * i + 2] = __float_as_uint(v.z); e[4 * i + 3] = __float_as_uint(v.w);
+                    }
+                    __syncwarp();
+                    if (n >= 32) tmem_st32(tl + c, e); else tmem_st16p(tl + c, e);
+                }
+                tmem_wait_st();
+                arrive_issuer(t, QB_BAR_AE_READY, true);
+            };
+            // final of a step: xhat' = xhat + o (+ C_m[code]) over this thread's columns; o sits in Eacc (no out_proj) or in
+            // the single out_proj chunk in Hacc.  Last step: scale / shift and write the result; otherwise write the running
+            // xhat and the next step's operand.
+            auto final_loop = [&](int t, int64_t row, bool valid, int code, const float* cb_blk, bool last) {
+                const uint32_t taddr = lane_base + (uint32_t)t * tile_cols + (pl.has_proj ? pl.tmem_h_col : pl.tmem_e_col);
+                float* xrow = p.xhat_out + row * D;
+                const bool skip = pl.skip != 0;
+#pragma unroll 1
+                for (int c = o0c; c < o1c; c += 32) {
+                    const int n = (o1c - c) >= 32 ? 32 : 16;
+                    uint32_t v[32];
+                    tmem_ld_cols(taddr + c, n, v);
+                    float4 xin[8], cb[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const bool on = 4 * i < n;
+                        xin[i] = (valid && on) ? *reinterpret_cast<const float4*>(xrow + c + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        cb[i] = (skip && on) ? ldg4(cb_blk + ((size_t)((c >> 2) + i) * K + code) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    tmem_wait_ld();
+                    float x[32];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        x[4 * i] = xin[i].x + (__uint_as_float(v[4 * i]) + cb[i].x);
+                        x[4 * i + 1] = xin[i].y + (__uint_as_float(v[4 * i + 1]) + cb[i].y);
+                        x[4 * i + 2] = xin[i].z + (__uint_as_float(v[4 * i + 2]) + cb[i].z);
+                        x[4 * i + 3] = xin[i].w + (__uint_as_float(v[4 * i + 3]) + cb[i].w);
+                    }
+                    if (!last) put_operand(t, c, n, x);
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            if (4 * i < n) {
+                                float4 o = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+                                if (last) {
+                                    if (p.out_shift) {
+                                        const float4 sh = ldg4(p.out_shift + c + 4 * i);
+                                        o.x = fmaf(o.x, p.out_scale, sh.x); o.y = fmaf(o.y, p.out_scale, sh.y);
+                                        o.z = fmaf(o.z, p.out_scale, sh.z); o.w = fmaf(o.w, p.out_scale, sh.w);
+                                    } else if (p.out_scale != 1.0f) {
+                                        o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale;
+                                    }
+                                }
+                                *reinterpret_cast<float4*>(xrow + c + 4 * i) = o;
+                            }
+                        }
+                    }
+                }
+            };
+            for (int64_t set = set_first; more_sets(set); set += set_stride) {
+                const int64_t row0 = (set * NT + 0) * QB_TILE_M + r, row1 = (set * NT + 1) * QB_TILE_M + r;
+                const bool valid0 = row0 < p.n_rows, valid1 = NT > 1 && row1 < p.n_rows;
+                seed_tile(0, valid0 ? row0 : 0, valid0);
+                if (NT > 1) seed_tile(1, valid1 ? row1 : 0, valid1);
+                int code0 = step_code(row0, valid0, 0), code1 = (NT > 1) ? step_code(row1, valid1, 0) : 0;
+                init_loop(0, code0, p.loop_steps[0].t_blk);
+                if (NT > 1) init_loop(1, code1, p.loop_steps[0].t_blk);
+#pragma unroll 1
+                for (int ls = 0; ls < n_ls; ls++) {
+                    const bool last = ls + 1 == n_ls;
+                    // e0 = T_m[code] + u is complete: fp16 copy for the first up-projection (or the out_proj)
+#pragma unroll 1
+                    for (int t = 0; t < NT; t++) {
+                        wait_l(t, QB_BAR_EACC_FULL, 0x425);
+                        acc_to_smem_operand(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, e0c, e1c,
+                                            smem_base + pl.smem_ae[t] + (uint32_t)r * 16u);
+                        arrive_issuer(t, QB_BAR_AE_READY, true);
+                    }
+#pragma unroll 1
+                    for (int l = 0; l < pl.L; l++) {
+#pragma unroll 1
+                        for (int j = 0; j < pl.n_hchunk; j++) {
+                            const int cw = min(pl.hc, pl.Dh - j * pl.hc);
+                            int c0, c1;
+                            group_range(cw, cg, c0, c1);
+#pragma unroll 1
+                            for (int t = 0; t < NT; t++) {
+                                wait_l(t, QB_BAR_HACC_FULL, 0x424);
+                                const uint32_t th = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
+                                if (kColGroups == 2 && pl.h_split && cw == pl.hc && (cw >> 2) <= 32) {
+                                    const int qw = cw >> 2;
+                                    acc_to_tmem_operand_half(th, cg * qw, qw, 1 + q);
+                                    arrive_issuer(t, QB_BAR_AH_READY, false);
+                                    acc_to_tmem_operand_half(th, (cw >> 1) + cg * qw, qw, 1 + q);
+                                    arrive_issuer(t, QB_BAR_AH2_READY, false);
+                                } else {
+                                    acc_to_tmem_operand(th, c0, c1, 1 + q);
+                                    arrive_issuer(t, QB_BAR_AH_READY, false);
+                                }
+                            }
+                        }
+                        if (l + 1 < pl.L || pl.has_proj) {
+#pragma unroll 1
+                            for (int t = 0; t < NT; t++) {
+                                wait_l(t, QB_BAR_EACC_FULL, 0x425);
+                                acc_to_smem_operand(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, e0c, e1c,
+                                                    smem_base + pl.smem_ae[t] + (uint32_t)r * 16u);
+                                arrive_issuer(t, QB_BAR_AE_READY, true);
+                            }
+                        }
+                    }
+#pragma unroll 1
+                    for (int t = 0; t < NT; t++) {
+                        if (pl.has_proj) wait_l(t, QB_BAR_HACC_FULL, 0x434);
+                        else if (pl.L > 0) wait_l(t, QB_BAR_EACC_FULL, 0x435);
+                        const int64_t row = t ? row1 : row0;
+                        const bool valid = t ? valid1 : valid0;
+                        final_loop(t, valid ? row : 0, valid, t ? code1 : code0, p.loop_steps[ls].cb_blk, last);
+                        tc_fence_before();
+                        if (!last) {            // tile slot t goes straight into its next step
+                            const int code = step_code(row, valid, ls + 1);
+                            if (t) code1 = code; else code0 = code;
+                            init_loop(t, code, p.loop_steps[ls + 1].t_blk);
+                        }
+                    }
+                }
+            }
+        } else {
         int64_t kset = 0;
         // per-tile row context, kept in scalars (no runtime-indexed arrays).  It belongs to the set whose tiles are
         // currently initialised: without an out_proj the init of the NEXT set's tile t is issued right after the final
@@ -1000,6 +1221,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             if (kResident) mbar_arrive((a_rempty + (uint32_t)(rb) * 8u));
             tr.ev(8);
         }
+        }   // !kLoop
     }
 
     // ---- teardown ------------------------------------------------------------------------------------------------
@@ -1029,7 +1251,8 @@ cudaError_t mlp_set_smem_attr(int smem_bytes) {
     if (smem_bytes <= current[dev]) return cudaSuccess;
     const void* fns[] = {(const void*)qb_mlp_kernel<true, false, false>, (const void*)qb_mlp_kernel<true, true, false>,
                          (const void*)qb_mlp_kernel<false, false, false>, (const void*)qb_mlp_kernel<true, false, true>,
-                         (const void*)qb_mlp_kernel<true, true, true>, (const void*)qb_mlp_kernel<false, false, true>};
+                         (const void*)qb_mlp_kernel<true, true, true>, (const void*)qb_mlp_kernel<false, false, true>,
+                         (const void*)qb_mlp_kernel<false, false, false, true>};
     for (const void* f : fns) {
         e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return e;
@@ -1048,6 +1271,9 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
                           p.plan.n_tiles == 2 && (p.n_rows & 255) == 0 && n_sm >= 4;
     const bool pair = p.plan.pair != 0 && n_sm >= 2;     // the weights are packed for the pair kernel: no other choice
     if (p.plan.pair && !pair) return cudaErrorInvalidConfiguration;
+    const bool loop = p.n_loop_steps > 0;
+    if (loop && (p.mode != QB_MODE_APPLY || pair || p.plan.n_ops_pre <= 0 || p.n_loop_steps > QB_MAX_LOOP_STEPS || p.plan.n_ochunk > 1))
+        return cudaErrorInvalidConfiguration;
     int grid;
     if (resident) {
         const int64_t sets = ((p.n_rows >> 8) + 3) / 4;       // per code quarter
@@ -1073,6 +1299,7 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        if (loop) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, false, true>, q);
         if (pair) {
             if (resident) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, true, true>, q);
             if (q.mode == QB_MODE_SCORE) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, true>, q);

@@ -79,7 +79,8 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     const int h_cols = h_need > 0 ? round_up(hc, 32) : 0;
     if (e_cols + h_cols > 512) { *err = "de too large for TMEM: round32(de) + round32(hc) must be <= 512 columns"; return -1; }
     const int a_kc_bytes = QB_TILE_M * 16;  // one 8-element k-chunk of a 128-row A operand
-    const int ae_bytes = (De / 8) * a_kc_bytes;
+    p->ae_chunks = (opt.uop ? std::max(De, 2 * D) : De) / 8;
+    const int ae_bytes = p->ae_chunks * a_kc_bytes;
     p->slot_bytes = opt.slot_bytes > 0 ? opt.slot_bytes : 32768;
     if (p->slot_bytes % 1024) { *err = "slot_bytes must be a multiple of 1024"; return -1; }
     // two tiles in flight share every weight slab: they need 2x the TMEM columns and 2x the A_E tile
@@ -111,7 +112,7 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     // the codes (64 codes x 2 beams per tile), whose rows of T_m (registers) and of the skip codebook (shared memory) stay
     // on the SM instead of being gathered from L2 for every tile (the gathers cost as much L2->SM bandwidth as the weights).
     p->smem_tres = -1;
-    if (n_tiles == 2 && !p->has_proj && K == 256 && De <= 128 && budget - off - D * 256 >= 4 * 16384 && opt.no_resident == 0) {
+    if (n_tiles == 2 && !p->has_proj && K == 256 && De <= 128 && budget - off - D * 256 >= 4 * 16384 && opt.no_resident == 0 && !opt.uop) {
         p->smem_tres = off;
         off += D * 256;          // the skip-codebook quarter; the T_m row slice of a thread (<= 64 columns) sits in registers
         if (opt.slot_bytes <= 0) p->slot_bytes = 16384;      // a deeper ring of smaller slabs fits next to the tables
@@ -193,6 +194,18 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
                   q > 0 ? QB_BAR_HACC_FREE : QB_BAR_NONE, QB_BAR_HACC_FULL);
     }
     p->n_ops_out = (int)ops->size() - p->n_ops_block;
+    // pre-ops of the decode loop: per column part of Eacc, [xhat_hi | xhat_lo] . [Wx_hi | Wx_hi]^T then xhat_hi . Wx_lo^T
+    if (opt.uop) {
+        if (p->pair) { *err = "the decode-loop plan has no CTA-pair variant"; return -1; }
+        if (p->n_ochunk > 1) { *err = "the decode-loop plan needs the whole out_proj in one chunk (D <= hc)"; return -1; }
+        for (int n0 = 0; n0 < De; n0 += epart) {
+            const int n = std::min(epart, De - n0);
+            const bool last = n0 + n >= De;
+            emit_gemm(n, 2 * D, QB_A_E, 0, p->tmem_e_col + n0, true, n0 == 0 ? QB_BAR_AE_READY : QB_BAR_NONE, QB_BAR_NONE, QB_BAR_NONE);
+            emit_gemm(n, D, QB_A_E, 0, p->tmem_e_col + n0, true, QB_BAR_NONE, QB_BAR_NONE, last ? QB_BAR_EACC_FULL : QB_BAR_NONE);
+        }
+    }
+    p->n_ops_pre = (int)ops->size() - p->n_ops_block - p->n_ops_out;
     if (ops->size() > QB_MAX_OPS) { *err = "op list too long"; return -1; }
     for (const QbOp& op : *ops)
         if ((int)op.slab_bytes > (p->pair ? 2 : 1) * p->slot_bytes || op.n_slab < 1) { *err = "internal: slab larger than ring slot"; return -1; }
@@ -246,6 +259,41 @@ int pack_step_weights(const QbStepPlan& p, const std::vector<QbOp>& ops, const f
     return 0;
 }
 
+int pack_pre_weights(const QbStepPlan& p, const std::vector<QbOp>& ops, const float* wx, uint16_t* blob, std::string* err) {
+    const int D = p.D, De = p.De;
+    const int n_eparts = (De + 255) / 256;
+    const int epart = round_up((De + n_eparts - 1) / n_eparts, 16);
+    size_t cursor = (size_t)(p.n_ops_block + p.n_ops_out);
+    const size_t end = cursor + (size_t)p.n_ops_pre;
+    // column k of the op's weight matrix -> (input dimension, hi or lo part of Wx)
+    auto put = [&](const QbOp& op, int row0, bool lo_only) {
+        for (int s = 0; s < op.n_slab; s++) {
+            uint16_t* dst = blob + (op.w_off + (size_t)s * op.slab_bytes) / 2;
+            const int k0 = s * op.ks, kn = std::min<int>(op.ks, op.k_total - k0);
+            for (int k = 0; k < kn; k++) {
+                const int d = (k0 + k) % D;
+                for (int r = 0; r < op.n; r++) {
+                    const float w = wx[(size_t)(row0 + r) * D + d];
+                    const uint16_t hi = f32_to_f16(w);
+                    const uint16_t v = lo_only ? f32_to_f16(w - f16_to_f32(hi)) : hi;
+                    dst[((size_t)(k / 8) * op.n + r) * 8 + (k % 8)] = v;
+                }
+            }
+        }
+    };
+    for (int n0 = 0; n0 < De && p.n_ops_pre > 0; n0 += epart) {
+        const int n = std::min(epart, De - n0);
+        if (cursor + 2 > end) { *err = "internal: pre-op pack order does not match the op list"; return -1; }
+        const QbOp& a = ops[cursor++];
+        const QbOp& b = ops[cursor++];
+        if (a.n != n || a.k_total != 2 * D || b.n != n || b.k_total != D) { *err = "internal: pre-op shapes do not match"; return -1; }
+        put(a, n0, false);     // [Wx_hi | Wx_hi]
+        put(b, n0, true);      // Wx_lo
+    }
+    if (cursor != end) { *err = "internal: pre-op pack order does not match the op list"; return -1; }
+    return 0;
+}
+
 // T_m[k] = e0 + Wcat[:, :De] . e0 + bcat,  e0 = Pin . C_m[k]   (double accumulation, stored fp32, blocked [De/4][K][4]:
 // consecutive codes are 16 B apart, so a warp whose lanes hold consecutive codes gathers 512 contiguous bytes)
 void build_tables(int D, int De, int K, const float* codebook, const float* in_proj, const float* concat_w,
@@ -285,7 +333,7 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
     qb::PlanOptions opt;
     if (opts5) {
         opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = opts5[1] >> 8; opt.slot_bytes = opts5[2];
-        opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.max_slab_k = opts5[4];
+        opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.uop = (opts5[3] >> 10) & 1; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
     std::vector<QbOp> ops;
@@ -294,7 +342,7 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
     const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_tiles, p.tmem_alloc_cols,
                          p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk, p.oc, p.n_ochunk, p.tmem_e_col, p.tmem_h_col,
                          p.tmem_tile_cols, p.smem_tres, p.smem_ring, p.slot_bytes, p.n_stage, p.smem_total,
-                         (int32_t)p.block_w_bytes, (int32_t)p.w_blob_bytes, p.pair, p.h_split};
+                         (int32_t)p.block_w_bytes, (int32_t)p.w_blob_bytes, p.pair, p.h_split, p.n_ops_pre, p.ae_chunks};
     const int nv = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < nv && i < n_plan_out; i++) plan_out[i] = v[i];
     if ((int)ops.size() > max_ops) return -2;
@@ -307,7 +355,7 @@ int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int
     qb::PlanOptions opt;
     if (opts5) {
         opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = opts5[1] >> 8; opt.slot_bytes = opts5[2];
-        opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.max_slab_k = opts5[4];
+        opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.uop = (opts5[3] >> 10) & 1; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
     std::vector<QbOp> ops;
@@ -315,6 +363,21 @@ int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int
     if (qb::make_step_plan(D, De, Dh, L, K, qinco1_mode, opt, &p, &ops, &err)) return -1;
     if (blob_halfs * 2 < p.w_blob_bytes) return -2;
     return qb::pack_step_weights(p, ops, up, down, out_proj, blob, &err);
+}
+
+int qb_plan_pack_pre(int D, int De, int Dh, int L, int K, int qinco1_mode, const int32_t* opts5, const float* wx, uint16_t* blob,
+                     int64_t blob_halfs) {
+    qb::PlanOptions opt;
+    if (opts5) {
+        opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = opts5[1] >> 8; opt.slot_bytes = opts5[2];
+        opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.uop = (opts5[3] >> 10) & 1; opt.max_slab_k = opts5[4];
+    }
+    QbStepPlan p;
+    std::vector<QbOp> ops;
+    std::string err;
+    if (qb::make_step_plan(D, De, Dh, L, K, qinco1_mode, opt, &p, &ops, &err)) return -1;
+    if (blob_halfs * 2 < p.w_blob_bytes) return -2;
+    return qb::pack_pre_weights(p, ops, wx, blob, &err);
 }
 
 int qb_plan_tables(int D, int De, int K, const float* codebook, const float* in_proj, const float* concat_w,

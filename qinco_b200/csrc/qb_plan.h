@@ -26,6 +26,7 @@
 
 #define QB_TILE_M 128
 #define QB_MAX_OPS 64
+#define QB_MAX_LOOP_STEPS 64
 #define QB_MAX_STAGE 12
 
 enum QbASrc : uint8_t { QB_A_E = 0, QB_A_H = 1 };   // A operand: e (shared memory) or relu(h) (TMEM, in place)
@@ -90,6 +91,14 @@ struct QbStepPlan {
                              // arrivals on AH_READY per chunk; the down-projection's slabs end on the half boundary)
     int32_t pair;            // 1: CTA-pair kernel (cta_group::2, M = 256 over two CTAs): every slab is packed as two row
                              // halves, CTA r of a pair streams half r into a ring slot of slot_bytes
+    // Decode loop (kLoop kernel: one tile walks every step, xhat stays with its rows): u = Wx . xhat runs on the tensor core
+    // as n_ops_pre "pre-ops" placed AFTER the out_proj ops in the op list (so block / out_proj indices and weight offsets
+    // are those of the plain plan): Eacc (initialised with T_m[code]) += [xhat_hi | xhat_lo] . [Wx_hi | Wx_hi]^T
+    // + xhat_hi . Wx_lo^T, fp16 hi/lo splits of an fp32 value (~22 mantissa bits).  The A operand [xhat_hi | xhat_lo]
+    // (2D/8 k-chunks) is written by the previous step's final epilogue into the A_E buffer, which therefore holds
+    // ae_chunks = max(De, 2D) / 8 k-chunks.  0 pre-ops: a plain plan.
+    int32_t n_ops_pre;
+    int32_t ae_chunks;
     int64_t block_w_bytes;   // packed weight bytes of one residual block
     int64_t w_blob_bytes;    // packed weight bytes for this step (L blocks + out_proj)
 };

@@ -20,7 +20,7 @@ OP_DTYPE = np.dtype([("w_off", "<u4"), ("slab_bytes", "<u4"), ("last_bytes", "<u
                      ("pad", "u1", 3)])
 PLAN_FIELDS = ["D", "De", "Dh", "L", "K", "has_proj", "skip", "n_tiles", "tmem_alloc_cols", "n_ops_block", "n_ops_out",
                "hc", "n_hchunk", "oc", "n_ochunk", "tmem_e_col", "tmem_h_col", "tmem_tile_cols", "smem_tres", "smem_ring",
-               "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes", "pair", "h_split"]
+               "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes", "pair", "h_split", "n_ops_pre", "ae_chunks"]
 A_E, A_H = 0, 1
 BAR_AE_READY, BAR_AH_READY, BAR_HACC_FREE, BAR_HACC_FULL, BAR_EACC_FULL = 1, 2, 3, 4, 5
 
@@ -268,3 +268,81 @@ def test_planner_replay_on_random_shapes(lib):
         if done >= 25:
             break
     assert done >= 15
+
+
+# ---------------------------------------------------------------------------------------------------- decode-loop plan
+UOP = 1 << 10       # opts5[3] bit 10: the decode-loop plan (pre-ops computing u = Wx . xhat on the tensor core)
+
+
+def pack_pre(lib, cfg, w, m, plan, opts, blob):
+    o = (C.c_int32 * 5)(*opts)
+    D, De = cfg["D"], cfg["de"]
+    wx = np.ascontiguousarray(w[f"steps.{m}.concat.mlp.weight"][:, De:], dtype=np.float32)       # [De][D]
+    lib.qb_plan_pack_pre.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    rc = lib.qb_plan_pack_pre(D, De, cfg["dh"], cfg["L"], cfg["K"], int(cfg["qinco1_mode"]), C.cast(o, C.c_void_p),
+                              wx.ctypes.data_as(C.c_void_p), blob.ctypes.data_as(C.c_void_p), len(blob))
+    assert rc == 0, rc
+
+
+def replay_pre(plan, ops, blob, T, codes, xhat):
+    """Software model of the decode loop's step start: Eacc = T_m[code], then the pre-ops accumulate the fp16 hi/lo
+    products of the operand [xhat_hi | xhat_lo] (k-chunks 0 .. 2D/8 of the A_E buffer) -> e0 = T_m[code] + Wx . xhat."""
+    D, De = plan["D"], plan["De"]
+    hi = f16(xhat)
+    a_x = np.concatenate([hi, f16(xhat - hi)], axis=1)                 # what the previous step's final epilogue writes
+    assert a_x.shape[1] // 8 <= plan["ae_chunks"]
+    e = T[codes].copy()
+    bytes_view = blob.view(np.uint8)
+    first = plan["n_ops_block"] + plan["n_ops_out"]
+    pre = ops[first:first + plan["n_ops_pre"]]
+    assert len(pre) == plan["n_ops_pre"] > 0
+    assert pre[0]["wait_a"] == BAR_AE_READY and pre[-1]["commit"] == BAR_EACC_FULL
+    for op in pre:
+        nn, ks, kt = int(op["n"]), int(op["ks"]), int(op["k_total"])
+        assert op["a_src"] == A_E and op["a_off"] == 0 and op["accumulate"] == 1 and kt in (D, 2 * D)
+        assert op["slab_bytes"] == nn * ks * 2 <= plan["slot_bytes"]
+        c0 = int(op["d_col"])
+        for s in range(int(op["n_slab"])):
+            kk = min(ks, kt - s * ks)
+            off = int(op["w_off"]) + s * int(op["slab_bytes"])
+            W = bytes_view[off: off + nn * kk * 2].view(np.float16).astype(np.float32).reshape(kk // 8, nn, 8).transpose(1, 0, 2).reshape(nn, kk)
+            e[:, c0:c0 + nn] += a_x[:, s * ks: s * ks + kk] @ W.T
+    return e
+
+
+@pytest.mark.parametrize("name", ["S", "Q1", "L", "deep", "odd", "tiny", "noblock"])
+def test_decode_loop_plan_replay(lib, name):
+    """The decode-loop plan keeps the plain plan's block / out_proj ops (one shared weight blob) and its pre-ops reproduce
+    e0 = T_m[code] + Wcat[:, De:] . xhat to ~fp32 accuracy (fp16 hi/lo split on both operands, three products)."""
+    cfg = synth.make_cfg(None, **SHAPES[name])
+    w = synth.make_weights(cfg, seed=3, n_train=512, kmeans_iters=1)          # NOT fp16-exact: the lo parts matter
+    base, base_ops = export_plan(lib, cfg, None)
+    opts = [base["hc"], 1 << 8, base["slot_bytes"], UOP, 0]
+    plan, ops = export_plan(lib, cfg, opts)
+    assert plan["n_ops_pre"] > 0 and plan["smem_tres"] == -1
+    assert plan["ae_chunks"] == max(cfg["de"], 2 * cfg["D"]) // 8
+    assert plan["smem_total"] + 15 * 1024 <= 227 * 1024
+    nb = len(base_ops)
+    assert plan["n_ops_block"] == base["n_ops_block"] and plan["n_ops_out"] == base["n_ops_out"]
+    assert ops[:nb].tobytes() == base_ops.tobytes()
+    blob = pack(lib, cfg, w, 1, plan, opts)
+    np.testing.assert_array_equal(blob[: len(pack(lib, cfg, w, 1, base, None))][: base["w_blob_bytes"] // 2],
+                                  pack(lib, cfg, w, 1, base, None)[: base["w_blob_bytes"] // 2])
+    pack_pre(lib, cfg, w, 1, plan, opts, blob)
+    T, CB, WxT = tables(lib, cfg, w, 1)
+    rng = np.random.default_rng(1)
+    n = 48
+    codes = rng.integers(0, cfg["K"], n)
+    xhat = (3.0 * rng.standard_normal((n, cfg["D"]))).astype(np.float32)
+    e0 = replay_pre(plan, ops, blob, T, codes, xhat)
+    ref = T[codes].astype(np.float64) + xhat.astype(np.float64) @ WxT.astype(np.float64)
+    u = xhat.astype(np.float64) @ WxT.astype(np.float64)
+    assert np.abs(e0 - ref).max() <= 2e-6 * max(np.abs(u).max(), 1.0)      # a single fp16 product would be ~5e-4
+
+
+def test_decode_loop_plan_refuses_chunked_out_proj(lib):
+    cfg = synth.make_cfg(None, **SHAPES["contriever"])
+    o = (C.c_int32 * 5)(0, 1 << 8, 0, UOP, 0)
+    plan = (C.c_int32 * 32)()
+    ops = np.zeros(256, OP_DTYPE)
+    assert lib.qb_plan_export(cfg["D"], cfg["de"], cfg["dh"], cfg["L"], cfg["K"], 0, o, plan, 32, ops.ctypes.data_as(C.c_void_p), 256) < 0
