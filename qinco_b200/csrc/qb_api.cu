@@ -92,6 +92,9 @@ struct qb_model {
     float* cb0_norm = nullptr; // [K] squared row norms of cb0
     float* mean = nullptr;     // [D]
     std::vector<StepDev> steps;   // index m, entry 0 unused
+    bool fuse_ok = true;          // fused beam selection inside the score launch (QB_NO_FUSE=1 keeps the unfused sequence for A/B runs)
+    int fuse_mode = 1;            // 1: arg-min in the score launch, xhat' by a 1/256-size update launch (default);
+                                  // 2 (QB_FUSE_FULL=1): the score launch also writes xhat' (measured slower)
     bool loop_ok = false;         // every step has a decode-loop plan (qb_mlp_kernel<.., kLoop>): decode is ONE launch
     uint32_t* err_host = nullptr;   // mapped pinned word written by the kernels before they trap
     uint32_t* err_dev = nullptr;
@@ -163,13 +166,15 @@ struct Workspace {
     float* dist;
     uint8_t* selp;
     uint8_t* selc;
+    unsigned long long* sel_best;   // fused selection state, one entry per vector
+    uint32_t* sel_cnt;
 };
 
 size_t encode_bytes_per_vector(const qb_model* m) {
     const size_t B = m->B, C = m->A > 0 ? m->A : m->K;
-    return 2 * B * m->D * 4 + 2 * B * m->M + B * m->D * 4 + B * m->De * 4 + B * std::max(m->A, 1) + B * C * 4 + 2 * B;
+    return 2 * B * m->D * 4 + 2 * B * m->M + B * m->D * 4 + B * m->De * 4 + B * std::max(m->A, 1) + B * C * 4 + 2 * B + 12;
 }
-constexpr size_t kWsSlack = 16 * 256;   // alignment padding of the carve-up
+constexpr size_t kWsSlack = 20 * 256;   // alignment padding of the carve-up
 
 int64_t default_chunk(const qb_model* m) {
     const int64_t rows_per_vec = (int64_t)m->B * (m->A > 0 ? m->A : m->K);
@@ -197,6 +202,8 @@ void carve(const qb_model* m, void* ws, int64_t nc, Workspace* w) {
     w->dist = (float*)take(n * B * C * 4);
     w->selp = take(n * B);
     w->selc = take(n * B);
+    w->sel_best = (unsigned long long*)take(n * 8);
+    w->sel_cnt = (uint32_t*)take(n * 4);
 }
 
 enum { KIND_PREP = 0, KIND_SCORE = 1, KIND_SELECT = 2, KIND_APPLY = 3, KIND_OTHER = 4, KIND_COUNT = 5 };
@@ -277,6 +284,10 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, int32_t*
         // it pre-selects max(A, B) candidates (QincoSubstep._n_codes, qinco_base.py:108-112)
         const int A = (m->A > 0 && m->ivf_K && step == 1) ? std::max(m->A, B) : m->A;
         const int C = A > 0 ? A : K;
+        // Fused selection (the score launch picks the winners and writes xhat' / the history itself): resident launches
+        // with one beam per vector, i.e. A == 0, beam 1 on K = 256 models whose tables fit the SM (QINCo1 / QINCo2-S shapes).
+        const bool fuse = m->fuse_ok && A == 0 && K == 256 && F_in == 1 && F_out == 1 && s.plan.smem_tres >= 0 &&
+                          s.plan.n_tiles == 2 && m->n_sm >= 4;
         {
             qb::PrepParams p;
             std::memset(&p, 0, sizeof(p));
@@ -284,6 +295,7 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, int32_t*
             p.n_beams = n * F_in; p.x = x; p.mean = mean; p.inv_std = inv_std_div;
             p.xhat = w.xhat[cur]; p.wx = s.wx; p.sub_cb = A > 0 ? s.sub_cb : nullptr; p.sub_norm = s.sub_norm;
             p.r = w.r; p.u = w.u; p.idx = w.idx;
+            if (fuse) { p.sel_best = w.sel_best; p.sel_cnt = w.sel_cnt; }
             QB_CUDA(timed_launch(m, KIND_PREP, p.n_beams, st, [&] { return qb::launch_prep(p, st); }));
         }
         {
@@ -292,7 +304,39 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, int32_t*
             p.C = C; p.A = A;
             p.n_rows = n * F_in * C;
             p.idx = w.idx; p.u = w.u; p.r = w.r; p.dist = w.dist;
+            if (fuse) {
+                p.fuse = m->fuse_mode; p.F_in = F_in; p.F_out = F_out;
+                p.sel_best = w.sel_best; p.sel_cnt = w.sel_cnt;
+                p.dist = nullptr;
+                if (m->fuse_mode == 2) {    // the score launch also writes xhat' and the history
+                    p.hist_in = w.hist[cur]; p.hist_out = last ? codes : w.hist[cur ^ 1]; p.hist_M = M; p.hist_m = m->col(step);
+                    p.xhat_in = w.xhat[cur];
+                    p.xhat_out = last ? xhat_out : w.xhat[cur ^ 1];      // NULL at the last step when the caller wants codes only
+                }
+            }
             QB_CUDA(timed_launch(m, KIND_SCORE, p.n_rows, st, [&] { return qb::launch_mlp(p, m->n_sm, st); }));
+        }
+        if (fuse && m->fuse_mode == 1) {
+            // the winners are in sel_best: a 1/256-size update launch recomputes their f_m, writes xhat' and the history
+            if (!last || xhat_out) {
+                qb::MlpParams p = base_mlp(m, step);
+                p.mode = qb::QB_MODE_APPLY;
+                p.F_in = 1; p.F_out = 1; p.n_rows = n;
+                p.sel_best = w.sel_best;
+                p.hist_in = w.hist[cur]; p.hist_out = last ? codes : w.hist[cur ^ 1]; p.hist_M = M; p.hist_m = m->col(step);
+                p.u = w.u; p.xhat_in = w.xhat[cur];
+                p.xhat_out = last ? xhat_out : w.xhat[cur ^ 1];
+                QB_CUDA(timed_launch(m, KIND_APPLY, p.n_rows, st, [&] { return qb::launch_mlp(p, m->n_sm, st); }));
+            } else {
+                QB_CUDA(timed_launch(m, KIND_SELECT, n, st, [&] {
+                    return qb::launch_take_codes(w.sel_best, n, w.hist[cur], codes, M, m->col(step), st);
+                }));
+            }
+        }
+        if (fuse) {
+            cur ^= 1;
+            F_in = F_out;
+            continue;
         }
         {
             qb::SelectParams p;
@@ -468,6 +512,8 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
     m->data_std = d->data_std;
     m->ivf_K = d->ivf_K;
     m->S = d->ivf_K > 0 ? d->M + 1 : d->M;
+    m->fuse_ok = getenv("QB_NO_FUSE") == nullptr;
+    m->fuse_mode = getenv("QB_FUSE_FULL") ? 2 : 1;
     auto bail = [&](int code) {
         qb_model_destroy(m);
         return code;

@@ -64,6 +64,19 @@ struct MlpParams {
     float* xhat_out;          // apply: [n_rows, D]
     float out_scale;          // apply
     const float* out_shift;   // apply: [D] or NULL
+    // Fused beam selection (fuse != 0, score mode; reference QINCoStep.encode, qinco_base.py:343-372: distances -> topk ->
+    // gathers).  The score launch itself picks the F_out best candidates of every vector and writes their xhat' = xhat_b + o
+    // and code history, so the step needs no `dist` array, no select launch and no second (apply) MLP launch.
+    //   resident launches (A == 0, C == 256, F_in == F_out == 1): a vector's 256 candidates are spread over the 4 code-quarter
+    //   CTAs; each keeps its local winner's o in shared memory, publishes (dist, code) with a packed 64-bit atomicMin on
+    //   sel_best[v] and counts itself on sel_cnt[v]; one set later the select warp of the CTA that owns the global winner adds
+    //   xhat_b and writes xhat' / the history.  sel_best / sel_cnt are initialised by the step's prep launch.
+    int32_t fuse;
+    int32_t hist_M, hist_m;         // history row length, column written by this step
+    unsigned long long* sel_best;   // [n vectors]  (dist bits << 32 | code)
+    uint32_t* sel_cnt;              // [n vectors]
+    const uint8_t* hist_in;         // [n, F_in, M]
+    uint8_t* hist_out;              // [n, F_out, M]
     // Decode loop (n_loop_steps > 0, apply mode, F_in = F_out = 1; reference QINCoInferenceDecoder.forward,
     // qinco_inference.py:66-75): row i starts at seed_tab[seed code] (C_0[codes[i][0]], or the IVF centroid of
     // seed_codes_i32[i]) and walks loop step s = 0 .. n_loop_steps-1 with code sel_code[i*code_stride + code_off + s];
@@ -103,6 +116,8 @@ struct PrepParams {
     uint8_t* idx;             // [n_beams, A]
     float* xhat_out;          // step0: [n, A, D]
     uint8_t* hist_out;        // step0: [n, A, M]
+    unsigned long long* sel_best;   // fused selection of the following score launch: reset to ~0 / 0 per vector (F == 1), or NULL
+    uint32_t* sel_cnt;
 };
 cudaError_t launch_prep(const PrepParams& p, cudaStream_t stream);
 
@@ -150,6 +165,11 @@ cudaError_t launch_codes_pack(const void* codes_MB, int elem_bytes, int64_t stri
                               int K, int ivf_K, uint8_t* codes_u8, int32_t* ivf, uint32_t* err_flag, cudaStream_t stream);
 cudaError_t launch_codes_unpack(const uint8_t* codes_u8, const int32_t* ivf, int64_t n, int M, int has_ivf, int64_t* codes_MB,
                                 cudaStream_t stream);
+
+// hist_out[v] = hist_in[v][0 .. m) ++ (code of sel_best[v]): the history update after a fused selection when no update launch
+// follows (last step, codes only)
+cudaError_t launch_take_codes(const unsigned long long* sel_best, int64_t n, const uint8_t* hist_in, uint8_t* hist_out, int M,
+                              int m, cudaStream_t stream);
 
 // out[i] = in[i]*scale + shift[i % D]
 cudaError_t launch_affine(const float* in, float* out, int64_t n, int D, float scale, const float* shift,

@@ -130,6 +130,10 @@ __global__ void __launch_bounds__(kPrepThreads) qb_prep_kernel(const PrepParams 
             for (int b = 0; b < 4; b++) acc[a][b] = acc2[a][b].x + acc2[a][b].y;
     };
 
+    if (p.sel_best && tid < nrow) {      // state of the fused selection in the score launch that follows (one beam per vector)
+        p.sel_best[b0 + tid] = ~0ull;
+        p.sel_cnt[b0 + tid] = 0u;
+    }
     float acc[4][4];
     if (p.wx) {          // u[b][e] = Wx[e] . xhat[b]
         for (int e0 = 0; e0 < De; e0 += kTileN) {
@@ -462,7 +466,22 @@ __global__ void qb_codes_unpack_kernel(const uint8_t* __restrict__ codes, const 
     for (int m = 0; m < M; m++) dst[(int64_t)(m + has_ivf) * n + v] = (int64_t)codes[v * M + m];
 }
 
+__global__ void qb_take_codes_kernel(const unsigned long long* __restrict__ best, int64_t n, const uint8_t* __restrict__ hist_in,
+                                     uint8_t* __restrict__ hist_out, int M, int m) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    for (int c = 0; c < m; c++) hist_out[v * M + c] = hist_in[v * M + c];
+    hist_out[v * M + m] = (uint8_t)(best[v] & 0xffull);
+}
+
 }  // namespace
+
+cudaError_t launch_take_codes(const unsigned long long* sel_best, int64_t n, const uint8_t* hist_in, uint8_t* hist_out, int M,
+                              int m, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    qb_take_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sel_best, n, hist_in, hist_out, M, m);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_codes_pack(const void* codes_MB, int elem_bytes, int64_t stride_row, int64_t stride_col, int64_t n, int M,
                               int K, int ivf_K, uint8_t* codes_u8, int32_t* ivf, uint32_t* err_flag, cudaStream_t stream) {

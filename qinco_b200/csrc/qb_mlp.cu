@@ -106,6 +106,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
     }
 }
 
+// Same for a warp whose latency does not matter (the select warp): it sleeps between polls instead of competing with the
+// epilogue warps of its scheduler for issue slots.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t* err_flag, uint32_t code) {
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(400);
+        if ((++spins & 255u) == 0) {
+            const uint64_t now = globaltimer();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 4000000000ull) {
+                if (err_flag) atomicExch(err_flag, code);
+                __threadfence_system();
+                __trap();
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -414,9 +433,16 @@ struct Tracer {
 
 }  // namespace
 
-template <bool kScore, bool kResident, bool kPair, bool kLoop = false>
+template <bool kScore, bool kResident, bool kPair, bool kLoop = false, int kFuse = 0>
 __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_constant__ MlpParams p) {
     static_assert(!kLoop || (!kScore && !kResident && !kPair), "the decode loop is an apply-mode, single-CTA variant");
+    static_assert(!kFuse || (kScore && !kPair && !kLoop), "fused selection lives in the single-CTA score variants");
+    constexpr bool kFuseA = kFuse != 0 && kResident; // cross-CTA arg-min of a beam-1 vector over its four code-quarter CTAs
+    // fused selection, resident launches: the local winner's o of [buffer = set parity][tile slot][beam of the tile], its
+    // packed (dist, code) key per lane quarter, and the epilogue <-> select-warp hand-off barriers per tile slot
+    __shared__ __align__(16) float sel_stash[kFuseA ? (kFuse == 2 ? 2 * 2 * 2 * 128 : 2 * 2 * 256) : 4];
+    __shared__ __align__(8) unsigned long long sel_key[kFuseA && kFuse == 2 ? 2 * 2 * 4 : 1];
+    __shared__ __align__(8) uint64_t sel_full[2], sel_empty[2];
     extern __shared__ __align__(1024) uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t bars[2][QB_BAR_COUNT];     // one barrier set per tile slot
     __shared__ __align__(8) uint64_t w_full[QB_MAX_STAGE];
@@ -472,6 +498,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             mbar_init(smem_u32(&bars[t][QB_BAR_HACC_FULL]), 1);
             mbar_init(smem_u32(&bars[t][QB_BAR_EACC_FULL]), 1);
         }
+        for (int t = 0; t < 2; t++) { mbar_init(smem_u32(&sel_full[t]), kEpiWarps); mbar_init(smem_u32(&sel_empty[t]), 1); }
         mbar_init(smem_u32(&tres_bar), 1);
         for (int b = 0; b < 3; b++) { mbar_init(smem_u32(&rows_full[b]), 1); mbar_init(smem_u32(&rows_empty[b]), kEpiThreads); }
         for (int s = 0; s < QB_MAX_STAGE; s++) {
@@ -507,6 +534,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     const uint32_t a_tres = opaque(smem_u32(&tres_bar)), a_rfull = opaque(smem_u32(&rows_full[0])), a_rempty = opaque(smem_u32(&rows_empty[0]));
     const uint32_t a_beam = opaque(smem_u32(&beam_rows[0][0][0][0]));
     const uint32_t a_dist = opaque(smem_u32(&dist_part[0][0][0]));
+    const uint32_t a_sfull = opaque(smem_u32(&sel_full[0])), a_sempty = opaque(smem_u32(&sel_empty[0]));
+    const uint32_t a_stash = opaque(smem_u32(&sel_stash[0])), a_skey = opaque(smem_u32(&sel_key[0]));
     auto bar_addr = [&](int t, int b) { return a_bars + (uint32_t)(t * QB_BAR_COUNT + b) * 8u; };
     const uint32_t tile_cols = (uint32_t)pl.tmem_tile_cols;
 
@@ -599,6 +628,101 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         }
                     }
                 }
+            }
+        } else if (kFuseA && t == 2) {
+            // ================================================================================= select warp (fused, resident)
+            // Per (set, tile slot): publish this CTA's local winners (packed atomicMin + arrival count per vector), then
+            // settle the PREVIOUS set: by then the other three code quarters have normally reported too, so the wait is a
+            // formality; whoever holds the global winner adds xhat_b to its stashed o and writes xhat' and the history.
+            const int lane = tid & 31;
+            const int D = pl.D;
+            auto ld_acquire_u32 = [](const uint32_t* ptr) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory"); return v; };
+            auto ld_relaxed_u64 = [](const unsigned long long* ptr) { unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory"); return v; };
+            auto settle = [&](int64_t set, int t, int buf) {
+                for (int h = 0; h < 2; h++) {
+                    const int64_t v = 4 * set + 2 * t + h;
+                    if (v >= n_beams) continue;
+                    uint32_t spins = 0;
+                    uint64_t t0 = 0;
+                    while (ld_acquire_u32(p.sel_cnt + v) < 4u) {          // all four code quarters have reported
+                        __nanosleep(200);
+                        if ((++spins & 255u) == 0) {
+                            const uint64_t now = globaltimer();
+                            if (t0 == 0) t0 = now;
+                            if (now - t0 > 4000000000ull) { atomicExch(p.err_flag, 0x800u); __threadfence_system(); __trap(); }
+                        }
+                    }
+                    const unsigned long long key = ld_relaxed_u64(p.sel_best + v);
+                    const int code = (int)(key & 0xffffffffull);
+                    if ((code >> 6) != hq) continue;                      // the winner sits in another quarter's CTA
+                    uint8_t* ho = p.hist_out + v * p.hist_M;
+                    const uint8_t* hi = p.hist_in + v * p.hist_M;
+                    for (int c = lane; c < p.hist_m; c += 32) ho[c] = hi[c];
+                    if (lane == 0) ho[p.hist_m] = (uint8_t)code;
+                    if (p.xhat_out) {
+                        const uint32_t st = a_stash + (uint32_t)(((buf * 2 + t) * 2 + h) * 128) * 4u;
+                        for (int d4 = lane; d4 * 4 < D; d4 += 32) {
+                            const float4 xi = *reinterpret_cast<const float4*>(p.xhat_in + v * D + d4 * 4);
+                            const float4 o = lds4(st + (uint32_t)d4 * 16u);
+                            *reinterpret_cast<float4*>(p.xhat_out + v * D + d4 * 4) = make_float4(xi.x + o.x, xi.y + o.y, xi.z + o.z, xi.w + o.w);
+                        }
+                    }
+                }
+            };
+            int64_t kset = 0, prev_set = -1;
+            constexpr bool lite = kFuse == 1;
+            for (int64_t set = set_first; more_sets(set); set += set_stride, kset++) {
+                const int buf = (int)(kset & 1);
+                for (int tt = 0; tt < 2; tt++) {
+                    mbar_wait_relaxed(a_sfull + (uint32_t)tt * 8u, (uint32_t)(kset & 1), p.err_flag, 0x810 + tt);
+                    if constexpr (lite) {
+                        // fuse == 1: the epilogue left the 128 distances of the tile in shared memory (rows 0-63 / 64-127 =
+                        // the code quarter of two consecutive vectors); this warp ranks them and reports the two local
+                        // minima.  The winner's xhat' is produced by the small update launch that follows the score launch.
+                        const uint32_t da = a_stash + (uint32_t)((buf * 2 + tt) * 256) * 4u;
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const float d0 = lds1(da + (uint32_t)(64 * h + lane) * 4u), d1 = lds1(da + (uint32_t)(64 * h + 32 + lane) * 4u);
+                            const unsigned long long ka = (((unsigned long long)__float_as_uint(d0)) << 32) | (unsigned)(hq * 64 + lane);
+                            const unsigned long long kb = (((unsigned long long)__float_as_uint(d1)) << 32) | (unsigned)(hq * 64 + 32 + lane);
+                            unsigned long long key = ka < kb ? ka : kb;
+#pragma unroll
+                            for (int off = 16; off > 0; off >>= 1) {
+                                const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, off);
+                                key = o < key ? o : key;
+                            }
+                            const int64_t v = 4 * set + 2 * tt + h;
+                            if (lane == 0 && v < n_beams) atomicMin(p.sel_best + v, key);
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(a_sempty + (uint32_t)tt * 8u);
+                    } else {
+                    if (lane < 2) {
+                        const int64_t v = 4 * set + 2 * tt + lane;
+                        if (v < n_beams) {
+                            unsigned long long k0, k1;
+                            const uint32_t ka = a_skey + (uint32_t)(((buf * 2 + tt) * 4 + 2 * lane) * 8);
+                            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(k0) : "r"(ka));
+                            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(k1) : "r"(ka + 8u));
+                            atomicMin(p.sel_best + v, k0 < k1 ? k0 : k1);
+                            __threadfence();
+                            atomicAdd(p.sel_cnt + v, 1u);
+                        }
+                    }
+                    __syncwarp();
+                    if (prev_set >= 0) settle(prev_set, tt, buf ^ 1);
+                    // one completion per set on sel_empty: "this set's keys are taken and the set before it is settled" --
+                    // the epilogue waits for it one set later, which bounds its lead over this warp to one set (the
+                    // barriers carry a single phase bit) and frees the stash buffer it is about to reuse
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_sempty + (uint32_t)tt * 8u);
+                    }   // full
+                }
+                prev_set = set;
+            }
+            if (prev_set >= 0 && kFuse == 2) {
+                settle(prev_set, 0, (int)((kset - 1) & 1));
+                settle(prev_set, 1, (int)((kset - 1) & 1));
             }
         } else if (t < NT) {
             uint32_t stage = 0, phase = 0;
@@ -871,9 +995,11 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
 #pragma unroll 1
                     for (int t = 0; t < NT; t++) {
                         wait_l(t, QB_BAR_EACC_FULL, 0x425);
-                        acc_to_smem_operand(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, e0c, e1c,
-                                            smem_base + pl.smem_ae[t] + (uint32_t)r * 16u);
-                        arrive_issuer(t, QB_BAR_AE_READY, true);
+                        if (pl.L > 0 || pl.has_proj) {      // (no GEMM follows in a block-less model without out_proj)
+                            acc_to_smem_operand(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, e0c, e1c,
+                                                smem_base + pl.smem_ae[t] + (uint32_t)r * 16u);
+                            arrive_issuer(t, QB_BAR_AE_READY, true);
+                        }
                     }
 #pragma unroll 1
                     for (int l = 0; l < pl.L; l++) {
@@ -956,9 +1082,16 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         const int64_t v = (int64_t)((uint32_t)row / (uint32_t)p.F_out);
                         const int parent = p.sel_parent ? (int)__ldg(p.sel_parent + row) : 0;
                         beam = v * p.F_in + parent;
-                        code = (int)__ldg(p.sel_code + row * p.code_stride + p.code_off);
+                        code = p.sel_best ? (int)(p.sel_best[row] & 0xffull)           // winner of the fused selection (low bits = code)
+                                          : (int)__ldg(p.sel_code + row * p.code_stride + p.code_off);
                     }
                     if (code >= K) code = K - 1;   // never read outside the tables (bad codes are rejected on the host)
+                    if (!kScore && p.hist_out && cg == 0) {     // update launch after a fused selection: extend the code history
+                        uint8_t* ho = p.hist_out + row * p.hist_M;
+                        const uint8_t* hi = p.hist_in + beam * p.hist_M;
+                        for (int c = 0; c < p.hist_m; c++) ho[c] = hi[c];
+                        ho[p.hist_m] = (uint8_t)code;
+                    }
                 }
             };
             if (!primed) {
@@ -1161,6 +1294,79 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     if (valid) p.dist[row] = a;
                 }
             };
+            // Fused selection, resident launches (one beam per vector, 64 candidates of it per tile half): CTA-local arg-min,
+            // the winner's o = Eacc + C_m[code] re-read from TMEM into the stash, hand-off to the select warp.
+            auto fused_select_resident = [&](int t, float a, int code, bool valid) {
+                const int buf = (int)(kset & 1);
+                if (cg > 0) sts1(a_dist + (uint32_t)((t * kParts + cg - 1) * QB_TILE_M + r) * 4u, a);
+                named_bar_sync(5, kEpiThreads);
+                if constexpr (kFuse == 1) {  // distances to shared memory for the select warp; nothing else on this path
+                    if (cg == 0) {
+#pragma unroll
+                        for (int g = 0; g < kColGroups - 1; g++) a += lds1(a_dist + (uint32_t)((t * kParts + g) * QB_TILE_M + r) * 4u);
+                        if (kset >= 1) mbar_wait(a_sempty + (uint32_t)t * 8u, (uint32_t)((kset - 1) & 1), p.err_flag, 0x820 + t);
+                        sts1(a_stash + (uint32_t)((buf * 2 + t) * 256 + r) * 4u, valid ? a : __uint_as_float(0x7f800000u));
+                    }
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(a_sfull + (uint32_t)t * 8u);
+                    return;
+                } else {
+                if (cg == 0) {
+#pragma unroll
+                    for (int g = 0; g < kColGroups - 1; g++) a += lds1(a_dist + (uint32_t)((t * kParts + g) * QB_TILE_M + r) * 4u);
+                    // (dist bits << 32 | code): distances are >= 0, so the integer order is the (dist, code) order
+                    unsigned long long key = valid ? (((unsigned long long)__float_as_uint(a)) << 32) | (unsigned)code : ~0ull;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, off);
+                        key = o < key ? o : key;
+                    }
+                    // the select warp has taken the previous set's keys and settled the set before it (whose stash / key
+                    // buffer is the one reused now)
+                    if (kset >= 1) mbar_wait(a_sempty + (uint32_t)t * 8u, (uint32_t)((kset - 1) & 1), p.err_flag, 0x820 + t);
+                    if ((tid & 31) == 0)
+                        asm volatile("st.shared.u64 [%0], %1;" ::"r"(a_skey + (uint32_t)(((buf * 2 + t) * 4 + q) * 8)), "l"(key) : "memory");
+                }
+                named_bar_sync(5, kEpiThreads);
+                if (p.xhat_out) {
+                    const int h = q >> 1;
+                    unsigned long long k0, k1;
+                    const uint32_t ka = a_skey + (uint32_t)(((buf * 2 + t) * 4 + 2 * h) * 8);
+                    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(k0) : "r"(ka));
+                    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(k1) : "r"(ka + 8u));
+                    const unsigned long long key = k0 < k1 ? k0 : k1;
+                    const int wrow = 64 * h + ((int)(key & 0xffffffffull) & 63);        // tile row of the local winner
+                    if (key != ~0ull && (wrow >> 5) == q) {                              // warp-uniform: this warp owns that row
+                        const uint32_t taddr = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col;
+                        const uint32_t cs_a = smem_base + (uint32_t)pl.smem_tres + (uint32_t)(wrow & 63) * 16u;
+                        const uint32_t st = a_stash + (uint32_t)(((buf * 2 + t) * 2 + h) * 128) * 4u;
+                        const bool skip = pl.skip != 0;
+#pragma unroll 1
+                        for (int c = o0c; c < o1c; c += 32) {
+                            const int n = o1c - c;
+                            uint32_t v[32];
+                            tmem_ld_cols(taddr + c, n, v);
+                            tmem_wait_ld();
+                            if ((tid & 31) == (wrow & 31)) {
+#pragma unroll
+                                for (int i = 0; i < 8; i++) {
+                                    if (4 * i < n) {
+                                        const float4 cv = skip ? lds4(cs_a + (uint32_t)((c >> 2) + i) * 1024u) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st + (uint32_t)(c + 4 * i) * 4u),
+                                                     "f"(__uint_as_float(v[4 * i]) + cv.x), "f"(__uint_as_float(v[4 * i + 1]) + cv.y),
+                                                     "f"(__uint_as_float(v[4 * i + 2]) + cv.z), "f"(__uint_as_float(v[4 * i + 3]) + cv.w)
+                                                     : "memory");
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(a_sfull + (uint32_t)t * 8u);
+                }   // full
+            };
             const int64_t set_next = set + set_stride;
             const bool has_next = more_sets(set_next);
             if (!pl.has_proj) {
@@ -1181,7 +1387,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                                a_beam + (uint32_t)(((rb * 2 + t) * 2 + (r >> 6)) * 256 + De) * 4u);
                     tc_fence_before();
                     tr.ev(7 + 0x80 * t);
-                    if (kScore) publish_dist(t, a, t ? row1 : row0, t ? valid1 : valid0);
+                    if (kFuseA) fused_select_resident(t, a, t ? code1 : code0, t ? valid1 : valid0);
+                    else if (kScore) publish_dist(t, a, t ? row1 : row0, t ? valid1 : valid0);
                     if (has_next) {         // tile slot t is free: start its next set now
                         if (kResident && t == 0)
                             mbar_wait((a_rfull + (uint32_t)(rbn) * 8u), (uint32_t)(((kset + 1) / 3) & 1), p.err_flag, 0x610 + rbn);
@@ -1252,7 +1459,7 @@ cudaError_t mlp_set_smem_attr(int smem_bytes) {
     const void* fns[] = {(const void*)qb_mlp_kernel<true, false, false>, (const void*)qb_mlp_kernel<true, true, false>,
                          (const void*)qb_mlp_kernel<false, false, false>, (const void*)qb_mlp_kernel<true, false, true>,
                          (const void*)qb_mlp_kernel<true, true, true>, (const void*)qb_mlp_kernel<false, false, true>,
-                         (const void*)qb_mlp_kernel<false, false, false, true>};
+                         (const void*)qb_mlp_kernel<false, false, false, true>, (const void*)qb_mlp_kernel<true, true, false, false, 1>, (const void*)qb_mlp_kernel<true, true, false, false, 2>};
     for (const void* f : fns) {
         e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return e;
@@ -1272,6 +1479,10 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
     const bool pair = p.plan.pair != 0 && n_sm >= 2;     // the weights are packed for the pair kernel: no other choice
     if (p.plan.pair && !pair) return cudaErrorInvalidConfiguration;
     const bool loop = p.n_loop_steps > 0;
+    // fused selection needs the resident score variant with one beam per vector, all its CTAs co-resident (they wait for
+    // each other's reports) and the selection state; anything else must go through the unfused launches
+    if (p.fuse && (!resident || pair || p.F_in != 1 || p.F_out != 1 || !p.sel_best || p.plan.D > 128)) return cudaErrorInvalidConfiguration;
+    if (p.fuse == 2 && (!p.sel_cnt || !p.hist_out || !p.xhat_in)) return cudaErrorInvalidConfiguration;
     if (loop && (p.mode != QB_MODE_APPLY || pair || p.plan.n_ops_pre <= 0 || p.n_loop_steps > QB_MAX_LOOP_STEPS || p.plan.n_ochunk > 1))
         return cudaErrorInvalidConfiguration;
     int grid;
@@ -1305,6 +1516,8 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
             if (q.mode == QB_MODE_SCORE) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, true>, q);
             return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, true>, q);
         }
+        if (resident && q.fuse == 1) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, true, false, false, 1>, q);
+        if (resident && q.fuse == 2) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, true, false, false, 2>, q);
         if (resident) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, true, false>, q);
         if (q.mode == QB_MODE_SCORE) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, false>, q);
         return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, false>, q);

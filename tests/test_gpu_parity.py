@@ -18,6 +18,10 @@ DEC_TOL = 1e-4        # relative MSE of decode vs reference (north_star)
 STEP_TOL = 1e-5       # one MLP step, relative MSE
 ENC_TOL_SMALL = 5e-3  # |MSE_ours - MSE_ref| / MSE_ref on the tiny golden samples (tens of vectors: one flipped path moves it)
 ENC_TOL_LARGE = 1e-4  # ... on thousands of vectors (north_star)
+# encode's returned x-hat vs decode(codes): two different kernels (u = Wx . xhat in fp32 on the CUDA cores vs fp16 hi/lo
+# products on the tensor core); the reference's own gap between its two paths is ~1e-4 max-abs relative = 1e-8 relative MSE
+# (oracle/make_golden.py enc_dec_gap)
+ENC_DEC_TOL = 1e-8
 
 
 @pytest.fixture(scope="module")
@@ -150,7 +154,7 @@ def test_encode_matches_reference(name, models):
     assert torch.equal(codes2, codes)
     dec = model.decode(codes2)
     model.synchronize()
-    assert rel_mse(xhat.cpu().numpy(), dec.cpu().numpy()) <= 1e-10
+    assert rel_mse(xhat.cpu().numpy(), dec.cpu().numpy()) <= ENC_DEC_TOL
     u8, _ = model.encode_u8(torch.from_numpy(xn).cuda())
     assert torch.equal(u8.t().long(), codes)
 
@@ -181,7 +185,7 @@ def test_encode_large_sample_mse():
     c3 = torch.cat([model.encode_u8(xb[i:i + 7777])[0] for i in range(0, len(xb), 7777)])
     model.synchronize()
     assert torch.equal(c1, c2) and torch.equal(c1, c3)
-    assert rel_mse(model.decode_u8(c1).cpu().numpy(), xh1.cpu().numpy()) <= 1e-10
+    assert rel_mse(model.decode_u8(c1).cpu().numpy(), xh1.cpu().numpy()) <= ENC_DEC_TOL
     model._h.close()
 
 
@@ -257,7 +261,7 @@ def test_v1_codec_matches_reference(golden_loader):
     c, xh = model.encode(xt)
     assert tuple(c.shape) == (len(xt), cfg["M"]) and c.dtype == torch.int64
     np.testing.assert_array_equal(c.cpu().numpy(), codes)
-    assert rel_mse(model.decode(c).cpu().numpy(), xh.cpu().numpy()) <= 1e-10
+    assert rel_mse(model.decode(c).cpu().numpy(), xh.cpu().numpy()) <= ENC_DEC_TOL
     # from a v1-keyed state dict
     m2 = codec.QINCoV1(synth.to_v1_state(cfg, w), db_scale=float(z["db_scale"]))
     np.testing.assert_array_equal(codec.encode(m2, z["x"], bs=96, verbose=False), codes)
@@ -293,7 +297,7 @@ def test_ivf_model_matches_reference(name, golden_loader):
         assert agree >= 0.8 and abs(mse_ours - mse_ref) <= ENC_TOL_SMALL * mse_ref
         codes2, xhat = model.encode(torch.from_numpy(xn).cuda())
         assert torch.equal(codes2, codes)
-        assert rel_mse(xhat.cpu().numpy(), model.decode(codes2).cpu().numpy()) <= 1e-10
+        assert rel_mse(xhat.cpu().numpy(), model.decode(codes2).cpu().numpy()) <= ENC_DEC_TOL
         with pytest.raises(IndexError):
             bad = z["codes_ref"].copy()
             bad[0, 0] = cfg["ivf_K"]
@@ -497,7 +501,7 @@ def test_full_depth_fixture_matches_reference(name, golden_loader):
         print(f"\n{name}: identical vectors {agree:.3f}, mse ours {d_ours.mean():.5f} ref {d_ref.mean():.5f} rel {rel:.2e}, "
               f"worst vector {np.abs(d_ours - d_ref).max() / d_ref.mean():.2e}")
         assert rel <= FULL_TOL[name][0] and agree >= FULL_TOL[name][1]
-        assert rel_mse(xhat.cpu().numpy(), model.decode(codes).cpu().numpy()) <= 1e-10
+        assert rel_mse(xhat.cpu().numpy(), model.decode(codes).cpu().numpy()) <= ENC_DEC_TOL
     finally:
         model._h.close()
 
@@ -545,3 +549,86 @@ def test_encode_mse_at_contract_sample(workload, rows):
     assert rel <= ENC_TOL_LARGE, (workload, rel)
     if len(delta) > 30:
         assert abs(delta.mean()) <= 4 * sem + 1e-12, "the differing vectors are systematically better or worse than the reference's"
+
+
+# ------------------------------------------------------------------------------------------- single-launch decode
+@pytest.mark.parametrize("name", GOLDEN_V2 + ["ivf_a8_b4", "ivf_a0_b1"])
+def test_decode_loop_kernel(name, golden_loader, monkeypatch):
+    """The one-launch decode (every tile walks all steps inside qb_mlp_kernel<.., kLoop>, u = Wx . xhat on the tensor core
+    as fp16 hi/lo products) against the reference AND against the per-step launch sequence it replaces: same result to
+    fp32 rounding, 1 launch instead of 2 (M - 1) + 1, ragged / single-row batches."""
+    from qinco_b200.model import QINCo
+    cfg, w, z = golden_loader(name)
+    loop = QINCo(cfg, w, device="cuda:0")
+    monkeypatch.setenv("QB_NO_DECODE_LOOP", "1")
+    steps = QINCo(cfg, w, device="cuda:0")
+    monkeypatch.delenv("QB_NO_DECODE_LOOP")
+    try:
+        assert loop._h.info(1)["decode_loop"] == 1 and steps._h.info(1)["decode_loop"] == 0
+        codes = torch.from_numpy(z["codes_ref"]).cuda()
+        l0 = loop.launch_count
+        a = loop(codes, step="decode")
+        n_launch = loop.launch_count - l0
+        b = steps(codes, step="decode")
+        loop.synchronize(); steps.synchronize()
+        assert n_launch == 2, n_launch                  # the code pack kernel + ONE decode kernel
+        assert rel_mse(a.cpu().numpy(), z["dec_ref"]) <= DEC_TOL
+        assert rel_mse(a.cpu().numpy(), b.cpu().numpy()) <= 1e-10
+        # a bigger, ragged batch of random codes (several tile sets per CTA), and single rows
+        rng = np.random.default_rng(5)
+        S = codes.shape[0]
+        big = rng.integers(0, cfg["K"], size=(S, 40000 if cfg["D"] <= 32 else 3001))
+        if cfg.get("ivf_K"):
+            big[0] = rng.integers(0, cfg["ivf_K"], size=big.shape[1])
+        bt = torch.from_numpy(big).cuda()
+        ya, yb = loop.decode(bt), steps.decode(bt)
+        loop.synchronize(); steps.synchronize()
+        assert rel_mse(ya.cpu().numpy(), yb.cpu().numpy()) <= 1e-9
+        assert torch.equal(loop.decode(bt[:, :1]), ya[:1]) and torch.equal(loop.decode(bt[:, 129:130]), ya[129:130])
+        assert torch.equal(loop.decode(bt), ya)          # deterministic
+    finally:
+        loop._h.close(); steps._h.close()
+
+
+# ------------------------------------------------------------------------------------------------ fused beam selection
+@pytest.mark.parametrize("mode", ["lite", "full"])
+@pytest.mark.parametrize("name", ["s_a0_b1", "q1_l4", "ivf_a0_b1"])
+def test_fused_selection_matches_unfused(name, mode, golden_loader, monkeypatch):
+    """Selection fused into the score launch (distance -> arg-min inside the kernel, no `dist` array, no select launch;
+    reference qinco_base.py:343-372) against the unfused launch sequence.  The arithmetic is the same, so codes AND xhat must
+    be bit-identical.  `lite` (default): the winner's xhat' comes from a 1/256-size update launch; `full` (QB_FUSE_FULL=1):
+    the score launch writes xhat' and the history itself."""
+    from qinco_b200.model import QINCo
+    cfg, w, z = golden_loader(name)
+    if mode == "full":
+        monkeypatch.setenv("QB_FUSE_FULL", "1")
+    fused = QINCo(cfg, w, device="cuda:0")
+    monkeypatch.delenv("QB_FUSE_FULL", raising=False)
+    monkeypatch.setenv("QB_NO_FUSE", "1")
+    plain = QINCo(cfg, w, device="cuda:0")
+    monkeypatch.delenv("QB_NO_FUSE")
+    try:
+        ivf = bool(cfg.get("ivf_K"))
+        enc = (lambda m, x: m.encode_ivf_u8(x)) if ivf else (lambda m, x: (None,) + m.encode_u8(x))
+        steps = cfg["M"] - (0 if ivf else 1)
+        for n in (len(z["x"]), 1, 129, 39999):
+            x = torch.from_numpy(synth.make_data(n, cfg["D"], seed=n)).cuda() if n != len(z["x"]) else \
+                torch.from_numpy((z["x"] - w["data_mean"]) / np.float32(w["data_std"])).cuda()
+            l0, p0 = fused.launch_count, plain.launch_count
+            iv_a, c_a, x_a = enc(fused, x)
+            n_fused = fused.launch_count - l0
+            iv_b, c_b, x_b = enc(plain, x)
+            n_plain = plain.launch_count - p0
+            fused.synchronize(); plain.synchronize()
+            assert torch.equal(c_a, c_b), (name, n, float((c_a == c_b).all(1).float().mean()))
+            assert torch.equal(x_a, x_b)
+            if ivf:
+                assert torch.equal(iv_a, iv_b)
+            if n < 128:          # one chunk: step 0, then per step prep + score (+ the update launch in lite mode) vs 4 launches
+                assert n_plain == 1 + 4 * steps and n_fused == 1 + (3 if mode == "lite" else 2) * steps, (n_plain, n_fused)
+        # codes only (no xhat wanted)
+        c_only = fused(torch.from_numpy(z["x"]).cuda(), step="encode")
+        fused.synchronize()
+        np.testing.assert_array_equal(c_only.cpu().numpy(), plain(torch.from_numpy(z["x"]).cuda(), step="encode").cpu().numpy())
+    finally:
+        fused._h.close(); plain._h.close()
