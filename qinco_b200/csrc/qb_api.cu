@@ -57,6 +57,8 @@ struct StepDev {
     float* wx = nullptr;         // [De][D] = Wcat[:, De:]
     float* sub_cb = nullptr;     // [K][D] pre-selection codebook (A > 0)
     float* sub_norm = nullptr;   // [K] squared row norms of sub_cb
+    uint8_t* wx_pack = nullptr;  // tensor-core beam preparation: fp16 hi/lo operand parts of wx / sub_cb (qb_prep_tc.cu)
+    uint8_t* sub_pack = nullptr;
     // decode loop (one launch walks every step): the same weight blob, extended by the pre-op slabs (u = Wx . xhat)
     QbStepPlan loop_plan;
     std::vector<QbOp> loop_ops;
@@ -93,6 +95,7 @@ struct qb_model {
     float* mean = nullptr;     // [D]
     std::vector<StepDev> steps;   // index m, entry 0 unused
     bool fuse_ok = true;          // fused beam selection inside the score launch (QB_NO_FUSE=1 keeps the unfused sequence for A/B runs)
+    bool prep_tc = true;          // beam preparation on the tensor core (QB_PREP_CC=1: the fp32 CUDA-core kernel, for A/B runs)
     int fuse_mode = 1;            // 1: arg-min in the score launch, xhat' by a 1/256-size update launch (default);
                                   // 2 (QB_FUSE_FULL=1): the score launch also writes xhat' (measured slower)
     bool loop_ok = false;         // every step has a decode-loop plan (qb_mlp_kernel<.., kLoop>): decode is ONE launch
@@ -287,8 +290,19 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, int32_t*
         // Fused selection (the score launch picks the winners and writes xhat' / the history itself): resident launches
         // with one beam per vector, i.e. A == 0, beam 1 on K = 256 models whose tables fit the SM (QINCo1 / QINCo2-S shapes).
         const bool fuse = m->fuse_ok && A == 0 && K == 256 && F_in == 1 && F_out == 1 && s.plan.smem_tres >= 0 &&
-                          s.plan.n_tiles == 2 && m->n_sm >= 4;
-        {
+                          s.plan.n_tiles == 2 && !s.plan.pair && m->n_sm >= 4;
+        if (m->prep_tc) {       // u and the pre-selection distances as tensor-core GEMMs (fp16 hi/lo splits), top-A in the kernel
+            qb::PrepTcParams p;
+            std::memset(&p, 0, sizeof(p));
+            p.D = D; p.De = m->De; p.K = K; p.K16 = (K + 15) / 16 * 16; p.A = A; p.F = F_in;
+            p.n_beams = n * F_in; p.x = x; p.mean = mean; p.std_div = inv_std_div;
+            p.xhat = w.xhat[cur]; p.wx_pack = s.wx_pack; p.sub_pack = A > 0 ? s.sub_pack : nullptr; p.sub_norm = s.sub_norm;
+            p.r = w.r; p.u = w.u; p.idx = w.idx; p.err_flag = m->err_dev;
+            static const int dbg = getenv("QB_PREP_TC_DEBUG") ? atoi(getenv("QB_PREP_TC_DEBUG")) : 0;     // timing experiments only
+            p.dbg = dbg;
+            if (fuse) { p.sel_best = w.sel_best; p.sel_cnt = w.sel_cnt; }
+            QB_CUDA(timed_launch(m, KIND_PREP, p.n_beams, st, [&] { return qb::launch_prep_tc(p, st); }));
+        } else {
             qb::PrepParams p;
             std::memset(&p, 0, sizeof(p));
             p.D = D; p.De = m->De; p.K = K; p.A = A; p.F = F_in; p.step0 = 0; p.M = M;
@@ -514,6 +528,7 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
     m->S = d->ivf_K > 0 ? d->M + 1 : d->M;
     m->fuse_ok = getenv("QB_NO_FUSE") == nullptr;
     m->fuse_mode = getenv("QB_FUSE_FULL") ? 2 : 1;
+    m->prep_tc = getenv("QB_PREP_CC") == nullptr;
     auto bail = [&](int code) {
         qb_model_destroy(m);
         return code;
@@ -594,6 +609,9 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
                 for (int dd = 0; dd < D; dd++) wx[(size_t)e * D + dd] = wx_t[(size_t)dd * De + e];
             if ((rc = dev_upload(m, wx.data(), wx.size(), &sd.wx))) return bail(rc);
             if (loop && qb::pack_pre_weights(sd.loop_plan, lops, wx.data(), blob.data(), &err)) return bail(fail(QB_ERR_INVALID, err));
+            std::vector<uint16_t> pk(qb::prep_pack_bytes(De, D) / 2);
+            qb::prep_pack(wx.data(), De, D, pk.data());
+            if ((rc = dev_upload(m, (const uint8_t*)pk.data(), pk.size() * 2, &sd.wx_pack))) return bail(rc);
         }
         if ((rc = dev_upload(m, (const uint8_t*)blob.data(), blob.size() * 2, &sd.w_blob))) return bail(rc);
         if (m->A > 0) {
@@ -601,6 +619,9 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
             for (int k = 0; k < K; k++) nrm[k] = row_norm2(d->substep_codebook[s] + (size_t)k * D, D);
             if ((rc = dev_upload(m, d->substep_codebook[s], (size_t)K * D, &sd.sub_cb))) return bail(rc);
             if ((rc = dev_upload(m, nrm.data(), nrm.size(), &sd.sub_norm))) return bail(rc);
+            std::vector<uint16_t> pk(qb::prep_pack_bytes(K, D) / 2);
+            qb::prep_pack(d->substep_codebook[s], K, D, pk.data());
+            if ((rc = dev_upload(m, (const uint8_t*)pk.data(), pk.size() * 2, &sd.sub_pack))) return bail(rc);
         }
         max_smem = std::max(max_smem, sd.plan.smem_total);
     }

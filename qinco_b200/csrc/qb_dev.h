@@ -121,6 +121,33 @@ struct PrepParams {
 };
 cudaError_t launch_prep(const PrepParams& p, cudaStream_t stream);
 
+// The same beam preparation on the tensor core (qb_prep_tc.cu): u and the pre-selection distances as tcgen05 GEMMs over
+// fp16 hi/lo operand splits (fp32-level accuracy), top-A in the same kernel.  The weights come pre-packed (prep_pack):
+// for every chunk of QB_PREP_DC input dimensions, for every part of <= QB_PREP_NP rows (row count padded to a multiple of
+// 16 with zero rows): w_hi then w_lo, each as K-major core matrices [dc/8][np][8] fp16.  Not used for step 0.
+#define QB_PREP_DC 64
+#define QB_PREP_NP 256
+struct PrepTcParams {
+    int32_t D, De, K, K16, A;   // K16 = K rounded up to a multiple of 16
+    int32_t F;                  // beams per vector
+    int64_t n_beams;
+    const float* x;             // [n, D] raw input
+    const float* mean;          // [D] or NULL
+    float std_div;              // divisor after the mean shift (data_std or 1)
+    const float* xhat;          // [n_beams, D]
+    const uint8_t* wx_pack;     // packed Wcat[:, De:] ([De][D]) or NULL: skip u
+    const uint8_t* sub_pack;    // packed pre-selection codebook ([K16][D]) or NULL: no ranking
+    const float* sub_norm;      // [K] squared row norms
+    float* r;                   // [n_beams, D] or NULL
+    float* u;                   // [n_beams, De]
+    uint8_t* idx;               // [n_beams, A]
+    unsigned long long* sel_best;   // fused selection state to reset (F == 1), or NULL
+    uint32_t* sel_cnt;
+    uint32_t* err_flag;
+    int32_t dbg;                // timing experiments: bit 0 skips the ranking, bit 1 the MMAs, bit 2 the distance epilogue
+};
+cudaError_t launch_prep_tc(const PrepTcParams& p, cudaStream_t stream);
+
 // Beam selection (qinco_base.py:346-372): per vector the F_out smallest of R = F_in*C distances, ascending;
 // writes parent beam, code and the extended code history.
 struct SelectParams {

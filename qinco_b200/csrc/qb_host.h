@@ -35,6 +35,10 @@ int pack_step_weights(const QbStepPlan& plan, const std::vector<QbOp>& ops, cons
 // slabs of the pre-ops (decode-loop plans): wx is Wcat[:, De:] as [De][D] rows
 int pack_pre_weights(const QbStepPlan& plan, const std::vector<QbOp>& ops, const float* wx, uint16_t* blob, std::string* err);
 
+// operand blob of the tensor-core beam preparation (layout: qb_dev.h, PrepTcParams): w is [n_rows][D] fp32 row-major
+size_t prep_pack_bytes(int n_rows, int D);
+void prep_pack(const float* w, int n_rows, int D, uint16_t* out);
+
 void build_tables(int D, int De, int K, const float* codebook, const float* in_proj, const float* concat_w,
                   const float* concat_b, float* t_blk, float* cb_blk, float* wx_t);
 

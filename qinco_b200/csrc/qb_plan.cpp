@@ -294,6 +294,34 @@ int pack_pre_weights(const QbStepPlan& p, const std::vector<QbOp>& ops, const fl
     return 0;
 }
 
+size_t prep_pack_bytes(int n_rows, int D) {
+    const int n16 = (n_rows + 15) / 16 * 16;
+    return (size_t)n16 * D * 2 * 2;
+}
+
+void prep_pack(const float* w, int n_rows, int D, uint16_t* out) {
+    constexpr int kDc = 64, kNp = 256;          // QB_PREP_DC / QB_PREP_NP (qb_dev.h)
+    const int n16 = (n_rows + 15) / 16 * 16;
+    size_t off = 0;                             // in fp16 elements
+    for (int d0 = 0; d0 < D; d0 += kDc) {
+        const int dc = std::min(kDc, D - d0);
+        for (int r0 = 0; r0 < n16; r0 += kNp) {
+            const int np = std::min(kNp, n16 - r0);
+            uint16_t* hi = out + off;
+            uint16_t* lo = hi + (size_t)np * dc;
+            for (int k = 0; k < dc; k++)
+                for (int r = 0; r < np; r++) {
+                    const float v = (r0 + r < n_rows) ? w[(size_t)(r0 + r) * D + d0 + k] : 0.f;
+                    const uint16_t h = f32_to_f16(v);
+                    const size_t at = ((size_t)(k / 8) * np + r) * 8 + (k % 8);
+                    hi[at] = h;
+                    lo[at] = f32_to_f16(v - f16_to_f32(h));
+                }
+            off += 2 * (size_t)np * dc;
+        }
+    }
+}
+
 // T_m[k] = e0 + Wcat[:, :De] . e0 + bcat,  e0 = Pin . C_m[k]   (double accumulation, stored fp32, blocked [De/4][K][4]:
 // consecutive codes are 16 B apart, so a warp whose lanes hold consecutive codes gathers 512 contiguous bytes)
 void build_tables(int D, int De, int K, const float* codebook, const float* in_proj, const float* concat_w,

@@ -1,0 +1,433 @@
+// Beam preparation on the tensor core, sm_100a (tcgen05 / TMEM / TMA bulk copy).
+//
+// Per beam row b of step m the encode loop needs (reference QincoSubstep.get_distances_for_codes / select_code_candidates,
+// qinco/model/qinco_base.py:114-121; the hoisted half of QConcat, :60-64; distances qinco/utils.py:336-346):
+//     r_b  = x_n - xhat_b                                      (fp32, written for the score launch)
+//     u_b  = Wcat[:, De:] . xhat_b                             [De]
+//     idx_b = the A smallest of  (|r_b|^2 + |S_k|^2) - 2 r_b . S_k   over the K pre-selection codewords (A > 0)
+// The two contractions are GEMMs with M = beams, K-dim = D and N = De / K.  The CUDA-core version (qb_prep_kernel) ran them
+// at ~20 TFLOP/s and was 41 % of a QINCo2-S A=16 step; here a CTA takes a tile of 128 beams and runs them as tcgen05.mma with
+// fp32-level accuracy: both operands are split into fp16 hi + lo parts and three products are accumulated in TMEM
+//     a . w  ~=  a_hi . w_hi + a_lo . w_hi + a_hi . w_lo          (error ~2^-22 relative, the dropped lo . lo term)
+// so the ranking sees the same numbers as an fp32 evaluation up to rounding-level ties.
+//
+// Dataflow of one CTA (256 threads, no warp specialisation: the kernel is <2 % of a step, what matters is that it is not 40 %):
+//   for pass in {u, distances}:  for every 64-wide chunk of D:
+//       all threads   build the A operand chunk [a_hi | a_lo] in shared memory from xhat_b / r_b (K-major core matrices)
+//       thread 0      streams the pre-packed weight parts [w_hi | w_lo] (<= 256 rows each) with cp.async.bulk into a
+//                     two-deep ring and issues the three MMA groups per part; accumulators: TMEM columns [0, N)
+//   epilogue u:       TMEM -> u_b (global, fp32)
+//   epilogue dist:    TMEM -> d = (|r|^2 + |S_k|^2) - 2 g -> shared memory -> top-A per row (a warp ranks four rows at a time,
+//                     ties to the lower index like torch.topk)
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "qb_dev.h"
+
+namespace qb {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kRows = 128;                  // beams per CTA = MMA M
+constexpr int kDc = QB_PREP_DC;             // D chunk
+constexpr int kNp = QB_PREP_NP;             // weight rows per part = MMA N (<= 256)
+constexpr int kAkc = kRows * 16;            // bytes of one 8-element k-chunk of the A operand
+constexpr int kAHalf = (kDc / 8) * kAkc;    // a_hi (or a_lo) of one chunk: 16 KB
+constexpr int kBHalf = kNp * kDc * 2;       // w_hi (or w_lo) of one part and chunk: 32 KB
+constexpr int kSmemA = 0, kSmemB = 2 * kAHalf, kSmemTotal = kSmemB + 2 * 2 * kBHalf;      // 32 KB + 128 KB
+constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);     // SBO = 128 B, descriptor version 1
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* err_flag, uint32_t code) {
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0) {       // bounded: a protocol bug traps and reports instead of hanging the GPU
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 4000000000ull) { if (err_flag) atomicExch(err_flag, code); __threadfence_system(); __trap(); }
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kDescHi) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+
+// 8 consecutive values of an operand row -> fp16 hi / lo k-chunk rows (16 B each)
+__device__ __forceinline__ void put_hi_lo(uint32_t dst_hi, uint32_t dst_lo, const float (&x)[8]) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const __half2 h = __floats2half2_rn(x[2 * k], x[2 * k + 1]);
+        const float2 hf = __half22float2(h);
+        hi[k] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[k] = pack_h2(x[2 * k] - hf.x, x[2 * k + 1] - hf.y);
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_hi), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_lo), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+}
+
+// ---- top-16 of a stream of 16-value batches, exact: keys are (order-preserving bits of the fp32 distance) << 32 | index, so
+// the unsigned order is the (distance, index) order torch.topk(largest=False) produces.  Everything is a fixed network on
+// registers: no shared memory, no divergence.
+__device__ __forceinline__ unsigned long long dist_key(float d, int k) {
+    const uint32_t b = __float_as_uint(d);
+    const uint32_t ord = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);      // negative floats (rounding) order below positive ones
+    return ((unsigned long long)ord << 32) | (uint32_t)k;
+}
+__device__ __forceinline__ void cex(unsigned long long& a, unsigned long long& b) {      // a <= b afterwards
+    const bool sw = a > b;
+    const unsigned long long lo = sw ? b : a, hi = sw ? a : b;
+    a = lo; b = hi;
+}
+// bitonic merge of a bitonic 16-sequence into ascending order (4 stages of 8 compare-exchanges)
+__device__ __forceinline__ void bitonic_merge16(unsigned long long (&v)[16]) {
+#pragma unroll
+    for (int j = 8; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int l = i ^ j;
+            if (l > i) cex(v[i], v[l]);
+        }
+    }
+}
+// full bitonic sort of 16 keys, ascending (10 stages)
+__device__ __forceinline__ void bitonic_sort16(unsigned long long (&v)[16]) {
+#pragma unroll
+    for (int k = 2; k <= 16; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int l = i ^ j;
+                if (l > i) {
+                    if ((i & k) == 0) cex(v[i], v[l]); else cex(v[l], v[i]);
+                }
+            }
+        }
+    }
+}
+// best <- the 16 smallest of best U other (both ascending): min(best[i], other[15 - i]) is bitonic and holds them
+__device__ __forceinline__ void keep_smallest16(unsigned long long (&best)[16], const unsigned long long (&other)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) best[i] = best[i] < other[15 - i] ? best[i] : other[15 - i];
+    bitonic_merge16(best);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) qb_prep_tc_kernel(const __grid_constant__ PrepTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t b_full[2], mma_done[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float rn_part[2][kRows];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & (kRows - 1), half = tid >> 7;            // operand building: thread = (row, half of every chunk)
+    const int D = p.D, De = p.De, K = p.K;
+    const int64_t b0 = (int64_t)blockIdx.x * kRows;
+    const int nrow = (int)min((int64_t)kRows, p.n_beams - b0);
+    const bool live = row < nrow;
+    const int64_t b = b0 + row;
+    const uint32_t sbase = smem_u32(smem);
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&mma_done[i]), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (p.sel_best && tid < nrow) {       // state of the fused selection in the score launch that follows (one beam per vector)
+        p.sel_best[b0 + tid] = ~0ull;
+        p.sel_cnt[b0 + tid] = 0u;
+    }
+
+    const float* xrow = p.x + (b / p.F) * D;
+    const float* hrow = p.xhat + b * D;
+    int it = 0;                              // (pass, chunk, part) iterations so far: ring buffer it & 1, barrier phase (it >> 1) & 1
+    float rn = 0.f;                          // this thread's share of |r_b|^2
+    const int n_chunks = (D + kDc - 1) / kDc;
+
+    for (int pass = 0; pass < 2; pass++) {
+        const uint8_t* pack = pass == 0 ? p.wx_pack : p.sub_pack;
+        if (!pack) continue;
+        const int N = pass == 0 ? De : p.K16;
+        const int n_parts = (N + kNp - 1) / kNp;
+        size_t pack_off = 0;                 // parts and chunks are stored in the order they are consumed
+        for (int c = 0; c < n_chunks; c++) {
+            const int d0 = c * kDc, dc = min(kDc, D - d0);
+            // every MMA issued so far has read its operands: the A chunk may be rebuilt (and both ring slots are free)
+            if (it > 0) mbar_wait(smem_u32(&mma_done[(it - 1) & 1]), (uint32_t)(((it - 1) >> 1) & 1), p.err_flag, 0x900);
+            tc_fence_after();
+            // ---- A operand chunk: this thread's row, columns d0 + [half * dc/2 ..): xhat (pass 0) or r = x_n - xhat (pass 1)
+            {
+                const int cw = dc >> 1;      // dc is a multiple of 16, so cw is a multiple of 8
+                const int c_lo = d0 + half * cw;
+                const bool want_r = (pass == 1) || (p.sub_pack == nullptr && p.r != nullptr);
+#pragma unroll 1
+                for (int j = 0; j < cw; j += 8) {
+                    float xh[8], val[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { xh[q] = 0.f; val[q] = 0.f; }
+                    if (live) {
+                        const float4 h0 = *reinterpret_cast<const float4*>(hrow + c_lo + j), h1 = *reinterpret_cast<const float4*>(hrow + c_lo + j + 4);
+                        xh[0] = h0.x; xh[1] = h0.y; xh[2] = h0.z; xh[3] = h0.w; xh[4] = h1.x; xh[5] = h1.y; xh[6] = h1.z; xh[7] = h1.w;
+                        if (want_r) {
+                            float xn[8];
+                            const float4 x0 = *reinterpret_cast<const float4*>(xrow + c_lo + j), x1 = *reinterpret_cast<const float4*>(xrow + c_lo + j + 4);
+                            xn[0] = x0.x; xn[1] = x0.y; xn[2] = x0.z; xn[3] = x0.w; xn[4] = x1.x; xn[5] = x1.y; xn[6] = x1.z; xn[7] = x1.w;
+#pragma unroll
+                            for (int q = 0; q < 8; q++) {
+                                if (p.mean) xn[q] -= __ldg(p.mean + c_lo + j + q);
+                                xn[q] /= p.std_div;               // the reference divides: (x - mean) / std (qinco_base.py:533)
+                                val[q] = xn[q] - xh[q];
+                            }
+                            if (p.r) {
+                                *reinterpret_cast<float4*>(p.r + b * D + c_lo + j) = make_float4(val[0], val[1], val[2], val[3]);
+                                *reinterpret_cast<float4*>(p.r + b * D + c_lo + j + 4) = make_float4(val[4], val[5], val[6], val[7]);
+                            }
+                            if (pass == 1) {
+#pragma unroll
+                                for (int q = 0; q < 8; q++) rn = fmaf(val[q], val[q], rn);
+                            }
+                        }
+                    }
+                    const uint32_t kc = (uint32_t)((half * cw + j) >> 3);       // k-chunk inside the A chunk
+                    const uint32_t dst = sbase + kSmemA + kc * kAkc + (uint32_t)row * 16u;
+                    put_hi_lo(dst, dst + kAHalf, pass == 0 ? xh : val);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            // ---- weight parts of this chunk: thread 0 streams and issues
+            for (int part = 0; part < n_parts; part++, it++) {
+                const int np = min(kNp, N - part * kNp);
+                const uint32_t half_bytes = (uint32_t)np * (uint32_t)dc * 2u;
+                if (tid == 0) {
+                    const int buf = it & 1;
+                    const uint32_t bdst = sbase + kSmemB + (uint32_t)buf * 2u * kBHalf;
+                    const uint32_t full = smem_u32(&b_full[buf]);
+                    // the slot was read by the MMAs of iteration it - 2 (it - 1 is covered by the chunk-boundary wait or below)
+                    if (it >= 2) mbar_wait(smem_u32(&mma_done[buf]), (uint32_t)(((it - 2) >> 1) & 1), p.err_flag, 0x901);
+                    mbar_expect_tx(full, 2u * half_bytes);
+                    for (uint32_t o = 0; o < 2u * half_bytes; o += 32768u)
+                        bulk_g2s(bdst + o, pack + pack_off + o, min(32768u, 2u * half_bytes - o), full);
+                    mbar_wait(full, (uint32_t)((it >> 1) & 1), p.err_flag, 0x902);
+                    // D[:, part columns] (+)= a_hi . w_hi^T + a_lo . w_hi^T + a_hi . w_lo^T      (K = dc, in steps of 16)
+                    const uint32_t idesc = (1u << 4) | ((uint32_t)(np >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(part * kNp);
+                    const uint32_t a_hi = (((uint32_t)kAkc >> 4) << 16) | (((sbase + kSmemA) >> 4) & 0x3FFFu);
+                    const uint32_t a_lo = (((uint32_t)kAkc >> 4) << 16) | (((sbase + kSmemA + kAHalf) >> 4) & 0x3FFFu);
+                    const uint32_t w_hi = ((uint32_t)np << 16) | ((bdst >> 4) & 0x3FFFu);
+                    const uint32_t w_lo = ((uint32_t)np << 16) | (((bdst + half_bytes) >> 4) & 0x3FFFu);
+                    const uint32_t a_step = (2u * kAkc) >> 4, w_step = 2u * (uint32_t)np;
+                    uint32_t acc = c > 0 ? 1u : 0u;
+                    for (int g = 0; g < ((p.dbg & 2) ? 0 : 3); g++) {
+                        uint32_t a = g == 1 ? a_lo : a_hi, w = g == 2 ? w_lo : w_hi;
+                        for (int k = 0; k < dc; k += 16, a += a_step, w += w_step) {
+                            mma_f16(d_tmem, a, w, idesc, acc);
+                            acc = 1u;
+                        }
+                    }
+                    tc_commit(smem_u32(&mma_done[buf]));
+                }
+                pack_off += 2 * (size_t)half_bytes;
+            }
+        }
+        // ---- epilogue of the pass: wait for the last MMA group, then read the accumulators
+        mbar_wait(smem_u32(&mma_done[(it - 1) & 1]), (uint32_t)(((it - 1) >> 1) & 1), p.err_flag, 0x903);
+        tc_fence_after();
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);     // TMEM lane = row
+        if (pass == 0) {
+            // u_b: the two warps of a lane quarter split the De columns in 16-column units
+            const int units = De >> 4, u_lo = half ? units / 2 : 0, u_hi = half ? units : units / 2;
+            for (int un = u_lo; un < u_hi; un++) {
+                uint32_t v[16];
+                __syncwarp();
+                tmem_ld16(lane_addr + (uint32_t)(un * 16), v);
+                tmem_wait_ld();
+                if (live) {
+                    float4* dst = reinterpret_cast<float4*>(p.u + b * De + un * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                }
+            }
+            tc_fence_before();
+            __syncthreads();                 // the distance pass reuses the TMEM columns
+        } else {
+            // d[b][k] = (|r_b|^2 + |S_k|^2) - 2 g -> top-A
+            rn_part[half][row] = rn;
+            __syncthreads();
+            if (p.A <= 16 && !(p.dbg & 8)) {
+                // A <= 16 (every preset): each thread ranks its half of the row's candidates straight out of TMEM, 16 at a
+                // time (sort the batch, keep the 16 smallest of list + batch); the two halves of a row meet in shared memory
+                const float rnorm = rn_part[0][row] + rn_part[1][row];
+                float* sn = reinterpret_cast<float*>(smem);                       // |S_k|^2, staged once (operands are dead)
+                unsigned long long* xch = reinterpret_cast<unsigned long long*>(smem + 4096);     // [kRows][2][16]
+                for (int k = tid; k < p.K16; k += kThreads) sn[k] = k < K ? __ldg(p.sub_norm + k) : 0.f;
+                __syncthreads();
+                const int units = p.K16 >> 4, u_lo = half ? units / 2 : 0, u_hi = half ? units : units / 2;
+                unsigned long long best[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) best[i] = ~0ull;
+                for (int un = u_lo; un < ((p.dbg & 4) ? u_lo : u_hi); un++) {
+                    uint32_t v[16];
+                    __syncwarp();
+                    tmem_ld16(lane_addr + (uint32_t)(un * 16), v);
+                    tmem_wait_ld();
+                    unsigned long long key[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int k = un * 16 + i;
+                        const float d = (rnorm + sn[k]) - 2.f * __uint_as_float(v[i]);          // utils.py:346
+                        key[i] = k < K ? dist_key(d, k) : ~0ull;
+                    }
+                    if (!(p.dbg & 1)) {
+                        bitonic_sort16(key);
+                        keep_smallest16(best, key);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++) xch[(row * 2 + half) * 16 + i] = best[i];
+                tc_fence_before();
+                __syncthreads();
+                if (half == 0 && live) {
+                    unsigned long long other[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) other[i] = xch[(row * 2 + 1) * 16 + i];
+                    keep_smallest16(best, other);
+#pragma unroll
+                    for (int a = 0; a < 16; a++)
+                        if (a < p.A) p.idx[b * p.A + a] = (uint8_t)(best[a] & 0xffull);
+                }
+                continue;        // (pass 1 is the last pass)
+            }
+            // [kRows][K16 + 1] floats from the start of the dynamic region (operands and ring are dead now); the odd row
+            // stride keeps the per-row stores of a warp (same k, 32 rows) on 32 different banks
+            float* dpre = reinterpret_cast<float*>(smem);
+            const float rnorm = rn_part[0][row] + rn_part[1][row];
+            const int K16 = p.K16, ld = K16 + 1;
+            const int units = K16 >> 4, u_lo = half ? units / 2 : 0, u_hi = half ? units : units / 2;
+            for (int un = u_lo; un < ((p.dbg & 4) ? u_lo : u_hi); un++) {
+                uint32_t v[16];
+                __syncwarp();
+                tmem_ld16(lane_addr + (uint32_t)(un * 16), v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int k = un * 16 + i;
+                    dpre[row * ld + k] = k < K ? (rnorm + __ldg(p.sub_norm + k)) - 2.f * __uint_as_float(v[i]) : FLT_MAX;      // utils.py:346
+                }
+            }
+            tc_fence_before();
+            __syncthreads();
+            // the A smallest per row, ascending, ties to the lower index (torch.topk(largest=False)); a warp ranks FOUR rows at
+            // a time so that the shuffle latencies of their butterfly reductions overlap
+            constexpr int kRG = 4, kWarps = kThreads / 32;
+            for (int i0 = warp; i0 < nrow; i0 += kWarps * kRG) {
+                float vals[kRG][8];
+#pragma unroll
+                for (int g = 0; g < kRG; g++) {
+                    const int i = i0 + g * kWarps;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int k = lane + 32 * j;
+                        vals[g][j] = (i < nrow && k < K) ? dpre[i * ld + k] : FLT_MAX;
+                    }
+                }
+                for (int a = 0; a < ((p.dbg & 1) ? 0 : p.A); a++) {
+                    float bv[kRG];
+                    int bi[kRG];
+#pragma unroll
+                    for (int g = 0; g < kRG; g++) {
+                        bv[g] = FLT_MAX;
+                        bi[g] = 0x7fffffff;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const int k = lane + 32 * j;
+                            if (k < K && (vals[g][j] < bv[g] || (vals[g][j] == bv[g] && k < bi[g]))) { bv[g] = vals[g][j]; bi[g] = k; }
+                        }
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                        for (int g = 0; g < kRG; g++) {
+                            const float ov = __shfl_xor_sync(0xffffffffu, bv[g], off);
+                            const int oi = __shfl_xor_sync(0xffffffffu, bi[g], off);
+                            if (ov < bv[g] || (ov == bv[g] && oi < bi[g])) { bv[g] = ov; bi[g] = oi; }
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < kRG; g++) {
+                        const int i = i0 + g * kWarps;
+                        if (i >= nrow) continue;
+                        if (bi[g] >= K) bi[g] = 0;       // all-NaN row: stay in range
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            if (lane + 32 * j == bi[g]) vals[g][j] = FLT_MAX;
+                        if (lane == 0) p.idx[(b0 + i) * p.A + a] = (uint8_t)bi[g];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+}  // namespace
+
+static_assert(kRows * (256 + 1) * 4 <= kSmemTotal, "the distance matrix must fit the dynamic shared memory");
+
+cudaError_t launch_prep_tc(const PrepTcParams& p, cudaStream_t stream) {
+    if (p.n_beams <= 0) return cudaSuccess;
+    if (p.D % 16 || p.De % 16 || p.De > 512 || p.K > 256 || p.K16 % 16 || p.K16 < p.K) return cudaErrorInvalidValue;
+    static int attr_dev[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!attr_dev[dev]) {
+        e = cudaFuncSetAttribute(qb_prep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+        if (e != cudaSuccess) return e;
+        attr_dev[dev] = 1;
+    }
+    const int64_t grid = (p.n_beams + kRows - 1) / kRows;
+    qb_prep_tc_kernel<<<(unsigned)grid, kThreads, kSmemTotal, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace qb
