@@ -504,7 +504,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the beam16 / torch_gpu_baseline / c1 / small_batch blocks of the default line")
     ap.add_argument("--beam16-n", type=int, default=100_000, help="vectors per step of the beam16 block (BASELINE config 3)")
     ap.add_argument("--c1-rows", type=int, default=10_000, help="vectors of the config-1 block (QINCo1, CPU encode + decode)")
-    ap.add_argument("--plan-opts", default="", help="kernel planner overrides, e.g. slot_bytes=8192,pair=1,hc=64,max_stage=4 (pair: 0 auto, 1 off, 2 on)")
+    ap.add_argument("--plan-opts", default="", help="kernel planner overrides, e.g. slot_bytes=8192,pair=1,hc=64,max_stage=4 (pair / mcast: 0 auto, 1 off, 2 on)")
     args = ap.parse_args()
     if args.workload == "c5pw":
         args.warmup = max(args.warmup, 3)
@@ -536,7 +536,7 @@ def main():
     if args.plan_opts:
         kv = dict(t.split("=") for t in args.plan_opts.split(","))
         plan_opts = {k: int(v) for k, v in kv.items() if k in ("hc", "slot_bytes", "max_stage", "max_slab_k", "stagger")}
-        plan_opts["n_tiles"] = int(kv.get("n_tiles", 0)) | (int(kv.get("pair", 0)) << 8)
+        plan_opts["n_tiles"] = int(kv.get("n_tiles", 0)) | (int(kv.get("pair", 0)) << 8) | (int(kv.get("mcast", 0)) << 16)
     model = QINCo(cfg, w, device=dev, plan_opts=plan_opts)
     h = model._h
     x_pin = x_host.pin_memory()

@@ -563,7 +563,9 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         (void)mma;
     }
     qb::PlanOptions opt;
-    opt.hc = d->opt_hc; opt.n_tiles = d->opt_n_tiles & 0xff; opt.pair = d->opt_n_tiles >> 8;
+    opt.hc = d->opt_hc; opt.n_tiles = d->opt_n_tiles & 0xff; opt.pair = (d->opt_n_tiles >> 8) & 0xff; opt.mcast = (d->opt_n_tiles >> 16) & 0xff;
+    if (opt.mcast == 0)
+        if (const char* e = getenv("QB_MCAST")) opt.mcast = atoi(e);  // debug / A-B runs: 1 = off, 2 = on
     opt.slot_bytes = d->opt_slot_bytes;
     if (opt.pair == 0)
         if (const char* e = getenv("QB_PAIR")) opt.pair = atoi(e);   // debug / A-B runs: 1 = single-CTA kernel, 2 = force pairs
@@ -580,7 +582,7 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         std::vector<QbOp> lops;
         if (loop) {
             qb::PlanOptions lo = opt;
-            lo.uop = 1; lo.pair = 1; lo.hc = sd.plan.hc; lo.slot_bytes = sd.plan.slot_bytes;
+            lo.uop = 1; lo.pair = 1; lo.hc = sd.plan.hc; lo.slot_bytes = sd.plan.slot_bytes; lo.mcast = sd.plan.mcast ? 2 : 1;
             std::string lerr;
             loop = qb::make_step_plan(D, De, m->Dh, m->L, K, m->q1, lo, &sd.loop_plan, &lops, &lerr) == 0 &&
                    sd.loop_plan.n_ops_block == sd.plan.n_ops_block && sd.loop_plan.n_ops_out == sd.plan.n_ops_out &&
@@ -723,6 +725,17 @@ static int decode_impl(qb_model* m, const int32_t* ivf_codes_dev, const uint8_t*
     nc = std::min<int64_t>(nc, default_chunk(m) * 16);
     if (nc < 1) return fail(QB_ERR_WORKSPACE, "workspace too small for one vector; see qb_decode_workspace_bytes");
     if (nc >= 128) nc = nc / 128 * 128;
+    if (m->loop_ok && m->S > 1) {
+        // One-launch decode: the workspace is not used, so a launch may cover any number of vectors.  Models whose step
+        // weights together do not fit half the L2 (QINCo2-L: 7 x 9.4 MB) go in waves of ONE tile set per CTA: all CTAs then
+        // walk the steps in lockstep and stream the same ~10 MB at any time; with several sets per CTA they drift apart,
+        // the working set becomes every step's weights and the stream falls back to HBM (measured: 8.6 -> 6.9 ms per 100 k
+        // vectors of BASELINE config 3, and no more 2-5x outliers).
+        const QbStepPlan& lp = m->steps[1].loop_plan;
+        const int64_t wave = (int64_t)(lp.mcast ? (m->n_sm & ~1) : m->n_sm) * lp.n_tiles * QB_TILE_M;
+        const bool big = (int64_t)(m->S - 1) * lp.w_blob_bytes > (int64_t)24 << 20;
+        nc = big ? wave : std::max<int64_t>(nc, (int64_t)1 << 22);
+    }
     qb::DeviceGuard guard(m->device);
     QB_CUDA(guard.err);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

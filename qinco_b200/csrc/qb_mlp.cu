@@ -131,6 +131,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  : "memory");
 }
 
+// Multicast variant: the bytes land at the same CTA-relative offset in every CTA of `mask`, and each destination CTA's
+// mbarrier (same offset) gets the complete_tx.
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -139,6 +147,14 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// commit of cta_group::1 MMAs whose arrival goes to the barrier at the same offset in BOTH CTAs of a 2-CTA cluster (weight
+// multicast variant: a ring slot is recycled cluster-wide)
+__device__ __forceinline__ void tc_commit_mcast(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
 }
 
 // ---- CTA pair (cta_group::2): one M=256 MMA spans the two CTAs of a cluster; each CTA holds its own 128 rows of A and
@@ -433,8 +449,13 @@ struct Tracer {
 
 }  // namespace
 
-template <bool kScore, bool kResident, bool kPair, bool kLoop = false, int kFuse = 0>
+// kMcast: weight multicast over a 2-CTA cluster.  Both CTAs walk the same slab sequence; each streams HALF of every slab
+// and multicasts it into the ring slot of both (cp.async.bulk ... .multicast::cluster), so a slab crosses L2 -> SM once per
+// two CTAs while every MMA stays local (cta_group::1, no cross-CTA accumulator traffic as in the pair kernel).  A ring
+// slot is recycled when the MMA warps of BOTH CTAs have committed it (multicast tcgen05.commit).
+template <bool kScore, bool kResident, bool kPair, bool kLoop = false, int kFuse = 0, bool kMcast = false>
 __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_constant__ MlpParams p) {
+    static_assert(!kMcast || (!kPair && !kResident && kFuse == 0), "weight multicast: non-resident single-CTA-MMA variants");
     static_assert(!kLoop || (!kScore && !kResident && !kPair), "the decode loop is an apply-mode, single-CTA variant");
     static_assert(!kFuse || (kScore && !kPair && !kLoop), "fused selection lives in the single-CTA score variants");
     constexpr bool kFuseA = kFuse != 0 && kResident; // cross-CTA arg-min of a beam-1 vector over its four code-quarter CTAs
@@ -480,9 +501,9 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     // CTA pair: both CTAs walk the same number of sets (they share every MMA).  Resident mode gives both the same set
     // indices (adjacent code quarters); otherwise the peer's set is the leader's + 1 and may be past the end (all rows
     // invalid: it computes on row 0's operands and writes nothing).
-    const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+    const uint32_t cta_rank = (kPair || kMcast) ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
-    const int64_t set_lead_off = (kPair && !kResident) ? (int64_t)cta_rank : 0;
+    const int64_t set_lead_off = ((kPair || kMcast) && !kResident) ? (int64_t)cta_rank : 0;
     auto more_sets = [&](int64_t set) { return set - set_lead_off < n_sets; };
 
     // ---- one-time setup ------------------------------------------------------------------------------------------
@@ -503,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         for (int b = 0; b < 3; b++) { mbar_init(smem_u32(&rows_full[b]), 1); mbar_init(smem_u32(&rows_empty[b]), kEpiThreads); }
         for (int s = 0; s < QB_MAX_STAGE; s++) {
             mbar_init(smem_u32(&w_full[s]), (kPair && leader) ? 2 : 1);   // leader: own half landed + the peer's relay
-            mbar_init(smem_u32(&w_empty[s]), (uint32_t)pl.n_tiles);   // released by every tile slot's MMA warp
+            mbar_init(smem_u32(&w_empty[s]), (uint32_t)pl.n_tiles * (kMcast ? 2u : 1u));   // released by every tile slot's MMA warp (of both CTAs with multicast)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -522,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if (kPair) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them remotely
+    if (kPair || kMcast) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
     // Shared-window addresses, computed ONCE and made opaque to the compiler.  Left alone, it re-derives every
@@ -588,12 +609,18 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     for (uint32_t s = 0; s < n_slab; s++) {
                         // CTA pair: each CTA streams only its half of the slab's rows (packed half after half)
                         const uint32_t full = (s + 1 == n_slab) ? last_bytes : slab_bytes;
-                        const uint32_t bytes = kPair ? full >> 1 : full;
+                        const uint32_t bytes = (kPair || kMcast) ? full >> 1 : full;
                         mbar_wait((a_wempty + stage * 8u), phase ^ 1, p.err_flag, 0x100 + stage);
                         if (elect_one()) {
+                            if (kMcast) {       // the whole slab lands here: this CTA's half and the peer's, both multicast
+                                mbar_expect_tx((a_wfull + stage * 8u), full);
+                                bulk_g2s_mcast(smem_base + pl.smem_ring + stage * pl.slot_bytes + cta_rank * bytes,
+                                               src + (size_t)s * slab_bytes + cta_rank * bytes, bytes, (a_wfull + stage * 8u), (uint16_t)3);
+                            } else {
                             mbar_expect_tx((a_wfull + stage * 8u), bytes);
                             bulk_g2s(smem_base + pl.smem_ring + stage * pl.slot_bytes,
                                      src + (size_t)s * slab_bytes + (kPair ? cta_rank * bytes : 0u), bytes, (a_wfull + stage * 8u));
+                            }
                         }
                         __syncwarp();
                         if (++stage == (uint32_t)pl.n_stage) { stage = 0; phase ^= 1; }
@@ -789,7 +816,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                                     tc_commit_pair((a_wempty + stage * 8u));
                                     if (s + 1 == n_slab && commit_bar) tc_commit_pair(bar_addr(t, commit_bar));
                                 } else {
-                                    tc_commit((a_wempty + stage * 8u));
+                                    if (kMcast) tc_commit_mcast((a_wempty + stage * 8u)); else tc_commit((a_wempty + stage * 8u));
                                     if (s + 1 == n_slab && commit_bar) tc_commit(bar_addr(t, commit_bar));
                                 }
                             }
@@ -1434,7 +1461,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     // ---- teardown ------------------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (kPair) cluster_sync_all();      // no CTA of a pair leaves while the other may still signal its barriers / read its smem
+    if (kPair || kMcast) cluster_sync_all();      // no CTA of a pair leaves while the other may still signal its barriers / write its smem
     tc_fence_after();
     if (warp == kMmaWarp) {
         if (kPair)
@@ -1459,7 +1486,9 @@ cudaError_t mlp_set_smem_attr(int smem_bytes) {
     const void* fns[] = {(const void*)qb_mlp_kernel<true, false, false>, (const void*)qb_mlp_kernel<true, true, false>,
                          (const void*)qb_mlp_kernel<false, false, false>, (const void*)qb_mlp_kernel<true, false, true>,
                          (const void*)qb_mlp_kernel<true, true, true>, (const void*)qb_mlp_kernel<false, false, true>,
-                         (const void*)qb_mlp_kernel<false, false, false, true>, (const void*)qb_mlp_kernel<true, true, false, false, 1>, (const void*)qb_mlp_kernel<true, true, false, false, 2>};
+                         (const void*)qb_mlp_kernel<false, false, false, true>, (const void*)qb_mlp_kernel<true, true, false, false, 1>, (const void*)qb_mlp_kernel<true, true, false, false, 2>,
+                         (const void*)qb_mlp_kernel<true, false, false, false, 0, true>, (const void*)qb_mlp_kernel<false, false, false, false, 0, true>,
+                         (const void*)qb_mlp_kernel<false, false, false, true, 0, true>};
     for (const void* f : fns) {
         e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return e;
@@ -1485,6 +1514,7 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
     if (p.fuse == 2 && (!p.sel_cnt || !p.hist_out || !p.xhat_in)) return cudaErrorInvalidConfiguration;
     if (loop && (p.mode != QB_MODE_APPLY || pair || p.plan.n_ops_pre <= 0 || p.n_loop_steps > QB_MAX_LOOP_STEPS || p.plan.n_ochunk > 1))
         return cudaErrorInvalidConfiguration;
+    const bool mcast = p.plan.mcast != 0 && !pair && !resident && n_sm >= 2;     // weight multicast over 2-CTA clusters
     int grid;
     if (resident) {
         const int64_t sets = ((p.n_rows >> 8) + 3) / 4;       // per code quarter
@@ -1492,8 +1522,8 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
         grid = (int)(4 * per_quarter);                         // a multiple of 4: CTA pairs are code quarters (0,1) / (2,3)
     } else {
         grid = (int)(n_sets < n_sm ? n_sets : n_sm);
-        if (pair) grid = (grid + 1) & ~1;                      // whole pairs; a peer without work of its own follows its leader
-        if (pair && grid > n_sm) grid = n_sm & ~1;
+        if (pair || mcast) grid = (grid + 1) & ~1;             // whole pairs; a peer without work of its own follows its leader
+        if ((pair || mcast) && grid > n_sm) grid = n_sm & ~1;
     }
     auto launch = [&](const MlpParams& q0) {
         MlpParams q = q0;
@@ -1505,12 +1535,17 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = pair ? 2 : 1;
+        attr[0].val.clusterDim.x = (pair || mcast) ? 2 : 1;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        if (loop && mcast) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, false, true, 0, true>, q);
         if (loop) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, false, true>, q);
+        if (mcast) {
+            if (q.mode == QB_MODE_SCORE) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, false, false, 0, true>, q);
+            return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, false, false, 0, true>, q);
+        }
         if (pair) {
             if (resident) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, true, true>, q);
             if (q.mode == QB_MODE_SCORE) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, true>, q);

@@ -206,6 +206,9 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
         }
     }
     p->n_ops_pre = (int)ops->size() - p->n_ops_block - p->n_ops_out;
+    // Weight multicast (2-CTA clusters, each CTA streams half of every slab into both rings): auto = on for the shapes
+    // that run one tile per CTA (de = 384 ...), whose weight stream sits at the L2 -> SM limit; off with CTA pairs.
+    p->mcast = (!p->pair && (opt.mcast == 2 || (opt.mcast == 0 && n_tiles == 1))) ? 1 : 0;
     if (ops->size() > QB_MAX_OPS) { *err = "op list too long"; return -1; }
     for (const QbOp& op : *ops)
         if ((int)op.slab_bytes > (p->pair ? 2 : 1) * p->slot_bytes || op.n_slab < 1) { *err = "internal: slab larger than ring slot"; return -1; }
@@ -360,7 +363,7 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
                    int n_plan_out, void* ops_out, int max_ops) {
     qb::PlanOptions opt;
     if (opts5) {
-        opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = opts5[1] >> 8; opt.slot_bytes = opts5[2];
+        opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = (opts5[1] >> 8) & 0xff; opt.mcast = (opts5[1] >> 16) & 0xff; opt.slot_bytes = opts5[2];
         opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.uop = (opts5[3] >> 10) & 1; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
@@ -382,7 +385,7 @@ int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int
                  const float* const* down, const float* out_proj, uint16_t* blob, int64_t blob_halfs) {
     qb::PlanOptions opt;
     if (opts5) {
-        opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = opts5[1] >> 8; opt.slot_bytes = opts5[2];
+        opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = (opts5[1] >> 8) & 0xff; opt.mcast = (opts5[1] >> 16) & 0xff; opt.slot_bytes = opts5[2];
         opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.uop = (opts5[3] >> 10) & 1; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
@@ -397,7 +400,7 @@ int qb_plan_pack_pre(int D, int De, int Dh, int L, int K, int qinco1_mode, const
                      int64_t blob_halfs) {
     qb::PlanOptions opt;
     if (opts5) {
-        opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = opts5[1] >> 8; opt.slot_bytes = opts5[2];
+        opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = (opts5[1] >> 8) & 0xff; opt.mcast = (opts5[1] >> 16) & 0xff; opt.slot_bytes = opts5[2];
         opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.uop = (opts5[3] >> 10) & 1; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;

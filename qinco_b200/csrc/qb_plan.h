@@ -99,6 +99,8 @@ struct QbStepPlan {
     // ae_chunks = max(De, 2D) / 8 k-chunks.  0 pre-ops: a plain plan.
     int32_t n_ops_pre;
     int32_t ae_chunks;
+    int32_t mcast;           // 1: non-resident launches run as 2-CTA clusters that multicast the weight slabs (each CTA streams
+                             // half of every slab into both ring slots); needs slab halves that are multiples of 16 bytes
     int64_t block_w_bytes;   // packed weight bytes of one residual block
     int64_t w_blob_bytes;    // packed weight bytes for this step (L blocks + out_proj)
 };
