@@ -312,12 +312,29 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, int32_t*
             if (fuse) { p.sel_best = w.sel_best; p.sel_cnt = w.sel_cnt; }
             QB_CUDA(timed_launch(m, KIND_PREP, p.n_beams, st, [&] { return qb::launch_prep(p, st); }));
         }
+        // ... and for the one-tile-per-CTA shapes with a single out_proj chunk (QINCo2-L family) the whole selection: running
+        // top-F_out per vector and the winners' xhat' inside the score launch (qb_mlp_kernel<.., kFuse = 3>)
+        const int R = F_in * C;
+        const bool fuse_b = m->fuse_ok && !fuse && s.plan.n_tiles == 1 && s.plan.has_proj && s.plan.n_ochunk == 1 && !s.plan.pair &&
+                            s.plan.smem_total <= 196608 &&
+                            R >= 4 && ((R < QB_TILE_M && QB_TILE_M % R == 0) || R % QB_TILE_M == 0) && R / QB_TILE_M <= 255 &&
+                            F_out <= 32 && F_out <= R && (QB_TILE_M / std::min(R, QB_TILE_M)) * F_out * D <= 4096;
         {
             qb::MlpParams p = base_mlp(m, step);
             p.mode = qb::QB_MODE_SCORE;
             p.C = C; p.A = A;
             p.n_rows = n * F_in * C;
             p.idx = w.idx; p.u = w.u; p.r = w.r; p.dist = w.dist;
+            if (fuse_b) {
+                p.fuse = 3; p.F_in = F_in; p.F_out = F_out;
+                static const int fb_dbg = getenv("QB_FUSEB_DEBUG") ? atoi(getenv("QB_FUSEB_DEBUG")) : 0;
+                p.dbg = fb_dbg;
+                p.sel_spv = R > QB_TILE_M ? R / QB_TILE_M : 1;
+                p.hist_in = w.hist[cur]; p.hist_out = last ? codes : w.hist[cur ^ 1]; p.hist_M = M; p.hist_m = m->col(step);
+                p.xhat_in = w.xhat[cur];
+                p.xhat_out = (last && xhat_out) ? xhat_out : w.xhat[cur ^ 1];
+                p.dist = nullptr;
+            }
             if (fuse) {
                 p.fuse = m->fuse_mode; p.F_in = F_in; p.F_out = F_out;
                 p.sel_best = w.sel_best; p.sel_cnt = w.sel_cnt;
@@ -347,7 +364,7 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, int32_t*
                 }));
             }
         }
-        if (fuse) {
+        if (fuse || fuse_b) {
             cur ^= 1;
             F_in = F_out;
             continue;

@@ -71,7 +71,12 @@ struct MlpParams {
     //   CTAs; each keeps its local winner's o in shared memory, publishes (dist, code) with a packed 64-bit atomicMin on
     //   sel_best[v] and counts itself on sel_cnt[v]; one set later the select warp of the CTA that owns the global winner adds
     //   xhat_b and writes xhat' / the history.  sel_best / sel_cnt are initialised by the step's prep launch.
+    //   fuse == 3 (one-tile-per-CTA shapes with an out_proj, i.e. the QINCo2-L family): the sel_spv tiles of a vector are walked
+    //   back to back by one CTA, which keeps the vector's running top-F_out and the winners' xhat' in shared memory and emits
+    //   xhat' / history when the vector is complete -- no atomics, no second launch.
     int32_t fuse;
+    int32_t dbg;                    // timing experiments only (QB_FUSEB_DEBUG): skip phases of the fused selection
+    int32_t sel_spv;                // fuse == 3: tiles per vector (1 when a tile holds whole vectors)
     int32_t hist_M, hist_m;         // history row length, column written by this step
     unsigned long long* sel_best;   // [n vectors]  (dist bits << 32 | code)
     uint32_t* sel_cnt;              // [n vectors]

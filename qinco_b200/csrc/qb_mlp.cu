@@ -455,10 +455,18 @@ struct Tracer {
 // slot is recycled when the MMA warps of BOTH CTAs have committed it (multicast tcgen05.commit).
 template <bool kScore, bool kResident, bool kPair, bool kLoop = false, int kFuse = 0, bool kMcast = false>
 __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_constant__ MlpParams p) {
-    static_assert(!kMcast || (!kPair && !kResident && kFuse == 0), "weight multicast: non-resident single-CTA-MMA variants");
+    static_assert(!kMcast || (!kPair && !kResident && (kFuse == 0 || kFuse == 3)), "weight multicast: non-resident single-CTA-MMA variants");
     static_assert(!kLoop || (!kScore && !kResident && !kPair), "the decode loop is an apply-mode, single-CTA variant");
     static_assert(!kFuse || (kScore && !kPair && !kLoop), "fused selection lives in the single-CTA score variants");
-    constexpr bool kFuseA = kFuse != 0 && kResident; // cross-CTA arg-min of a beam-1 vector over its four code-quarter CTAs
+    constexpr bool kFuseB = kFuse == 3;              // in-CTA top-F_out + xhat' / history for one-tile-per-CTA shapes with out_proj
+    static_assert(!kFuseB || !kResident, "fused selection B is the non-resident variant");
+    // fused selection B: the winners' xhat' rows by stash slot, the running (sorted) candidate list of the vector(s) whose
+    // tiles this CTA is walking, the tile-local winners and the slot every tile row was granted (0xff: none)
+    __shared__ __align__(16) float selb_stash[kFuseB ? 4096 : 4];
+    __shared__ float selb_run_d[kFuseB ? 2 * 128 : 1];
+    __shared__ uint16_t selb_run_flat[kFuseB ? 2 * 128 : 1];
+    __shared__ uint8_t selb_run_slot[kFuseB ? 2 * 128 : 1], selb_lrow[kFuseB ? 128 : 1], selb_take[kFuseB ? 128 : 1], selb_nrun[kFuseB ? 128 : 1];
+    constexpr bool kFuseA = kFuse != 0 && kFuse != 3 && kResident; // cross-CTA arg-min of a beam-1 vector over its four code-quarter CTAs
     // fused selection, resident launches: the local winner's o of [buffer = set parity][tile slot][beam of the tile], its
     // packed (dist, code) key per lane quarter, and the epilogue <-> select-warp hand-off barriers per tile slot
     __shared__ __align__(16) float sel_stash[kFuseA ? (kFuse == 2 ? 2 * 2 * 2 * 128 : 2 * 2 * 256) : 4];
@@ -472,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     __shared__ __align__(8) uint64_t rows_full[3], rows_empty[3];   // resident mode: per-beam rows (u_b, r_b) of a set, 3 sets deep
     __shared__ __align__(16) float beam_rows[3][2][2][256];     // [buffer][tile slot][beam of the tile][u_b (De) | r_b (D)]
     __shared__ uint32_t tmem_base_s;
-    __shared__ float dist_part[2][kColGroups > 1 ? kColGroups - 1 : 1][QB_TILE_M];
+    __shared__ __align__(16) float dist_part[2][kColGroups > 1 ? kColGroups - 1 : 1][QB_TILE_M];
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (uniform datapath)
@@ -505,6 +513,15 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     const bool leader = cta_rank == 0;
     const int64_t set_lead_off = ((kPair || kMcast) && !kResident) ? (int64_t)cta_rank : 0;
     auto more_sets = [&](int64_t set) { return set - set_lead_off < n_sets; };
+    // Fused selection B walks the tiles of a vector back to back in ONE CTA (sel_spv tiles per vector, vectors strided over
+    // the CTAs) and gives every CTA the same number of iterations (sets past the end have no valid rows).
+    const int64_t fb_spv = kFuseB ? (int64_t)p.sel_spv : 1;
+    const int64_t fb_groups = kFuseB ? (n_tiles / fb_spv + (n_tiles % fb_spv ? 1 : 0)) : 0;
+    const int64_t fb_nit = kFuseB ? ((fb_groups + gridDim.x - 1) / gridDim.x) * fb_spv : 0;
+    auto fb_set_at = [&](int64_t it) { return ((it / fb_spv) * (int64_t)gridDim.x + blockIdx.x) * fb_spv + it % fb_spv; };
+#define QB_FOR_SETS(IT, SET)                                                                        \
+    for (int64_t IT = 0, SET = kFuseB ? fb_set_at(0) : set_first; kFuseB ? (IT < fb_nit) : more_sets(SET); \
+         IT++, SET = kFuseB ? fb_set_at(IT) : SET + set_stride)
 
     // ---- one-time setup ------------------------------------------------------------------------------------------
     if (tid == 0) {
@@ -594,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         };
         int64_t kset = 0;
         if (kResident) push_rows(set_first, 0);
-        for (int64_t set = set_first; more_sets(set); set += set_stride, kset++) {
+        QB_FOR_SETS(it_p, set) {
             if (kResident) push_rows(set + set_stride, kset + 1);
             for (int ls = 0; ls < n_ls; ls++)
             for (int l = kFirstPhase; l <= pl.L; l++) {
@@ -627,6 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     }
                 }
             }
+            kset++;
         }
     } else if (warp >= kMmaWarp) {
         // ======================================================================================= MMA issuers
@@ -760,7 +778,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             const uint32_t slot_lo = (uint32_t)pl.slot_bytes >> 4;
             const uint32_t tcol = tmem_base + (uint32_t)t * tile_cols;
             const uint32_t ae_lo = ((smem_base + pl.smem_ae[t]) >> 4) & 0x3FFFu;
-            for (int64_t set = set_first; more_sets(set); set += set_stride) {
+            QB_FOR_SETS(it_m, set) {
                 for (int ls = 0; ls < n_ls; ls++)
                 for (int l = kFirstPhase; l <= pl.L; l++) {
                     int i0, i1;
@@ -1086,7 +1104,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         int64_t beam0 = 0, beam1 = 0, row0 = 0, row1 = 0;
         bool valid0 = false, valid1 = false;
         bool primed = false;        // the current set's tiles were initialised by the previous iteration
-        for (int64_t set = set_first; more_sets(set); set += set_stride, kset++) {
+        QB_FOR_SETS(it_e, set) {
             const int rb = (int)(kset % 3);
             if (kResident && !primed) mbar_wait((a_rfull + (uint32_t)(rb) * 8u), (uint32_t)((kset / 3) & 1), p.err_flag, 0x610 + rb);
             auto row_ctx = [&](int64_t set, int t, int64_t& row, int64_t& beam, int& code, bool& valid) {
@@ -1438,6 +1456,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         for (int i = 0; i < 8; i++) cb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (pl.skip && c0 < c1) load_row32(cb, p.cb_blk, t ? code1 : code0, qq * pl.oc + c0, c1 - c0);
                         if (qq == 0 && cg == 0 && r * 32 < D) prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
+                        if (kFuseB && qq == 0 && cg == 1 && r * 32 < D) prefetch_l1(p.xhat_in + beam0 * D + r * 32);
                         wait_bar(t, QB_BAR_HACC_FULL, 0x414);
                         const uint32_t ta = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
                         float a = t ? acc1 : acc0;
@@ -1448,12 +1467,166 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     }
                 }
             }
-            if (pl.has_proj && kScore) {
+            if constexpr (kFuseB) {
+                // ================================================================= fused selection B (one tile per CTA, out_proj)
+                // reference QINCoStep.encode, qinco_base.py:343-372: distances -> topk(F_out) -> gathers of xhat' / history
+                const int R = p.F_in * p.C, seg = R < QB_TILE_M ? R : QB_TILE_M, vpt = QB_TILE_M / seg, F_out = p.F_out;
+                const int s_idx = r / seg, r_in = r - s_idx * seg;
+                const int seg_in_v = (int)(set % fb_spv);                         // which tile of its vector this is
+                const int64_t n_vec = p.n_rows / R;
+                const uint32_t a_sd = a_dist;                                     // dist totals of the tile: dist_part[0][0][..]
+                const uint32_t a_rd = opaque(smem_u32(&selb_run_d[0])), a_rf = opaque(smem_u32(&selb_run_flat[0]));
+                float a = acc0;
+                if (cg > 0) sts1(a_dist + (uint32_t)((cg - 1) * QB_TILE_M + r) * 4u, a);
+                named_bar_sync(5, kEpiThreads);
+                if (cg == 0) {
+#pragma unroll
+                    for (int g = 0; g < kColGroups - 1; g++) a += lds1(a_dist + (uint32_t)(g * QB_TILE_M + r) * 4u);
+                    if (!valid0) a = __uint_as_float(0x7f800000u);
+                    sts1(a_sd + (uint32_t)r * 4u, a);       // (the slot held this row's partial, which only this thread reads)
+                    selb_take[r] = 0xff;
+                }
+                named_bar_sync(5, kEpiThreads);                                   // totals published
+                if (cg == 0) {          // rank inside the segment, ties to the lower row (= lower flat index, like torch.topk)
+                    const uint32_t base = a_sd + (uint32_t)(s_idx * seg) * 4u;
+                    int cnt = 0;
+                    for (int j = 0; j < ((p.dbg & 4) ? 0 : seg); j += 4) {
+                        const float4 d4 = lds4(base + (uint32_t)j * 4u);
+                        cnt += (d4.x < a || (d4.x == a && j < r_in)) + (d4.y < a || (d4.y == a && j + 1 < r_in)) +
+                               (d4.z < a || (d4.z == a && j + 2 < r_in)) + (d4.w < a || (d4.w == a && j + 3 < r_in));
+                    }
+                    if (p.dbg & 4) cnt = r_in;
+                    if (cnt < F_out) {
+                        selb_lrow[s_idx * F_out + cnt] = (uint8_t)r;
+                        if (fb_spv == 1) {          // the tile holds the whole vector: the local ranking is final, slot = rank
+                            selb_take[r] = (uint8_t)cnt;
+                            selb_run_d[s_idx * F_out + cnt] = a;
+                            selb_run_flat[s_idx * F_out + cnt] = (uint16_t)r_in;
+                            selb_run_slot[s_idx * F_out + cnt] = (uint8_t)cnt;
+                        }
+                    }
+                    if (fb_spv == 1 && r_in == 0) selb_nrun[s_idx] = (uint8_t)F_out;
+                }
+                named_bar_sync(5, kEpiThreads);
+                if (fb_spv > 1) {
+                    if (warp == 0) {    // one warp merges the tile's sorted winners into the vector's sorted running list (<= 64 entries)
+                        const int lane = tid & 31;
+                        const int n_run = seg_in_v == 0 ? 0 : (int)selb_nrun[0], k_loc = F_out, total = n_run + k_loc;
+                        uint32_t used = 0, n_new_before = 0;
+                        float e_d[2]; int e_flat[2], e_slot[2], e_rank[2], e_lr[2]; bool e_new[2], e_surv[2];
+#pragma unroll
+                        for (int rr = 0; rr < 2; rr++) {
+                            const int e = lane + 32 * rr;
+                            e_surv[rr] = false; e_new[rr] = false; e_d[rr] = 0.f; e_flat[rr] = 0; e_slot[rr] = 0; e_rank[rr] = 0; e_lr[rr] = 0;
+                            if (e < total) {
+                                int before = 0;
+                                if (e < n_run) {            // running entry: local entries precede it only when strictly smaller
+                                    e_d[rr] = selb_run_d[e]; e_flat[rr] = selb_run_flat[e]; e_slot[rr] = selb_run_slot[e];
+                                    for (int j = 0; j < k_loc; j++) before += lds1(a_sd + (uint32_t)selb_lrow[j] * 4u) < e_d[rr];
+                                    e_rank[rr] = e + before;
+                                } else {                    // newcomer: running entries precede it on ties (earlier tile = lower flat index)
+                                    const int j = e - n_run;
+                                    e_lr[rr] = selb_lrow[j];
+                                    e_d[rr] = lds1(a_sd + (uint32_t)e_lr[rr] * 4u);
+                                    e_flat[rr] = seg_in_v * QB_TILE_M + e_lr[rr];
+                                    e_new[rr] = true;
+                                    for (int i = 0; i < n_run; i++) before += selb_run_d[i] <= e_d[rr];
+                                    e_rank[rr] = j + before;
+                                }
+                                e_surv[rr] = e_rank[rr] < F_out;
+                            }
+                            used |= __reduce_or_sync(0xffffffffu, (e_surv[rr] && !e_new[rr]) ? (1u << e_slot[rr]) : 0u);
+                        }
+                        const uint32_t free_slots = ~used;
+#pragma unroll
+                        for (int rr = 0; rr < 2; rr++) {
+                            const uint32_t nb = __ballot_sync(0xffffffffu, e_surv[rr] && e_new[rr]);
+                            if (e_surv[rr] && e_new[rr]) {
+                                const uint32_t t_idx = n_new_before + (uint32_t)__popc(nb & ((1u << lane) - 1u));
+                                e_slot[rr] = (int)__fns(free_slots, 0, (int)t_idx + 1);
+                                selb_take[e_lr[rr]] = (uint8_t)e_slot[rr];
+                            }
+                            n_new_before += (uint32_t)__popc(nb);
+                        }
+                        __syncwarp();       // every lane has read the old list: overwrite it in merged order
+#pragma unroll
+                        for (int rr = 0; rr < 2; rr++) {
+                            if (e_surv[rr]) {
+                                selb_run_d[e_rank[rr]] = e_d[rr];
+                                selb_run_flat[e_rank[rr]] = (uint16_t)e_flat[rr];
+                                selb_run_slot[e_rank[rr]] = (uint8_t)e_slot[rr];
+                            }
+                        }
+                        if (lane == 0) selb_nrun[0] = (uint8_t)(total < F_out ? total : F_out);
+                    }
+                    named_bar_sync(5, kEpiThreads);
+                }
+                {                       // the granted rows add xhat_parent to their o (still in TMEM) and park xhat' in the stash
+                    const int slot = (int)selb_take[r];
+                    if (!(p.dbg & 1) && __any_sync(0xffffffffu, slot != 0xff)) {
+                        int c0, c1;
+                        group_range(D, cg, c0, c1);
+                        const uint32_t ta = lane_base + (pl.has_proj ? pl.tmem_h_col : pl.tmem_e_col);
+                        const uint32_t st = opaque(smem_u32(&selb_stash[0])) + (uint32_t)((s_idx * F_out + (slot & 0x3f)) * D) * 4u;
+#pragma unroll 1
+                        for (int c = c0; c < c1; c += 32) {
+                            const int n = c1 - c;
+                            uint32_t v[32];
+                            tmem_ld_cols(ta + c, n, v);
+                            tmem_wait_ld();
+                            if (slot != 0xff) {
+                                const float* xp = p.xhat_in + beam0 * D + c;
+#pragma unroll
+                                for (int i = 0; i < 8; i++) {
+                                    if (4 * i < n) {
+                                        const float4 xi = ldg4(xp + 4 * i);
+                                        const float4 cv = pl.skip ? ldg4(p.cb_blk + ((size_t)((c >> 2) + i) * K + code0) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st + (uint32_t)(c + 4 * i) * 4u),
+                                                     "f"(xi.x + (__uint_as_float(v[4 * i]) + cv.x)), "f"(xi.y + (__uint_as_float(v[4 * i + 1]) + cv.y)),
+                                                     "f"(xi.z + (__uint_as_float(v[4 * i + 2]) + cv.z)), "f"(xi.w + (__uint_as_float(v[4 * i + 3]) + cv.w))
+                                                     : "memory");
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                if (seg_in_v == (int)fb_spv - 1 && !(p.dbg & 2)) {       // the vector(s) are complete: emit xhat' and the histories in rank order
+                    named_bar_sync(5, kEpiThreads);
+                    const int d4n = D >> 2;
+                    const int items = vpt * F_out * d4n;
+                    for (int it2 = tid; it2 < items; it2 += kEpiThreads) {
+                        const int d4 = it2 % d4n, e = it2 / d4n, sgm = e / F_out, j = e - sgm * F_out;
+                        const int64_t vs = fb_spv > 1 ? set / fb_spv : set * vpt + sgm;
+                        if (vs < n_vec && j < (int)selb_nrun[sgm]) {
+                            const int slot = selb_run_slot[sgm * F_out + j];
+                            const float4 xv = lds4(opaque(smem_u32(&selb_stash[0])) + (uint32_t)(((sgm * F_out + slot) * D) + 4 * d4) * 4u);
+                            *reinterpret_cast<float4*>(p.xhat_out + (vs * F_out + j) * D + 4 * d4) = xv;
+                        }
+                    }
+                    if (tid < vpt * F_out) {
+                        const int sgm = tid / F_out, j = tid - sgm * F_out;
+                        const int64_t vs = fb_spv > 1 ? set / fb_spv : set * vpt + sgm;
+                        if (vs < n_vec && j < (int)selb_nrun[sgm]) {
+                            const int flat = selb_run_flat[sgm * F_out + j];
+                            const int parent = flat / p.C, slot_a = flat - parent * p.C;
+                            const int code = p.A > 0 ? (int)__ldg(p.idx + (vs * p.F_in + parent) * p.A + slot_a) : slot_a;
+                            uint8_t* ho = p.hist_out + (vs * F_out + j) * p.hist_M;
+                            const uint8_t* hi = p.hist_in + (vs * p.F_in + parent) * p.hist_M;
+                            for (int c = 0; c < p.hist_m; c++) ho[c] = hi[c];
+                            ho[p.hist_m] = (uint8_t)code;
+                        }
+                    }
+                    (void)a_rd; (void)a_rf;
+                }
+            } else if (pl.has_proj && kScore) {
                 publish_dist(0, acc0, row0, valid0);
                 if (NT > 1) publish_dist(1, acc1, row1, valid1);
             }
             if (kResident) mbar_arrive((a_rempty + (uint32_t)(rb) * 8u));
             tr.ev(8);
+            kset++;
         }
         }   // !kLoop
     }
@@ -1488,9 +1661,16 @@ cudaError_t mlp_set_smem_attr(int smem_bytes) {
                          (const void*)qb_mlp_kernel<true, true, true>, (const void*)qb_mlp_kernel<false, false, true>,
                          (const void*)qb_mlp_kernel<false, false, false, true>, (const void*)qb_mlp_kernel<true, true, false, false, 1>, (const void*)qb_mlp_kernel<true, true, false, false, 2>,
                          (const void*)qb_mlp_kernel<true, false, false, false, 0, true>, (const void*)qb_mlp_kernel<false, false, false, false, 0, true>,
-                         (const void*)qb_mlp_kernel<false, false, false, true, 0, true>};
+                         (const void*)qb_mlp_kernel<false, false, false, true, 0, true>,
+                         (const void*)qb_mlp_kernel<true, false, false, false, 3, false>, (const void*)qb_mlp_kernel<true, false, false, false, 3, true>};
     for (const void* f : fns) {
-        e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        // variants with more static shared memory (fused selection B) can take less dynamic memory; the plans they run
+        // (one tile per CTA) stay below that, and launch_mlp refuses anything else
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, f);
+        if (e != cudaSuccess) return e;
+        const int cap = 232448 - (int)fa.sharedSizeBytes;
+        e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes < cap ? smem_bytes : cap);
         if (e != cudaSuccess) return e;
     }
     current[dev] = smem_bytes;
@@ -1510,6 +1690,15 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
     const bool loop = p.n_loop_steps > 0;
     // fused selection needs the resident score variant with one beam per vector, all its CTAs co-resident (they wait for
     // each other's reports) and the selection state; anything else must go through the unfused launches
+    if (p.fuse == 3) {      // in-CTA selection: one tile per CTA with a single out_proj chunk, whole vectors per tile or whole tiles per vector
+        const int R = p.F_in * p.C;
+        const int seg = R < QB_TILE_M ? R : QB_TILE_M, vpt = QB_TILE_M / seg;
+        if (p.mode != QB_MODE_SCORE || resident || pair || p.plan.n_tiles != 1 || !p.plan.has_proj || p.plan.n_ochunk != 1 ||
+            !((R < QB_TILE_M && QB_TILE_M % R == 0) || R % QB_TILE_M == 0) || p.sel_spv != (R > QB_TILE_M ? R / QB_TILE_M : 1) ||
+            p.plan.smem_total > 196608 || p.F_out > 32 || p.F_out > R || R < 4 || vpt * p.F_out * p.plan.D > 4096 || (int64_t)R * QB_TILE_M > 65535 * (int64_t)QB_TILE_M ||
+            !p.xhat_in || !p.xhat_out || !p.hist_out || !p.hist_in)
+            return cudaErrorInvalidConfiguration;
+    } else
     if (p.fuse && (!resident || pair || p.F_in != 1 || p.F_out != 1 || !p.sel_best || p.plan.D > 128)) return cudaErrorInvalidConfiguration;
     if (p.fuse == 2 && (!p.sel_cnt || !p.hist_out || !p.xhat_in)) return cudaErrorInvalidConfiguration;
     if (loop && (p.mode != QB_MODE_APPLY || pair || p.plan.n_ops_pre <= 0 || p.n_loop_steps > QB_MAX_LOOP_STEPS || p.plan.n_ochunk > 1))
@@ -1522,6 +1711,10 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
         grid = (int)(4 * per_quarter);                         // a multiple of 4: CTA pairs are code quarters (0,1) / (2,3)
     } else {
         grid = (int)(n_sets < n_sm ? n_sets : n_sm);
+        if (p.fuse == 3) {          // vectors (groups of sel_spv tiles) are strided over the CTAs
+            const int64_t groups = (n_sets + p.sel_spv - 1) / p.sel_spv;
+            grid = (int)(groups < n_sm ? groups : n_sm);
+        }
         if (pair || mcast) grid = (grid + 1) & ~1;             // whole pairs; a peer without work of its own follows its leader
         if ((pair || mcast) && grid > n_sm) grid = n_sm & ~1;
     }
@@ -1542,6 +1735,10 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
         cfg.numAttrs = 1;
         if (loop && mcast) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, false, true, 0, true>, q);
         if (loop) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, false, true>, q);
+        if (q.fuse == 3) {
+            if (mcast) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, false, false, 3, true>, q);
+            return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, false, false, 3, false>, q);
+        }
         if (mcast) {
             if (q.mode == QB_MODE_SCORE) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, false, false, 0, true>, q);
             return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, false, false, 0, true>, q);

@@ -86,7 +86,9 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     // two tiles in flight share every weight slab: they need 2x the TMEM columns and 2x the A_E tile
     int n_tiles = opt.n_tiles > 0 ? opt.n_tiles : 2;
     if (n_tiles > 2) { *err = "n_tiles must be 1 or 2"; return -1; }
-    const int budget = opt.smem_budget > 0 ? opt.smem_budget : 208 * 1024;   // + <= 15 KB static (barriers, beam rows) <= 227 KB
+    int budget = opt.smem_budget > 0 ? opt.smem_budget : 208 * 1024;   // + <= 15 KB static (barriers, beam rows) <= 227 KB
+    // shapes the fused-selection-B kernel serves (one tile per CTA, whole out_proj in one chunk) leave it 16 KB for its stash
+    if (opt.smem_budget <= 0 && De != D && D <= (opt.hc > 0 ? opt.hc : 128) && 2 * (e_cols + h_cols) > 512) budget = 192 * 1024;
     if (n_tiles == 2 && (2 * (e_cols + h_cols) > 512 || budget - 2 * ae_bytes < 4 * p->slot_bytes)) {
         if (opt.n_tiles == 2) { *err = "two tiles in flight do not fit (TMEM columns or shared memory)"; return -1; }
         n_tiles = 1;

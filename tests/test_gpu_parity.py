@@ -592,13 +592,15 @@ def test_decode_loop_kernel(name, golden_loader, monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------------ fused beam selection
-@pytest.mark.parametrize("mode", ["lite", "full"])
-@pytest.mark.parametrize("name", ["s_a0_b1", "q1_l4", "ivf_a0_b1"])
+@pytest.mark.parametrize("name,mode", [("s_a0_b1", "lite"), ("q1_l4", "lite"), ("ivf_a0_b1", "lite"), ("s_a0_b1", "full"),
+                                       ("q1_l4", "full"), ("ivf_a0_b1", "full"), ("l_a16_b16", "b"), ("proj_a8_b4", "b"),
+                                       ("full_l_b16", "b"), ("full_deep_m16", "b")])
 def test_fused_selection_matches_unfused(name, mode, golden_loader, monkeypatch):
     """Selection fused into the score launch (distance -> arg-min inside the kernel, no `dist` array, no select launch;
     reference qinco_base.py:343-372) against the unfused launch sequence.  The arithmetic is the same, so codes AND xhat must
-    be bit-identical.  `lite` (default): the winner's xhat' comes from a 1/256-size update launch; `full` (QB_FUSE_FULL=1):
-    the score launch writes xhat' and the history itself."""
+    be bit-identical.  `lite` (default for beam-1 resident launches): the winner's xhat' comes from a 1/256-size update
+    launch; `full` (QB_FUSE_FULL=1): the score launch writes xhat' and the history itself; `b` (default for the QINCo2-L
+    family): running top-F_out per vector and the winners' xhat' inside the score launch, tiles of a vector walked by one CTA."""
     from qinco_b200.model import QINCo
     cfg, w, z = golden_loader(name)
     if mode == "full":
@@ -612,7 +614,7 @@ def test_fused_selection_matches_unfused(name, mode, golden_loader, monkeypatch)
         ivf = bool(cfg.get("ivf_K"))
         enc = (lambda m, x: m.encode_ivf_u8(x)) if ivf else (lambda m, x: (None,) + m.encode_u8(x))
         steps = cfg["M"] - (0 if ivf else 1)
-        for n in (len(z["x"]), 1, 129, 39999):
+        for n in ((len(z["x"]), 1, 129, 39999) if mode != "b" else (len(z["x"]), 1, 300, 2049)):
             x = torch.from_numpy(synth.make_data(n, cfg["D"], seed=n)).cuda() if n != len(z["x"]) else \
                 torch.from_numpy((z["x"] - w["data_mean"]) / np.float32(w["data_std"])).cuda()
             l0, p0 = fused.launch_count, plain.launch_count
@@ -627,6 +629,8 @@ def test_fused_selection_matches_unfused(name, mode, golden_loader, monkeypatch)
                 assert torch.equal(iv_a, iv_b)
             if n < 128:          # one chunk: step 0, then per step prep + score (+ the update launch in lite mode) vs 4 launches
                 assert n_plain == 1 + 4 * steps and n_fused == 1 + (3 if mode == "lite" else 2) * steps, (n_plain, n_fused)
+                if mode == "b":
+                    assert fused._h.info(1)["n_tiles"] == 1
         # codes only (no xhat wanted)
         c_only = fused(torch.from_numpy(z["x"]).cuda(), step="encode")
         fused.synchronize()
