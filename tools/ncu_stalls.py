@@ -16,7 +16,7 @@ for r in rows[2:]:
     for i, h in enumerate(hdr):
         if any(h.endswith(w) or h == w for w in want):
             print(f"  {h:90s} {units[i]:12s} {r[i]}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-id", sys.argv[2]] if len(sys.argv) > 2 else []), capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-id", sys.argv[2]] if len(sys.argv) > 2 and sys.argv[2] not in ("", "-") else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = None
 data = []
