@@ -37,6 +37,7 @@ WORKLOADS = {
     "c4": dict(name="QINCo2-L 16x8 K=256 d=96 (Deep1B shape) A=16 beam=16", cfg=dict(D=96, M=16, K=256, L=16, de=384, dh=384, A=16, B=16, qinco1_mode=False), n=50_000),
     "c5": dict(name="QINCo2-L 8x8 K=256 d=768 (Contriever shape) A=16 beam=32", cfg=dict(D=768, M=8, K=256, L=16, de=384, dh=384, A=16, B=32, qinco1_mode=False), n=50_000),
     "livf": dict(name="IVF-QINCo2-L 8x8 K=256 d=128 A=16 beam=16, IVF 65536 centroids", cfg=dict(D=128, M=8, K=256, L=16, de=384, dh=384, A=16, B=16, qinco1_mode=False, ivf_K=65536), n=50_000),
+    "ivf1m": dict(name="IVF-QINCo2-S 8x8 K=256 d=128 A=16 beam=1, IVF 1048576 centroids (billion-scale index shape)", cfg=dict(D=128, M=8, K=256, L=2, de=128, dh=256, A=16, B=1, qinco1_mode=False, ivf_K=1 << 20), n=189_440),      # 10 waves of 148 x 128 vectors
     "q1": dict(name="QINCo1 8x8 K=256 d=128 L=16 beam=1", cfg=dict(D=128, M=8, K=256, L=16, de=128, dh=256, A=0, B=1, qinco1_mode=True), n=200_000),
 }
 
@@ -119,15 +120,17 @@ def make_model_inputs(wl, n, rank):
     import torch
     from qinco_b200 import synth
     cfg = synth.make_cfg(None, **wl["cfg"])
-    w = synth.make_weights(cfg, seed=4321, gain=0.5, n_train=8192, kmeans_iters=1 if cfg.get("ivf_K") else 3)
+    w = synth.make_weights(cfg, seed=4321, gain=0.5, n_train=8192 if (cfg.get("ivf_K") or 0) <= 65536 else 2048,
+                           kmeans_iters=1 if cfg.get("ivf_K") else 3)
     g = torch.Generator().manual_seed(1234 + rank)
     x = torch.randn(n, cfg["D"], generator=g, dtype=torch.float32)
     return cfg, w, x
 
 
 def contract_sample(cfg):
-    """SURVEY.md section 8(d) "Parity subsets": the first 10 000 rows for the small models (S / QINCo1), 1 024 for QINCo2-L."""
-    return 1024 if cfg["de"] >= 384 else 10000
+    """SURVEY.md section 8(d) "Parity subsets": the first 10 000 rows for the small models (S / QINCo1), 1 024 for QINCo2-L
+    (and for models with a 2^20-centroid IVF step, whose CPU arg-min alone is 268 MFLOP per vector)."""
+    return 1024 if (cfg["de"] >= 384 or (cfg.get("ivf_K") or 0) > 65536) else 10000
 
 
 def cpu_port_rate(cfg, w, x_np):
@@ -672,6 +675,17 @@ def main():
             out["e2e"] = e2e
         if dec:
             out["decode"] = dec
+        if ivf and kinds["ivf"][1] > 0:
+            # the IVF arg-min launch on its own: useful flops = 2 D ivf_K per vector (what an fp32 evaluation costs; the kernel
+            # issues three fp16 products per useful one), graded against the tf32 rate = half the measured bf16 peak
+            ms_ivf, n_ivf, rows_ivf = kinds["ivf"]
+            useful = rows_ivf * 2.0 * cfg["D"] * cfg["ivf_K"] / (ms_ivf * 1e-3) / 1e12
+            out["ivf"] = {"kernel": "qb_ivf_tc_kernel" if cfg["D"] <= 128 else "qb_ivf_assign_kernel", "centroids": cfg["ivf_K"],
+                          "ms_per_step": ms_ivf / args.steps, "vectors_per_s_ivf_only": rows_ivf / (ms_ivf * 1e-3),
+                          "useful_tflops": useful, "issued_tflops_fp16": 3 * useful if cfg["D"] <= 128 else None,
+                          "roofline": {"bound": "tensor", "peak": peaks["tflops"] / 2, "unit": "TFLOP/s (tf32-equivalent)",
+                                       "achieved": useful, "frac": useful / (peaks["tflops"] / 2),
+                                       "peak_source": "half of " + peaks["source"]}}
         if world == 1 and not args.no_cpu_baseline:
             ns = min(n, contract_sample(cfg))
             rate, n_s, ref_codes, ref_xhat, threads, port, dec_rate = cpu_port_rate(cfg, w, x_host[:ns].numpy())

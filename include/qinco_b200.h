@@ -131,7 +131,7 @@ int qb_check(qb_model* m);
 int64_t qb_launch_count(const qb_model* m);      /* kernels launched by this model so far */
 /* Per-kernel device timing for bench.py's roofline block: with timing on, every launch is bracketed by CUDA events on
  * its own stream; qb_timing_read waits for them and returns, per kernel kind {0 prep, 1 mlp-score, 2 select,
- * 3 mlp-apply, 4 other}, the summed milliseconds, launch count and rows processed since the last read. */
+ * 3 mlp-apply (update), 4 other, 5 IVF arg-min}, the summed milliseconds, launch count and rows processed since the last read. */
 int qb_timing_enable(qb_model* m, int on);
 int qb_timing_read(qb_model* m, double* ms_out, int64_t* launches_out, int64_t* rows_out, int n_kinds);
 int qb_model_info(const qb_model* m, int step, int32_t* out, int n_out); /* plan of step>=1: see qb_api.cu */

@@ -77,7 +77,9 @@ class TorchPort:
         ivf = bool(cfg.get("ivf_K"))
         if ivf:                                          # IVFBook.quantize (qinco_base.py:146-163): arg-min, one beam
             M = M + 1                                    # cfg._M_ivf
-            c0 = self.pairwise(x, self.w["steps.0.ivf_centroids.weight"]).argmin(-1, keepdim=True)
+            cent = self.w["steps.0.ivf_centroids.weight"]
+            rows = max(1, (1 << 30) // len(cent))        # IVFBook.quantize batches rows the same way (qinco_base.py:149-156)
+            c0 = torch.cat([self.pairwise(x[i:i + rows], cent).argmin(-1, keepdim=True) for i in range(0, max(n, 1), rows)])
             xhat = self.w["steps.0.ivf_centroids.weight"][c0]
         else:
             F1 = B if M > 1 else 1

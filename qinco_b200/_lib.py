@@ -265,7 +265,7 @@ class Handle:
     def check(self):
         check(self._lib.qb_check(self._h))
 
-    KINDS = ["prep", "mlp_score", "select", "mlp_apply", "other"]
+    KINDS = ["prep", "mlp_score", "select", "mlp_apply", "other", "ivf"]
 
     def timing_enable(self, on: bool = True):
         check(self._lib.qb_timing_enable(self._h, int(on)))

@@ -16,8 +16,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libqinco_b200.so")
-SOURCES = ["qb_api.cu", "qb_mlp.cu", "qb_kernels.cu", "qb_prep_tc.cu", "qb_pairwise.cu", "qb_plan.cpp"]
-HEADERS = ["qb_dev.h", "qb_host.h", "qb_plan.h", os.path.join(ROOT, "include", "qinco_b200.h")]
+SOURCES = ["qb_api.cu", "qb_mlp.cu", "qb_kernels.cu", "qb_prep_tc.cu", "qb_ivf_tc.cu", "qb_pairwise.cu", "qb_plan.cpp"]
+HEADERS = ["qb_dev.h", "qb_host.h", "qb_plan.h", "qb_tc_util.h", os.path.join(ROOT, "include", "qinco_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
 

@@ -84,6 +84,7 @@ struct qb_model {
     // M = uint8 codes per vector.  S = quantisation steps: M, or M + 1 with an IVF first step (then step s >= 1 writes
     // code column s - 1 and the IVF code lives in its own int32 array).
     int S = 0, ivf_K = 0;
+    uint8_t* ivf_pack = nullptr;  // tensor-core arg-min operand parts (qb_ivf_tc.cu), or NULL: the fp32 CUDA-core kernel
     float* ivf_cent = nullptr;    // [ivf_K][D]
     float* ivf_cnorm = nullptr;   // [ivf_K]
     int col(int step) const { return ivf_K ? step - 1 : step; }
@@ -209,7 +210,7 @@ void carve(const qb_model* m, void* ws, int64_t nc, Workspace* w) {
     w->sel_cnt = (uint32_t*)take(n * 4);
 }
 
-enum { KIND_PREP = 0, KIND_SCORE = 1, KIND_SELECT = 2, KIND_APPLY = 3, KIND_OTHER = 4, KIND_COUNT = 5 };
+enum { KIND_PREP = 0, KIND_SCORE = 1, KIND_SELECT = 2, KIND_APPLY = 3, KIND_OTHER = 4, KIND_IVF = 5, KIND_COUNT = 6 };
 
 cudaEvent_t take_event(qb_model* m) {
     if (!m->ev_pool.empty()) {
@@ -262,12 +263,18 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, int32_t*
     const int S = m->S;
     // ---- step 0 (qinco_base.py:218,263; qinco_inference.py:239-246), or the IVF arg-min (IVFBook.encode, :165-174; F = 1)
     const int F1 = m->ivf_K ? 1 : ((M == 1) ? 1 : B);
-    if (m->ivf_K) {
+    if (m->ivf_K && m->ivf_pack) {
+        qb::IvfTcParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.D = D; p.ivf_K = m->ivf_K; p.n = n; p.x = x; p.mean = mean; p.std_div = inv_std_div;
+        p.cent_pack = m->ivf_pack; p.cent = m->ivf_cent; p.codes_out = ivf_codes; p.xhat_out = w.xhat[cur]; p.err_flag = m->err_dev;
+        QB_CUDA(timed_launch(m, KIND_IVF, n, st, [&] { return qb::launch_ivf_tc(p, st); }));
+    } else if (m->ivf_K) {
         qb::IvfParams p;
         std::memset(&p, 0, sizeof(p));
         p.D = D; p.ivf_K = m->ivf_K; p.n = n; p.x = x; p.mean = mean; p.std_div = inv_std_div;
         p.cent = m->ivf_cent; p.cnorm = m->ivf_cnorm; p.codes_out = ivf_codes; p.xhat_out = w.xhat[cur];
-        QB_CUDA(timed_launch(m, KIND_PREP, n, st, [&] { return qb::launch_ivf_assign(p, st); }));
+        QB_CUDA(timed_launch(m, KIND_IVF, n, st, [&] { return qb::launch_ivf_assign(p, st); }));
     } else {
         qb::PrepParams p;
         std::memset(&p, 0, sizeof(p));
@@ -561,6 +568,11 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         for (int k = 0; k < m->ivf_K; k++) cn[k] = row_norm2(d->ivf_centroids + (size_t)k * D, D);
         if ((rc = dev_upload(m, d->ivf_centroids, (size_t)m->ivf_K * D, &m->ivf_cent))) return bail(rc);
         if ((rc = dev_upload(m, cn.data(), cn.size(), &m->ivf_cnorm))) return bail(rc);
+        if (D <= QB_IVF_TC_MAX_D && !getenv("QB_IVF_CC")) {       // (QB_IVF_CC=1: keep the fp32 CUDA-core arg-min, for A/B runs)
+            std::vector<uint8_t> pk(qb::ivf_pack_bytes(m->ivf_K, D));
+            qb::ivf_pack(d->ivf_centroids, m->ivf_K, D, pk.data());
+            if ((rc = dev_upload(m, pk.data(), pk.size(), &m->ivf_pack))) return bail(rc);
+        }
     } else {            // step 0: plain codebook and its squared row norms
         std::vector<float> nrm((size_t)K);
         for (int k = 0; k < K; k++) nrm[k] = row_norm2(d->codebook[0] + (size_t)k * D, D);

@@ -182,6 +182,25 @@ struct IvfParams {
     float* xhat_out;          // [n, D]
 };
 cudaError_t launch_ivf_assign(const IvfParams& p, cudaStream_t stream);
+
+// The same arg-min on the tensor core (qb_ivf_tc.cu) for D <= QB_IVF_TC_MAX_D: centroids pre-packed (ivf_pack) in parts of
+// QB_IVF_NP: [c_hi | c_lo] as K-major fp16 core matrices [D/8][NP][8] each, then the NP squared norms (fp32; +max for the
+// padding rows of the last part).
+#define QB_IVF_NP 128
+#define QB_IVF_TC_MAX_D 128
+struct IvfTcParams {
+    int32_t D, ivf_K;
+    int64_t n;
+    const float* x;
+    const float* mean;
+    float std_div;
+    const uint8_t* cent_pack;  // [ceil(ivf_K / NP)] parts of (NP * D * 4 + NP * 4) bytes
+    const float* cent;         // [ivf_K, D] fp32 (the lookup)
+    int32_t* codes_out;
+    float* xhat_out;
+    uint32_t* err_flag;
+};
+cudaError_t launch_ivf_tc(const IvfTcParams& p, cudaStream_t stream);
 // xhat[v] = centroids[ivf_codes[v]]  (IVFBook.decode, qinco_base.py:176-183)
 cudaError_t launch_ivf_lookup(const float* cent, const int32_t* ivf_codes, int64_t n, int D, int ivf_K, float* xhat,
                               uint32_t* err_flag, cudaStream_t stream);

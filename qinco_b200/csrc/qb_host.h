@@ -40,6 +40,10 @@ int pack_pre_weights(const QbStepPlan& plan, const std::vector<QbOp>& ops, const
 size_t prep_pack_bytes(int n_rows, int D);
 void prep_pack(const float* w, int n_rows, int D, uint16_t* out);
 
+// operand blob of the tensor-core IVF arg-min (layout: qb_dev.h, IvfTcParams)
+size_t ivf_pack_bytes(int ivf_K, int D);
+void ivf_pack(const float* cent, int ivf_K, int D, uint8_t* out);
+
 void build_tables(int D, int De, int K, const float* codebook, const float* in_proj, const float* concat_w,
                   const float* concat_b, float* t_blk, float* cb_blk, float* wx_t);
 

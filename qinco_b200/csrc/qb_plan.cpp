@@ -327,6 +327,35 @@ void prep_pack(const float* w, int n_rows, int D, uint16_t* out) {
     }
 }
 
+size_t ivf_pack_bytes(int ivf_K, int D) {
+    constexpr int kNp = 128;                    // QB_IVF_NP
+    return (size_t)((ivf_K + kNp - 1) / kNp) * ((size_t)kNp * D * 4 + kNp * 4);
+}
+
+void ivf_pack(const float* cent, int ivf_K, int D, uint8_t* out) {
+    constexpr int kNp = 128;
+    const size_t part_bytes = (size_t)kNp * D * 4 + kNp * 4;
+    for (int k0 = 0, part = 0; k0 < ivf_K; k0 += kNp, part++) {
+        uint16_t* hi = reinterpret_cast<uint16_t*>(out + (size_t)part * part_bytes);
+        uint16_t* lo = hi + (size_t)kNp * D;
+        float* cn = reinterpret_cast<float*>(out + (size_t)part * part_bytes + (size_t)kNp * D * 4);
+        for (int r = 0; r < kNp; r++) {
+            const bool real = k0 + r < ivf_K;
+            const float* c = cent + (size_t)(k0 + r) * D;
+            float nrm = 0.f;                     // fp32 like the reference's (b ** 2).sum(-1)
+            for (int d = 0; d < D; d++) {
+                const float v = real ? c[d] : 0.f;
+                nrm += v * v;
+                const uint16_t h = f32_to_f16(v);
+                const size_t at = ((size_t)(d / 8) * kNp + r) * 8 + (d % 8);
+                hi[at] = h;
+                lo[at] = f32_to_f16(v - f16_to_f32(h));
+            }
+            cn[r] = real ? nrm : 3.0e38f;
+        }
+    }
+}
+
 // T_m[k] = e0 + Wcat[:, :De] . e0 + bcat,  e0 = Pin . C_m[k]   (double accumulation, stored fp32, blocked [De/4][K][4]:
 // consecutive codes are 16 B apart, so a warp whose lanes hold consecutive codes gathers 512 contiguous bytes)
 void build_tables(int D, int De, int K, const float* codebook, const float* in_proj, const float* concat_w,

@@ -101,6 +101,19 @@ def make_weights(cfg: dict, seed: int = 4321, gain: float = 0.5, n_train: int = 
     resid = xt
     for m in range(n_steps):
         if ivf_K and m == 0:                 # frozen IVF centroids (qinco_base.py:128-146), key as in IVFBook
+            if ivf_K > 65536:                # billion-scale shape (2^20 centroids): k-means is pointless on synthetic data --
+                cb = rng.standard_normal((ivf_K, D), dtype=np.float32) * np.float32(0.9)      # distinct Gaussian centroids
+                best_d = np.full(len(resid), np.inf, np.float32)
+                best_k = np.zeros(len(resid), np.int64)
+                for k0 in range(0, ivf_K, 65536):                                             # arg-min in centroid slabs
+                    d = _sqdist(resid, cb[k0:k0 + 65536])
+                    a = d.argmin(1)
+                    dm = d[np.arange(len(resid)), a]
+                    upd = dm < best_d
+                    best_d[upd], best_k[upd] = dm[upd], a[upd] + k0
+                w["steps.0.ivf_centroids.weight"] = cb
+                resid = resid - cb[best_k]
+                continue
             cb = _kmeans(resid, ivf_K, kmeans_iters, rng).astype(np.float32)
             cb += rng.standard_normal(cb.shape, dtype=np.float32) * np.float32(0.02 * cb.std())
             w["steps.0.ivf_centroids.weight"] = cb

