@@ -93,6 +93,7 @@ struct qb_model {
     bool has_mean = false;
     float* cb0 = nullptr;      // [K][D]
     float* cb0_norm = nullptr; // [K] squared row norms of cb0
+    uint8_t* cb0_pack = nullptr;  // C_0 as tensor-core operand parts (qb_prep_tc.cu), step 0
     float* mean = nullptr;     // [D]
     std::vector<StepDev> steps;   // index m, entry 0 unused
     bool fuse_ok = true;          // fused beam selection inside the score launch (QB_NO_FUSE=1 keeps the unfused sequence for A/B runs)
@@ -275,6 +276,15 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, int32_t*
         p.D = D; p.ivf_K = m->ivf_K; p.n = n; p.x = x; p.mean = mean; p.std_div = inv_std_div;
         p.cent = m->ivf_cent; p.cnorm = m->ivf_cnorm; p.codes_out = ivf_codes; p.xhat_out = w.xhat[cur];
         QB_CUDA(timed_launch(m, KIND_IVF, n, st, [&] { return qb::launch_ivf_assign(p, st); }));
+    } else if (m->prep_tc && F1 <= 16) {     // step 0 on the tensor core: distances to C_0, the F_1 nearest start the beams
+        qb::PrepTcParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.D = D; p.De = m->De; p.K = K; p.K16 = (K + 15) / 16 * 16; p.A = F1; p.F = 1; p.step0 = 1; p.M = M;
+        p.n_beams = n; p.x = x; p.mean = mean; p.std_div = inv_std_div;
+        p.sub_pack = m->cb0_pack; p.sub_norm = m->cb0_norm; p.cb0 = m->cb0; p.err_flag = m->err_dev;
+        p.xhat_out = (M == 1 && xhat_out) ? xhat_out : w.xhat[cur];
+        p.hist_out = (M == 1) ? codes : w.hist[cur];
+        QB_CUDA(timed_launch(m, KIND_PREP, n, st, [&] { return qb::launch_prep_tc(p, st); }));
     } else {
         qb::PrepParams p;
         std::memset(&p, 0, sizeof(p));
@@ -305,8 +315,6 @@ int encode_chunk(qb_model* m, const float* x, int64_t n, int normalize, int32_t*
             p.n_beams = n * F_in; p.x = x; p.mean = mean; p.std_div = inv_std_div;
             p.xhat = w.xhat[cur]; p.wx_pack = s.wx_pack; p.sub_pack = A > 0 ? s.sub_pack : nullptr; p.sub_norm = s.sub_norm;
             p.r = w.r; p.u = w.u; p.idx = w.idx; p.err_flag = m->err_dev;
-            static const int dbg = getenv("QB_PREP_TC_DEBUG") ? atoi(getenv("QB_PREP_TC_DEBUG")) : 0;     // timing experiments only
-            p.dbg = dbg;
             if (fuse) { p.sel_best = w.sel_best; p.sel_cnt = w.sel_cnt; }
             QB_CUDA(timed_launch(m, KIND_PREP, p.n_beams, st, [&] { return qb::launch_prep_tc(p, st); }));
         } else {
@@ -578,6 +586,9 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         for (int k = 0; k < K; k++) nrm[k] = row_norm2(d->codebook[0] + (size_t)k * D, D);
         if ((rc = dev_upload(m, d->codebook[0], (size_t)K * D, &m->cb0))) return bail(rc);
         if ((rc = dev_upload(m, nrm.data(), nrm.size(), &m->cb0_norm))) return bail(rc);
+        std::vector<uint16_t> pk(qb::prep_pack_bytes(K, D) / 2);
+        qb::prep_pack(d->codebook[0], K, D, pk.data());
+        if ((rc = dev_upload(m, (const uint8_t*)pk.data(), pk.size() * 2, &m->cb0_pack))) return bail(rc);
     }
     if (d->data_mean) {
         bool nz = false;

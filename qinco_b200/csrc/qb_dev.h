@@ -149,7 +149,13 @@ struct PrepTcParams {
     unsigned long long* sel_best;   // fused selection state to reset (F == 1), or NULL
     uint32_t* sel_cnt;
     uint32_t* err_flag;
-    int32_t dbg;                // timing experiments: bit 0 skips the ranking, bit 1 the MMAs, bit 2 the distance epilogue
+    int32_t dbg;                // unused (timing experiments)
+    // step 0 (qinco_base.py:218,263; qinco_inference.py:239-246): xhat == NULL (zero), sub_pack / sub_norm = C_0, A = F_1 <= 16 beams:
+    // xhat_out[v][a] = C_0[code_a], hist_out[v][a][0] = code_a
+    int32_t step0, M;
+    const float* cb0;           // [K][D] fp32
+    float* xhat_out;            // [n, A, D]
+    uint8_t* hist_out;          // [n, A, M]
 };
 cudaError_t launch_prep_tc(const PrepTcParams& p, cudaStream_t stream);
 
