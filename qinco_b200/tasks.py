@@ -66,12 +66,12 @@ def load_model(args, device):
         bench = importlib.import_module("bench")
         wl = dict(bench.WORKLOADS[args.synthetic])
         wl["cfg"] = dict(wl["cfg"], **{k: v for k, v in (("A", args.A), ("B", args.B)) if v is not None})
-        cfg, w, x = bench.make_model_inputs(wl, args.n or 10000, 0)
+        cfg, w, x = bench.make_model_inputs(wl, args.limit or 10000, 0)
         return QINCo(cfg, w, device=device), x.numpy()
     cfg, sd = io.load_v2_checkpoint(args.model, dict(A=args.A, B=args.B), ivf_centroids=args.ivf_centroids)
     x = io.read_vectors(args.db)
-    if args.n:
-        x = x[: args.n]
+    if args.limit:
+        x = x[: args.limit]
     return QINCo(cfg, sd, device=device), x
 
 
@@ -170,7 +170,7 @@ def main(argv=None):
     ap.add_argument("--batch", type=int, default=1024, help="vectors per model call (cfg.batch of the reference)")
     ap.add_argument("--A", type=int, default=None)
     ap.add_argument("--B", type=int, default=None)
-    ap.add_argument("--n", type=int, default=0, help="use only the first n vectors")
+    ap.add_argument("--limit", type=int, default=0, help="use only the first LIMIT vectors (torchrun swallows a bare --n)")
     ap.add_argument("--synthetic", default=None, help="a bench.py workload name instead of --model / --db")
     ap.add_argument("--gather", action="store_true", help="encode: also all-gather the uint8 codes (one NCCL collective)")
     args = ap.parse_args(argv)
