@@ -602,22 +602,25 @@ def main():
     if not args.no_decode:
         model.decode_u8(codes, denormalize=True)
         barrier()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k_dec = max(1, min(args.steps, 3))
-        d0.record()
-        for _ in range(k_dec):
+        # every pass timed on its own (CUDA events); the median is reported, min / max beside it
+        k_dec = 5
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k_dec)]
+        for a_ev, b_ev in evs:
+            a_ev.record()
             xdec = model.decode_u8(codes, denormalize=True)
-        d1.record()
+            b_ev.record()
         barrier()
-        td = torch.tensor([d0.elapsed_time(d1)], device=dev, dtype=torch.float64)
+        per_pass = sorted(a_ev.elapsed_time(b_ev) for a_ev, b_ev in evs)
+        td = torch.tensor([per_pass[k_dec // 2]], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        dec_ms = float(td.item()) / k_dec
+        dec_ms = float(td.item())
         D_, M_ = cfg["D"], cfg["M"]
         dec_flops = decode_flops_per_vector(cfg)
         dec_tflops = n / (dec_ms * 1e-3) * dec_flops / 1e12
         pk = load_peaks()
         dec = {"value": world * n / (dec_ms * 1e-3), "unit": "vectors/s decoded", "ms_per_pass": dec_ms, "passes": k_dec,
+               "ms_per_pass_min_max": [per_pass[0], per_pass[-1]],
                "tflops": dec_tflops, "flops_per_vector": dec_flops,
                "roofline": {"bound": "tensor", "kernel": "qb_mlp_kernel (decode)", "achieved": dec_tflops, "peak": pk["tflops"],
                             "unit": "TFLOP/s", "frac": dec_tflops / pk["tflops"], "peak_source": pk["source"],

@@ -19,6 +19,7 @@ struct PlanOptions {
     int max_stage = 0;    // cap on ring depth (0 = QB_MAX_STAGE)
     int max_slab_k = 0;   // cap on slab K (0 = what fits a slot)
     int smem_budget = 0;  // bytes of dynamic shared memory the kernel may use (0 = 208 KiB)
+    int no_esplit = 0;    // 1: the E epilogue waits for the whole residual accumulator (debug / A-B tests)
     int mcast = 0;        // weight multicast over 2-CTA clusters: 0 = auto, 1 = off, 2 = on
     int uop = 0;          // 1: decode-loop plan: pre-ops computing u = Wx . xhat on the tensor core (fp16 hi/lo split), A_E
                           // buffer sized for [xhat_hi | xhat_lo], no resident tables

@@ -535,6 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             mbar_init(smem_u32(&bars[t][QB_BAR_AH2_READY]), (kPair ? 2 : 1) * kEpiWarps);
             mbar_init(smem_u32(&bars[t][QB_BAR_HACC_FULL]), 1);
             mbar_init(smem_u32(&bars[t][QB_BAR_EACC_FULL]), 1);
+            mbar_init(smem_u32(&bars[t][QB_BAR_EACC_HALF]), 1);
         }
         for (int t = 0; t < 2; t++) { mbar_init(smem_u32(&sel_full[t]), kEpiWarps); mbar_init(smem_u32(&sel_empty[t]), 1); }
         mbar_init(smem_u32(&tres_bar), 1);
@@ -1072,9 +1073,20 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         if (l + 1 < pl.L || pl.has_proj) {
 #pragma unroll 1
                             for (int t = 0; t < NT; t++) {
-                                wait_l(t, QB_BAR_EACC_FULL, 0x425);
-                                acc_to_smem_operand(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, e0c, e1c,
-                                                    smem_base + pl.smem_ae[t] + (uint32_t)r * 16u);
+                                const uint32_t te = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col;
+                                const uint32_t sd = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
+                                if (pl.e_split) {
+                                    int h0, h1;
+                                    group_range(pl.epart, cg, h0, h1);
+                                    wait_l(t, QB_BAR_EACC_HALF, 0x427);
+                                    acc_to_smem_operand(te, h0, h1, sd);
+                                    group_range(De - pl.epart, cg, h0, h1);
+                                    wait_l(t, QB_BAR_EACC_FULL, 0x425);
+                                    acc_to_smem_operand(te, pl.epart + h0, pl.epart + h1, sd);
+                                } else {
+                                    wait_l(t, QB_BAR_EACC_FULL, 0x425);
+                                    acc_to_smem_operand(te, e0c, e1c, sd);
+                                }
                                 arrive_issuer(t, QB_BAR_AE_READY, true);
                             }
                         }
@@ -1082,7 +1094,10 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
 #pragma unroll 1
                     for (int t = 0; t < NT; t++) {
                         if (pl.has_proj) wait_l(t, QB_BAR_HACC_FULL, 0x434);
-                        else if (pl.L > 0) wait_l(t, QB_BAR_EACC_FULL, 0x435);
+                        else if (pl.L > 0) {
+                            if (pl.e_split) wait_l(t, QB_BAR_EACC_HALF, 0x437);
+                            wait_l(t, QB_BAR_EACC_FULL, 0x435);
+                        }
                         const int64_t row = t ? row1 : row0;
                         const bool valid = t ? valid1 : valid0;
                         final_loop(t, valid ? row : 0, valid, t ? code1 : code0, p.loop_steps[ls].cb_blk, last);
@@ -1319,10 +1334,21 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 if (l + 1 < pl.L || pl.has_proj) {
 #pragma unroll 1
                     for (int t = 0; t < NT; t++) {
-                        wait_bar(t, QB_BAR_EACC_FULL, 0x405);
-                        tr.ev(5 + 0x80 * t);
-                        acc_to_smem_operand(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, e0c, e1c,
-                                            smem_base + pl.smem_ae[t] + (uint32_t)r * 16u);
+                        const uint32_t te = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col;
+                        const uint32_t sd = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
+                        if (pl.e_split) {       // first column part is final while the second part's MMAs still run
+                            int h0, h1;
+                            group_range(pl.epart, cg, h0, h1);
+                            wait_bar(t, QB_BAR_EACC_HALF, 0x407);
+                            acc_to_smem_operand(te, h0, h1, sd);
+                            group_range(De - pl.epart, cg, h0, h1);
+                            wait_bar(t, QB_BAR_EACC_FULL, 0x405);
+                            acc_to_smem_operand(te, pl.epart + h0, pl.epart + h1, sd);
+                        } else {
+                            wait_bar(t, QB_BAR_EACC_FULL, 0x405);
+                            tr.ev(5 + 0x80 * t);
+                            acc_to_smem_operand(te, e0c, e1c, sd);
+                        }
                         arrive_issuer(t, QB_BAR_AE_READY, true);
                         tr.ev(6 + 0x80 * t);
                     }
@@ -1424,6 +1450,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     // inputs of the final epilogue travel while the last down-projection runs
                     if (!kResident && cg == 0 && r * 32 < D) prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
                     if (!kResident && pl.skip && o0c < o1c) load_row32(cb, p.cb_blk, t ? code1 : code0, o0c, o1c - o0c);
+                    if (pl.L > 0 && pl.e_split) wait_bar(t, QB_BAR_EACC_HALF, 0x407);
                     if (pl.L > 0) wait_bar(t, QB_BAR_EACC_FULL, 0x405);
                     tr.ev(5 + 0x80 * t);
                     float a = 0.f;

@@ -171,6 +171,8 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     };
     const int n_eparts = (De + 255) / 256;
     const int epart = round_up((De + n_eparts - 1) / n_eparts, 16);
+    p->epart = epart;
+    p->e_split = (L > 0 && n_eparts == 2 && !p->pair && !opt.no_esplit) ? 1 : 0;
     if (L > 0) {                   // ops of ONE residual block, offsets relative to the block's weights
         for (int j = 0; j < p->n_hchunk; j++) {
             const int cw = std::min(hc, Dh - j * hc);
@@ -181,9 +183,10 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
             for (int n0 = 0; n0 < De; n0 += epart) {
                 const int n = std::min(epart, De - n0);
                 const bool last = (j == p->n_hchunk - 1) && (n0 + n >= De);
+                const bool half = p->e_split && (j == p->n_hchunk - 1) && n0 == 0;
                 emit_gemm(n, cw, QB_A_H, p->tmem_h_col, p->tmem_e_col + n0, true,
-                          n0 == 0 ? QB_BAR_AH_READY : QB_BAR_NONE, QB_BAR_NONE, last ? QB_BAR_EACC_FULL : QB_BAR_NONE,
-                          p->h_split && cw == hc);
+                          n0 == 0 ? QB_BAR_AH_READY : QB_BAR_NONE, QB_BAR_NONE,
+                          last ? QB_BAR_EACC_FULL : (half ? QB_BAR_EACC_HALF : QB_BAR_NONE), p->h_split && cw == hc);
             }
         }
     }
@@ -395,7 +398,7 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
     qb::PlanOptions opt;
     if (opts5) {
         opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = (opts5[1] >> 8) & 0xff; opt.mcast = (opts5[1] >> 16) & 0xff; opt.slot_bytes = opts5[2];
-        opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.uop = (opts5[3] >> 10) & 1; opt.max_slab_k = opts5[4];
+        opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.uop = (opts5[3] >> 10) & 1; opt.no_esplit = (opts5[3] >> 11) & 1; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
     std::vector<QbOp> ops;
@@ -417,7 +420,7 @@ int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int
     qb::PlanOptions opt;
     if (opts5) {
         opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = (opts5[1] >> 8) & 0xff; opt.mcast = (opts5[1] >> 16) & 0xff; opt.slot_bytes = opts5[2];
-        opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.uop = (opts5[3] >> 10) & 1; opt.max_slab_k = opts5[4];
+        opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.uop = (opts5[3] >> 10) & 1; opt.no_esplit = (opts5[3] >> 11) & 1; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
     std::vector<QbOp> ops;
@@ -432,7 +435,7 @@ int qb_plan_pack_pre(int D, int De, int Dh, int L, int K, int qinco1_mode, const
     qb::PlanOptions opt;
     if (opts5) {
         opt.hc = opts5[0]; opt.n_tiles = opts5[1] & 0xff; opt.pair = (opts5[1] >> 8) & 0xff; opt.mcast = (opts5[1] >> 16) & 0xff; opt.slot_bytes = opts5[2];
-        opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.uop = (opts5[3] >> 10) & 1; opt.max_slab_k = opts5[4];
+        opt.max_stage = opts5[3] & 0xff; opt.no_resident = (opts5[3] >> 8) & 1; opt.no_hsplit = (opts5[3] >> 9) & 1; opt.uop = (opts5[3] >> 10) & 1; opt.no_esplit = (opts5[3] >> 11) & 1; opt.max_slab_k = opts5[4];
     }
     QbStepPlan p;
     std::vector<QbOp> ops;

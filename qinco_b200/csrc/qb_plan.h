@@ -40,7 +40,9 @@ enum QbBar : uint8_t {
     QB_BAR_EACC_FULL = 5,
     QB_BAR_AH2_READY = 6,   // second K half of a split H chunk is in TMEM (its own barrier: with one barrier the epilogue
                             // could complete two phases before the issuer looks, and a parity wait cannot see that)
-    QB_BAR_COUNT = 7
+    QB_BAR_EACC_HALF = 7,   // first column part of Eacc is final (down-projection in two N parts, de > 256): the E epilogue converts it
+                            // while the second part's MMAs run
+    QB_BAR_COUNT = 8
 };
 
 struct QbOp {
@@ -99,6 +101,8 @@ struct QbStepPlan {
     // ae_chunks = max(De, 2D) / 8 k-chunks.  0 pre-ops: a plain plan.
     int32_t n_ops_pre;
     int32_t ae_chunks;
+    int32_t e_split;         // 1: the last down-projection of a block commits its first N part on QB_BAR_EACC_HALF (two parts: de > 256)
+    int32_t epart;           // columns of a down-projection N part
     int32_t mcast;           // 1: non-resident launches run as 2-CTA clusters that multicast the weight slabs (each CTA streams
                              // half of every slab into both ring slots); needs slab halves that are multiples of 16 bytes
     int64_t block_w_bytes;   // packed weight bytes of one residual block
