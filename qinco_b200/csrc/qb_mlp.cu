@@ -1483,7 +1483,6 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         for (int i = 0; i < 8; i++) cb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (pl.skip && c0 < c1) load_row32(cb, p.cb_blk, t ? code1 : code0, qq * pl.oc + c0, c1 - c0);
                         if (qq == 0 && cg == 0 && r * 32 < D) prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
-                        if (kFuseB && qq == 0 && cg == 1 && r * 32 < D) prefetch_l1(p.xhat_in + beam0 * D + r * 32);
                         wait_bar(t, QB_BAR_HACC_FULL, 0x414);
                         const uint32_t ta = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
                         float a = t ? acc1 : acc0;
@@ -1588,7 +1587,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     }
                     named_bar_sync(5, kEpiThreads);
                 }
-                {                       // the granted rows add xhat_parent to their o (still in TMEM) and park xhat' in the stash
+                {                       // the granted rows park their o (still in TMEM) in the stash; xhat_parent and the skip
+                                        // codeword are added at emit time, with coalesced loads, once per vector
                     const int slot = (int)selb_take[r];
                     if (!(p.dbg & 1) && __any_sync(0xffffffffu, slot != 0xff)) {
                         int c0, c1;
@@ -1602,18 +1602,12 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                             tmem_ld_cols(ta + c, n, v);
                             tmem_wait_ld();
                             if (slot != 0xff) {
-                                const float* xp = p.xhat_in + beam0 * D + c;
 #pragma unroll
-                                for (int i = 0; i < 8; i++) {
-                                    if (4 * i < n) {
-                                        const float4 xi = ldg4(xp + 4 * i);
-                                        const float4 cv = pl.skip ? ldg4(p.cb_blk + ((size_t)((c >> 2) + i) * K + code0) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st + (uint32_t)(c + 4 * i) * 4u),
-                                                     "f"(xi.x + (__uint_as_float(v[4 * i]) + cv.x)), "f"(xi.y + (__uint_as_float(v[4 * i + 1]) + cv.y)),
-                                                     "f"(xi.z + (__uint_as_float(v[4 * i + 2]) + cv.z)), "f"(xi.w + (__uint_as_float(v[4 * i + 3]) + cv.w))
+                                for (int i = 0; i < 8; i++)
+                                    if (4 * i < n)
+                                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + (uint32_t)(c + 4 * i) * 4u), "r"(v[4 * i]),
+                                                     "r"(v[4 * i + 1]), "r"(v[4 * i + 2]), "r"(v[4 * i + 3])
                                                      : "memory");
-                                    }
-                                }
                             }
                         }
                     }
@@ -1627,9 +1621,19 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         const int d4 = it2 % d4n, e = it2 / d4n, sgm = e / F_out, j = e - sgm * F_out;
                         const int64_t vs = fb_spv > 1 ? set / fb_spv : set * vpt + sgm;
                         if (vs < n_vec && j < (int)selb_nrun[sgm]) {
+                            // xhat'_j = xhat_parent + (o + C_m[code])     (same association as the update launch: bit-identical)
                             const int slot = selb_run_slot[sgm * F_out + j];
-                            const float4 xv = lds4(opaque(smem_u32(&selb_stash[0])) + (uint32_t)(((sgm * F_out + slot) * D) + 4 * d4) * 4u);
-                            *reinterpret_cast<float4*>(p.xhat_out + (vs * F_out + j) * D + 4 * d4) = xv;
+                            const int flat = selb_run_flat[sgm * F_out + j];
+                            const int parent = flat / p.C, slot_a = flat - parent * p.C;
+                            const float4 o = lds4(opaque(smem_u32(&selb_stash[0])) + (uint32_t)(((sgm * F_out + slot) * D) + 4 * d4) * 4u);
+                            const float4 xi = ldg4(p.xhat_in + (vs * p.F_in + parent) * D + 4 * d4);
+                            float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (pl.skip) {
+                                const int code = p.A > 0 ? (int)__ldg(p.idx + (vs * p.F_in + parent) * p.A + slot_a) : slot_a;
+                                cv = ldg4(p.cb_blk + ((size_t)d4 * K + code) * 4);
+                            }
+                            *reinterpret_cast<float4*>(p.xhat_out + (vs * F_out + j) * D + 4 * d4) =
+                                make_float4(xi.x + (o.x + cv.x), xi.y + (o.y + cv.y), xi.z + (o.z + cv.z), xi.w + (o.w + cv.w));
                         }
                     }
                     if (tid < vpt * F_out) {
