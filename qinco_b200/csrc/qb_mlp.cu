@@ -1075,17 +1075,16 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                             for (int t = 0; t < NT; t++) {
                                 const uint32_t te = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col;
                                 const uint32_t sd = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
-                                if (pl.e_split) {
-                                    int h0, h1;
-                                    group_range(pl.epart, cg, h0, h1);
-                                    wait_l(t, QB_BAR_EACC_HALF, 0x427);
+                                const int n_ep = pl.e_split ? 2 : 1;
+#pragma unroll 1
+                                for (int ep = 0; ep < n_ep; ep++) {
+                                    int h0 = e0c, h1 = e1c;
+                                    if (pl.e_split) {
+                                        group_range(ep == 0 ? pl.epart : De - pl.epart, cg, h0, h1);
+                                        if (ep) { h0 += pl.epart; h1 += pl.epart; }
+                                    }
+                                    wait_l(t, (pl.e_split && ep == 0) ? QB_BAR_EACC_HALF : QB_BAR_EACC_FULL, 0x425);
                                     acc_to_smem_operand(te, h0, h1, sd);
-                                    group_range(De - pl.epart, cg, h0, h1);
-                                    wait_l(t, QB_BAR_EACC_FULL, 0x425);
-                                    acc_to_smem_operand(te, pl.epart + h0, pl.epart + h1, sd);
-                                } else {
-                                    wait_l(t, QB_BAR_EACC_FULL, 0x425);
-                                    acc_to_smem_operand(te, e0c, e1c, sd);
                                 }
                                 arrive_issuer(t, QB_BAR_AE_READY, true);
                             }
@@ -1336,18 +1335,19 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     for (int t = 0; t < NT; t++) {
                         const uint32_t te = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col;
                         const uint32_t sd = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
-                        if (pl.e_split) {       // first column part is final while the second part's MMAs still run
-                            int h0, h1;
-                            group_range(pl.epart, cg, h0, h1);
-                            wait_bar(t, QB_BAR_EACC_HALF, 0x407);
-                            acc_to_smem_operand(te, h0, h1, sd);
-                            group_range(De - pl.epart, cg, h0, h1);
-                            wait_bar(t, QB_BAR_EACC_FULL, 0x405);
-                            acc_to_smem_operand(te, pl.epart + h0, pl.epart + h1, sd);
-                        } else {
-                            wait_bar(t, QB_BAR_EACC_FULL, 0x405);
+                        // with e_split the first column part is final while the second part's MMAs still run (ONE call site
+                        // of the conversion on purpose: a second inlined copy made ptxas spill ~900 B per thread)
+                        const int n_ep = pl.e_split ? 2 : 1;
+#pragma unroll 1
+                        for (int ep = 0; ep < n_ep; ep++) {
+                            int h0 = e0c, h1 = e1c;
+                            if (pl.e_split) {
+                                group_range(ep == 0 ? pl.epart : De - pl.epart, cg, h0, h1);
+                                if (ep) { h0 += pl.epart; h1 += pl.epart; }
+                            }
+                            wait_bar(t, (pl.e_split && ep == 0) ? QB_BAR_EACC_HALF : QB_BAR_EACC_FULL, 0x405);
                             tr.ev(5 + 0x80 * t);
-                            acc_to_smem_operand(te, e0c, e1c, sd);
+                            acc_to_smem_operand(te, h0, h1, sd);
                         }
                         arrive_issuer(t, QB_BAR_AE_READY, true);
                         tr.ev(6 + 0x80 * t);
