@@ -431,6 +431,7 @@ __device__ __forceinline__ void acc_to_tmem_operand_half(uint32_t taddr, int c0,
 }
 
 // Debug event log (MlpParams::trace, CTA 0 only): role 0 = epilogue thread 0, 1 = MMA issuer, 2 = producer.
+#ifdef QB_ENABLE_TRACE
 struct Tracer {
     unsigned long long* buf;
     int n;
@@ -446,6 +447,14 @@ struct Tracer {
         }
     }
 };
+#else
+// The event log costs four registers and a branch per event in every role: compiled in only with -DQB_ENABLE_TRACE
+// (QB_MLP_TRACE then dumps the timeline; a default build writes an empty one).
+struct Tracer {
+    __device__ __forceinline__ void init(const MlpParams&, int, bool) {}
+    __device__ __forceinline__ void ev(uint32_t) {}
+};
+#endif
 
 }  // namespace
 
@@ -1153,7 +1162,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     }
                 }
             };
-            if (!primed) {
+            if (!primed && !kResident) {      // (resident launches derive the context from the set index where it is used)
                 row_ctx(set, 0, row0, beam0, code0, valid0);
                 row_ctx(set, 1, row1, beam1, code1, valid1);
             }
@@ -1236,7 +1245,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             };
             if (!primed) {
 #pragma unroll 1
-                for (int t = 0; t < NT; t++) init_tile(t, t ? code1 : code0, t ? beam1 : beam0, rb);
+                for (int t = 0; t < NT; t++)
+                    init_tile(t, kResident ? hq * 64 + (r & 63) : (t ? code1 : code0), kResident ? 4 * set + 2 * t + (r >> 6) : (t ? beam1 : beam0), rb);
             }
             // ---- residual blocks -----------------------------------------------------------------------------------
             float acc0 = 0.f, acc1 = 0.f;
@@ -1454,18 +1464,27 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     if (pl.L > 0) wait_bar(t, QB_BAR_EACC_FULL, 0x405);
                     tr.ev(5 + 0x80 * t);
                     float a = 0.f;
-                    final_cols(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, o0c, o1c, 0, t ? code1 : code0, t ? beam1 : beam0,
-                               t ? row1 : row0, t ? valid1 : valid0, cb, a,
+                    // resident launches: code / beam / row follow from (set, tile slot, thread); nothing is carried in registers
+                    const int64_t beam_t = kResident ? 4 * set + 2 * t + (r >> 6) : (t ? beam1 : beam0);
+                    const int code_t = kResident ? hq * 64 + (r & 63) : (t ? code1 : code0);
+                    const int64_t row_t = kResident ? beam_t * 256 + code_t : (t ? row1 : row0);
+                    const bool valid_t = kResident ? beam_t < n_beams : (t ? valid1 : valid0);
+                    final_cols(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, o0c, o1c, 0, code_t, beam_t,
+                               row_t, valid_t, cb, a,
                                a_beam + (uint32_t)(((rb * 2 + t) * 2 + (r >> 6)) * 256 + De) * 4u);
                     tc_fence_before();
                     tr.ev(7 + 0x80 * t);
-                    if (kFuseA) fused_select_resident(t, a, t ? code1 : code0, t ? valid1 : valid0);
-                    else if (kScore) publish_dist(t, a, t ? row1 : row0, t ? valid1 : valid0);
+                    if (kFuseA) fused_select_resident(t, a, code_t, valid_t);
+                    else if (kScore) publish_dist(t, a, row_t, valid_t);
                     if (has_next) {         // tile slot t is free: start its next set now
                         if (kResident && t == 0)
                             mbar_wait((a_rfull + (uint32_t)(rbn) * 8u), (uint32_t)(((kset + 1) / 3) & 1), p.err_flag, 0x610 + rbn);
-                        if (t) row_ctx(set_next, 1, row1, beam1, code1, valid1); else row_ctx(set_next, 0, row0, beam0, code0, valid0);
-                        init_tile(t, t ? code1 : code0, t ? beam1 : beam0, rbn);
+                        if (kResident) {
+                            init_tile(t, code_t, 4 * set_next + 2 * t + (r >> 6), rbn);
+                        } else {
+                            if (t) row_ctx(set_next, 1, row1, beam1, code1, valid1); else row_ctx(set_next, 0, row0, beam0, code0, valid0);
+                            init_tile(t, t ? code1 : code0, t ? beam1 : beam0, rbn);
+                        }
                     }
                 }
                 primed = has_next;
