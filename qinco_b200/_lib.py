@@ -62,6 +62,11 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    override = os.environ.get("QINCO_B200_LIB")      # A/B tests of compile-time kernel variants: load exactly this build
+    if override:
+        if not os.path.exists(override):
+            raise RuntimeError(f"QINCO_B200_LIB={override} does not exist")
+        build_if_missing = False
     if build_if_missing:
         from . import build as _build
         try:
@@ -69,9 +74,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         except Exception as e:  # no nvcc on this machine: use the prebuilt library if there is one
             if not os.path.exists(LIB_PATH):
                 raise RuntimeError(f"libqinco_b200.so is missing and could not be built: {e}") from e
-    if not os.path.exists(LIB_PATH):
+    if not override and not os.path.exists(LIB_PATH):
         raise RuntimeError("libqinco_b200.so is missing; run `python -m qinco_b200.build` (there is no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(override or LIB_PATH)
     vp, i64, sz = C.c_void_p, C.c_int64, C.c_size_t
     lib.qb_version.restype = C.c_int
     lib.qb_last_error.restype = C.c_char_p

@@ -611,6 +611,7 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         if (const char* e = getenv("QB_PAIR")) opt.pair = atoi(e);   // debug / A-B runs: 1 = single-CTA kernel, 2 = force pairs
     opt.max_stage = d->opt_max_stage & 0xff; opt.no_resident = (d->opt_max_stage >> 8) & 1; opt.no_hsplit = (d->opt_max_stage >> 9) & 1; opt.max_slab_k = d->opt_max_slab_k;
     opt.no_esplit = ((d->opt_max_stage >> 11) & 1) || getenv("QB_NO_ESPLIT") != nullptr;
+    opt.blk32 = getenv("QB_BLK32") != nullptr;
     int max_smem = 0;
     for (int s = 1; s < m->S; s++) {
         StepDev& sd = m->steps[s];
@@ -623,7 +624,7 @@ int qb_model_create(const qb_model_desc* d, qb_model** out) {
         std::vector<QbOp> lops;
         if (loop) {
             qb::PlanOptions lo = opt;
-            lo.uop = 1; lo.pair = 1; lo.no_esplit = sd.plan.e_split ? 0 : 1; lo.hc = sd.plan.hc; lo.slot_bytes = sd.plan.slot_bytes; lo.mcast = sd.plan.mcast ? 2 : 1;
+            lo.uop = 1; lo.pair = 1; lo.no_esplit = sd.plan.e_split ? 0 : 1; lo.blk32 = opt.blk32; lo.hc = sd.plan.hc; lo.slot_bytes = sd.plan.slot_bytes; lo.mcast = sd.plan.mcast ? 2 : 1;
             std::string lerr;
             loop = qb::make_step_plan(D, De, m->Dh, m->L, K, m->q1, lo, &sd.loop_plan, &lops, &lerr) == 0 &&
                    sd.loop_plan.n_ops_block == sd.plan.n_ops_block && sd.loop_plan.n_ops_out == sd.plan.n_ops_out &&

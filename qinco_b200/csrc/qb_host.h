@@ -14,6 +14,8 @@ struct PlanOptions {
     int n_tiles = 0;      // 128-row tiles in flight per CTA (0 = auto: 2 when TMEM and shared memory allow)
     int pair = 0;         // CTA-pair (cta_group::2) kernel: 0 = auto (currently off), 1 = off, 2 = on (needs N % 32 == 0 down-projections)
     int no_resident = 0;  // 1: never keep table halves resident (debug / A-B tests)
+    int blk32 = 0;        // 1: blocked packed-H layout for hc == 128 (QbStepPlan::h_split == 2; measured 0.5 % slower than the
+                          // contiguous layout + quarter barrier with 8 epilogue warps, kept for A-B tests)
     int no_hsplit = 0;    // 1: hand every H chunk to the MMA issuer in one piece (debug / A-B tests)
     int slot_bytes = 0;   // weight ring slot size (0 = 16 KiB)
     int max_stage = 0;    // cap on ring depth (0 = QB_MAX_STAGE)

@@ -40,13 +40,23 @@ namespace qb {
 
 namespace {
 
-constexpr int kEpiWarps = 8;              // two warps per TMEM lane quarter: warp w owns lanes 32*(w%4).., column group w/4
+#ifndef QB_EPI_WARPS
+#define QB_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = QB_EPI_WARPS;   // 8 (16): two (four) warps per TMEM lane quarter: warp w owns lanes 32*(w%4).., column group w/4
 constexpr int kColGroups = kEpiWarps / 4;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiThreads + 128;  // + one warpgroup: producer warp, one MMA warp per tile slot, one idle warp
 // Registers are a per-scheduler pool (16 K per SM sub-partition = 3 warps x 168 at launch).  The service warpgroup
 // hands most of its share back (setmaxnreg.dec) and the epilogue warpgroups take it (setmaxnreg.inc): 2 x 232 + 40 = 504 <= 512.
-constexpr int kEpiRegs = 232, kSvcRegs = 40;
+constexpr int kEpiRegs = kEpiWarps == 8 ? 232 : 112, kSvcRegs = 40;      // 16 warps: 4 x 112 + 40 = 488 <= 512
+// Epilogue -> issuer hand-off: every epilogue THREAD arrives on the barrier (count = kEpiThreads) right after fencing its own
+// writes.  The elected form (warp converges, lane 0 arrives) costs an S2R / vote / predicate chain of ~5 dependent
+// instructions on each of the ~11 hand-offs per tile, on the warps that bound the kernel.
+#ifndef QB_ARRIVE_ALL
+#define QB_ARRIVE_ALL 1
+#endif
+constexpr int kArriveCount = QB_ARRIVE_ALL ? kEpiThreads : kEpiWarps;
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;   // MMA warps: kMmaWarp + tile slot
 constexpr int kAkcBytes = QB_TILE_M * 16;   // bytes of one 8-element k-chunk of an A operand tile
 constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);   // high word of every UMMA smem descriptor here: SBO = 128 B, version 1
@@ -202,41 +212,42 @@ __device__ __forceinline__ void mma_ss_step(uint32_t d, uint32_t& alo, uint32_t&
                      "add.u32 %0, %0, %7;\n\tadd.u32 %1, %1, %8;\n\t}"
                      : "+r"(alo), "+r"(blo) : "r"(d), "r"(ahi), "r"(bhi), "r"(idesc), "r"(acc), "r"(as), "r"(bs) : "memory");
 }
-// same with the A operand in TMEM (column address += 8 per K=16)
+// same with the A operand in TMEM (column address += as per K=16: 8 for a contiguous packed operand)
 template <bool kPairI>
 __device__ __forceinline__ void mma_ts_step(uint32_t d, uint32_t& a_tmem, uint32_t& blo, uint32_t bhi, uint32_t idesc, uint32_t acc,
-                                            uint32_t bs) {
+                                            uint32_t as, uint32_t bs) {
     if (kPairI)
         asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
                      "mov.b64 db, {%1, %3};\n\t"
                      "tcgen05.mma.cta_group::2.kind::f16 [%2], [%0], db, %4, p;\n\t"
-                     "add.u32 %0, %0, 8;\n\tadd.u32 %1, %1, %6;\n\t}"
-                     : "+r"(a_tmem), "+r"(blo) : "r"(d), "r"(bhi), "r"(idesc), "r"(acc), "r"(bs) : "memory");
+                     "add.u32 %0, %0, %7;\n\tadd.u32 %1, %1, %6;\n\t}"
+                     : "+r"(a_tmem), "+r"(blo) : "r"(d), "r"(bhi), "r"(idesc), "r"(acc), "r"(bs), "r"(as) : "memory");
     else
         asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
                      "mov.b64 db, {%1, %3};\n\t"
                      "tcgen05.mma.cta_group::1.kind::f16 [%2], [%0], db, %4, p;\n\t"
-                     "add.u32 %0, %0, 8;\n\tadd.u32 %1, %1, %6;\n\t}"
-                     : "+r"(a_tmem), "+r"(blo) : "r"(d), "r"(bhi), "r"(idesc), "r"(acc), "r"(bs) : "memory");
+                     "add.u32 %0, %0, %7;\n\tadd.u32 %1, %1, %6;\n\t}"
+                     : "+r"(a_tmem), "+r"(blo) : "r"(d), "r"(bhi), "r"(idesc), "r"(acc), "r"(bs), "r"(as) : "memory");
 }
-// nk MMAs of one slab; the common slab depths are fully unrolled
+// nk MMAs of one slab; the common slab depths are fully unrolled.  The A cursor advances by `as` after even and `as2`
+// after odd k-steps of the slab (equal except for the blocked TMEM layout of a packed H operand, QbOp::a_blk32).
 template <bool kPairI, bool kFromSmem>
 __device__ __forceinline__ void mma_slab(int nk, uint32_t d, uint32_t& a, uint32_t& blo, uint32_t ahi, uint32_t bhi, uint32_t idesc,
-                                         uint32_t acc, uint32_t as, uint32_t bs) {
-    auto one = [&](uint32_t ac) {
+                                         uint32_t acc, uint32_t as, uint32_t as2, uint32_t bs) {
+    auto one = [&](uint32_t ac, int k) {
         if (kFromSmem) mma_ss_step<kPairI>(d, a, blo, ahi, bhi, idesc, ac, as, bs);
-        else mma_ts_step<kPairI>(d, a, blo, bhi, idesc, ac, bs);
+        else mma_ts_step<kPairI>(d, a, blo, bhi, idesc, ac, (k & 1) ? as2 : as, bs);
     };
-    one(acc);
+    one(acc, 0);
     if (nk == 8) {
 #pragma unroll
-        for (int k = 1; k < 8; k++) one(1u);
+        for (int k = 1; k < 8; k++) one(1u, k);
     } else if (nk == 4) {
 #pragma unroll
-        for (int k = 1; k < 4; k++) one(1u);
+        for (int k = 1; k < 4; k++) one(1u, k);
     } else {
 #pragma unroll 1
-        for (int k = 1; k < nk; k++) one(1u);
+        for (int k = 1; k < nk; k++) one(1u, k);
     }
 }
 
@@ -296,9 +307,35 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// relu folded into the conversion (F2FP.RELU: one instruction per column pair instead of F2FP + HMNMX2)
 __device__ __forceinline__ uint32_t pack_h2_relu(float a, float b) {
-    __half2 h = __hmax2(__floats2half2_rn(a, b), __float2half2_rn(0.f));
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t w;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));      // low half = a
+    return w;
+}
+// Packed fp32 pairs (FADD2 / FFMA2: two IEEE round-to-nearest operations per issue slot, bit-identical to the scalar
+// forms).  The epilogue warps are latency / issue bound, not FLOP bound, so halving the instruction count is the point.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+    f32x2 v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+    f32x2 c;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+    return c;
+}
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) {
+    f32x2 c;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+    return c;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -417,16 +454,19 @@ __device__ __forceinline__ void acc_to_tmem_operand(uint32_t taddr, int c0, int 
 // [h * cw/2 + cg * cw/4, + cw/4) of this thread's row -> relu -> packed fp16 written at columns [(h * cw/2 + cg * cw/4) / 2, ...).
 // The packed block of the upper column group lands on fp32 columns the lower group reads in the same half, hence the
 // barrier between the loads and the stores; across halves the targets of half 1 were all read in half 0.
-__device__ __forceinline__ void acc_to_tmem_operand_half(uint32_t taddr, int c0, int n, int quarter_bar) {
+// `blk32` (n == 32, c0 a multiple of 32; QbStepPlan::h_split == 2): the packed block goes to the START of the thread's own
+// 32 fp32 columns, which nobody else reads -- no barrier, and the MMA issuer walks the blocked layout (QbOp::a_blk32).
+__device__ __forceinline__ void acc_to_tmem_operand_half(uint32_t taddr, int c0, int n, int quarter_bar, bool blk32) {
     uint32_t va[32];          // n = 16 or 32 columns
     tmem_ld_cols(taddr + c0, n, va);
     tmem_wait_ld();
-    named_bar_sync(quarter_bar, kColGroups * 32);
+    if (!blk32) named_bar_sync(quarter_bar, kColGroups * 32);
     uint32_t w[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) w[j] = pack_h2_relu(__uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
     __syncwarp();
-    if (n >= 32) tmem_st16(taddr + (c0 >> 1), w); else tmem_st8(taddr + (c0 >> 1), w);
+    const uint32_t dst = taddr + (blk32 ? c0 : (c0 >> 1));
+    if (n >= 32) tmem_st16(dst, w); else tmem_st8(dst, w);
     tmem_wait_st();
 }
 
@@ -536,12 +576,12 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     if (tid == 0) {
         for (int t = 0; t < 2; t++) {
             mbar_init(smem_u32(&bars[t][QB_BAR_NONE]), 1);
-            // epilogue -> MMA issuer: one elected arrival per epilogue warp, from both CTAs of a pair (the issuer lives
-            // in the leader CTA)
-            mbar_init(smem_u32(&bars[t][QB_BAR_AE_READY]), (kPair ? 2 : 1) * kEpiWarps);
-            mbar_init(smem_u32(&bars[t][QB_BAR_AH_READY]), (kPair ? 2 : 1) * kEpiWarps);
-            mbar_init(smem_u32(&bars[t][QB_BAR_HACC_FREE]), (kPair ? 2 : 1) * kEpiWarps);
-            mbar_init(smem_u32(&bars[t][QB_BAR_AH2_READY]), (kPair ? 2 : 1) * kEpiWarps);
+            // epilogue -> MMA issuer: one arrival per epilogue thread (QB_ARRIVE_ALL) or warp, from both CTAs of a pair
+            // (the issuer lives in the leader CTA)
+            mbar_init(smem_u32(&bars[t][QB_BAR_AE_READY]), (kPair ? 2 : 1) * kArriveCount);
+            mbar_init(smem_u32(&bars[t][QB_BAR_AH_READY]), (kPair ? 2 : 1) * kArriveCount);
+            mbar_init(smem_u32(&bars[t][QB_BAR_HACC_FREE]), (kPair ? 2 : 1) * kArriveCount);
+            mbar_init(smem_u32(&bars[t][QB_BAR_AH2_READY]), (kPair ? 2 : 1) * kArriveCount);
             mbar_init(smem_u32(&bars[t][QB_BAR_HACC_FULL]), 1);
             mbar_init(smem_u32(&bars[t][QB_BAR_EACC_FULL]), 1);
             mbar_init(smem_u32(&bars[t][QB_BAR_EACC_HALF]), 1);
@@ -809,6 +849,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         uint32_t a_cur = from_smem ? (((uint32_t)kAkcBytes >> 4) << 16) | (ae_lo + (uint32_t)op.a_off * (kAkcBytes >> 4))
                                                    : tcol + op.a_off;
                         uint32_t acc = op.accumulate;
+                        const bool blk32 = op.a_blk32 != 0;
+                        uint32_t j0 = 0;                    // k-steps issued so far (blocked TMEM operand layout)
                         int k16_left = op.k_total >> 4;
                         const uint32_t commit_bar = op.commit;
                         const uint32_t wa = op.wait_a, wd = op.wait_d, wa2_slab = op.wait_a2_slab;
@@ -838,8 +880,14 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                             }
                             if (elect_one()) {
                                 uint32_t a_l = a_cur, b_l = b_lo;      // cursors local to the issuing lane (the warp-wide ones advance below)
-                                if (from_smem) mma_slab<kPair, true>(nk, d_tmem, a_l, b_l, kDescHi, kDescHi, idesc, acc, (2 * kAkcBytes) >> 4, b_step);
-                                else mma_slab<kPair, false>(nk, d_tmem, a_l, b_l, kDescHi, kDescHi, idesc, acc, 0u, b_step);
+                                if (from_smem) {
+                                    mma_slab<kPair, true>(nk, d_tmem, a_l, b_l, kDescHi, kDescHi, idesc, acc, (2 * kAkcBytes) >> 4, (2 * kAkcBytes) >> 4, b_step);
+                                } else if (blk32) {     // k-step j of the op at column 32 * (j / 2) + 8 * (j % 2)
+                                    a_l = tcol + op.a_off + 32u * (j0 >> 1) + 8u * (j0 & 1u);
+                                    mma_slab<kPair, false>(nk, d_tmem, a_l, b_l, kDescHi, kDescHi, idesc, acc, (j0 & 1u) ? 24u : 8u, (j0 & 1u) ? 8u : 24u, b_step);
+                                } else {
+                                    mma_slab<kPair, false>(nk, d_tmem, a_l, b_l, kDescHi, kDescHi, idesc, acc, 8u, 8u, b_step);
+                                }
                                 if (kPair) {        // both CTAs recycle the ring slot / see the accumulator
                                     tc_commit_pair((a_wempty + stage * 8u));
                                     if (s + 1 == n_slab && commit_bar) tc_commit_pair(bar_addr(t, commit_bar));
@@ -850,6 +898,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                             }
                             __syncwarp();
                             a_cur += (uint32_t)nk * (from_smem ? ((2 * kAkcBytes) >> 4) : 8u);
+                            j0 += (uint32_t)nk;
                             acc = 1;
                             if (++stage == (uint32_t)pl.n_stage) { stage = 0; phase ^= 1; }
                         }
@@ -876,8 +925,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         auto arrive_issuer = [&](int t, int bar, bool wrote_smem) {
             tc_fence_before();
             if (wrote_smem) { if (kPair) proxy_fence_async_all(); else proxy_fence_async(); }
-            __syncwarp();
-            if ((tid & 31) == 0) {
+            if (!QB_ARRIVE_ALL) __syncwarp();
+            if (QB_ARRIVE_ALL || (tid & 31) == 0) {
                 if (kPair) mbar_arrive_cluster(mapa_rank(bar_addr(t, bar), 0));
                 else mbar_arrive(bar_addr(t, bar));
             }
@@ -890,11 +939,12 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         // Resident mode: this thread's code never changes, so its slice of the T_m row (<= 64 columns) lives in registers
         // for the whole launch; reading it from shared memory for every tile costs as much shared-memory bandwidth as a
         // quarter of the tile's MMAs.
-        float4 treg[16];
+        constexpr int kTReg = 32 / kColGroups;      // float4 registers: 128 / kColGroups columns
+        float4 treg[kTReg];
         if (kResident) {
             const float* tsrc = p.t_blk + ((size_t)(e0c >> 2) * K + (hq * 64 + (r & 63))) * 4;
 #pragma unroll
-            for (int i = 0; i < 16; i++)
+            for (int i = 0; i < kTReg; i++)
                 treg[i] = (e0c + 4 * i < e1c) ? ldg4(tsrc + (size_t)i * K * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if constexpr (kLoop) {
@@ -1069,13 +1119,18 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                                 const uint32_t th = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
                                 if (kColGroups == 2 && pl.h_split && cw == pl.hc && (cw >> 2) <= 32) {
                                     const int qw = cw >> 2;
-                                    acc_to_tmem_operand_half(th, cg * qw, qw, 1 + q);
+                                    acc_to_tmem_operand_half(th, cg * qw, qw, 1 + q, pl.h_split == 2);
                                     arrive_issuer(t, QB_BAR_AH_READY, false);
-                                    acc_to_tmem_operand_half(th, (cw >> 1) + cg * qw, qw, 1 + q);
+                                    acc_to_tmem_operand_half(th, (cw >> 1) + cg * qw, qw, 1 + q, pl.h_split == 2);
                                     arrive_issuer(t, QB_BAR_AH2_READY, false);
+                                } else if (kColGroups == 4 && cw == 128) {     // one 32-column block per warp
+                                    acc_to_tmem_operand_half(th, cg * 32, 32, 1 + q, pl.h_split == 2);
+                                    arrive_issuer(t, QB_BAR_AH_READY, false);
+                                    if (pl.h_split && cw == pl.hc) arrive_issuer(t, QB_BAR_AH2_READY, false);
                                 } else {
                                     acc_to_tmem_operand(th, c0, c1, 1 + q);
                                     arrive_issuer(t, QB_BAR_AH_READY, false);
+                                    if (kColGroups != 2 && pl.h_split && cw == pl.hc) arrive_issuer(t, QB_BAR_AH2_READY, false);
                                 }
                             }
                         }
@@ -1193,8 +1248,11 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         operands(h, tb, ub);
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            e[16 * h + 4 * i + 0] = __float_as_uint(tb[i].x + ub[i].x); e[16 * h + 4 * i + 1] = __float_as_uint(tb[i].y + ub[i].y);
-                            e[16 * h + 4 * i + 2] = __float_as_uint(tb[i].z + ub[i].z); e[16 * h + 4 * i + 3] = __float_as_uint(tb[i].w + ub[i].w);
+                            float s0, s1, s2, s3;
+                            f2_unpack(f2_add(f2_pack(tb[i].x, tb[i].y), f2_pack(ub[i].x, ub[i].y)), s0, s1);
+                            f2_unpack(f2_add(f2_pack(tb[i].z, tb[i].w), f2_pack(ub[i].z, ub[i].w)), s2, s3);
+                            e[16 * h + 4 * i + 0] = __float_as_uint(s0); e[16 * h + 4 * i + 1] = __float_as_uint(s1);
+                            e[16 * h + 4 * i + 2] = __float_as_uint(s2); e[16 * h + 4 * i + 3] = __float_as_uint(s3);
                         }
                     };
                     auto to_smem = [&](int j) {     // 8 columns -> one fp16 k-chunk row of A_E
@@ -1218,7 +1276,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 };
                 if (kResident) {
 #pragma unroll
-                    for (int b = 0; b < 2; b++) {       // <= 64 columns per thread in resident mode (planner)
+                    for (int b = 0; b < kTReg / 8; b++) {       // <= 128 / kColGroups columns per thread in resident mode (planner)
                         const int c = e0c + 32 * b;
                         if (c < e1c)
                             batch(c, e1c - c, [&](int h, float4 (&tb)[4], float4 (&ub)[4]) {
@@ -1264,7 +1322,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 const uint32_t rs_a = rows_a + (uint32_t)d0 * 4u;                        // resident: r_b row in shared memory
                 const uint32_t cs_a = smem_base + (uint32_t)pl.smem_tres + (uint32_t)(r & 63) * 16u;   // resident C_m quarter
                 const bool skip = pl.skip != 0;
-                float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;       // four independent accumulation chains
+                f32x2 axy = 0ull, azw = 0ull;                       // four independent accumulation chains, in packed pairs
 #pragma unroll 1
                 for (int cb0 = c0; cb0 < c1; cb0 += 32) {
                     const int n = c1 - cb0;                          // 16 or >= 32
@@ -1289,12 +1347,18 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
                             const int vi = 16 * h + 4 * i;
+                            if (kScore) {               // e = r - (v + c), acc += e * e: three packed operations per column pair
+                                const f32x2 e01 = f2_sub(f2_pack(tv[i].x, tv[i].y),
+                                                         f2_add(f2_pack(__uint_as_float(v[vi]), __uint_as_float(v[vi + 1])), f2_pack(cv[i].x, cv[i].y)));
+                                const f32x2 e23 = f2_sub(f2_pack(tv[i].z, tv[i].w),
+                                                         f2_add(f2_pack(__uint_as_float(v[vi + 2]), __uint_as_float(v[vi + 3])), f2_pack(cv[i].z, cv[i].w)));
+                                axy = f2_fma(e01, e01, axy);
+                                azw = f2_fma(e23, e23, azw);
+                                continue;
+                            }
                             const float o0 = __uint_as_float(v[vi]) + cv[i].x, o1 = __uint_as_float(v[vi + 1]) + cv[i].y;
                             const float o2 = __uint_as_float(v[vi + 2]) + cv[i].z, o3 = __uint_as_float(v[vi + 3]) + cv[i].w;
-                            if (kScore) {
-                                const float e0 = tv[i].x - o0, e1 = tv[i].y - o1, e2 = tv[i].z - o2, e3 = tv[i].w - o3;
-                                ax = fmaf(e0, e0, ax); ay = fmaf(e1, e1, ay); az = fmaf(e2, e2, az); aw = fmaf(e3, e3, aw);
-                            } else if (valid) {
+                            if (valid) {
                                 const int d = d0 + cb0 + 16 * h + 4 * i;
                                 float4 out = make_float4(tv[i].x + o0, tv[i].y + o1, tv[i].z + o2, tv[i].w + o3);
                                 if (p.out_shift) {
@@ -1311,7 +1375,12 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     half16(0, false);
                     if (n > 16) half16(1, true);
                 }
-                if (kScore) acc += (ax + ay) + (az + aw);
+                if (kScore) {
+                    float ax, ay, az, aw;
+                    f2_unpack(axy, ax, ay);
+                    f2_unpack(azw, az, aw);
+                    acc += (ax + ay) + (az + aw);
+                }
             };
 #pragma unroll 1
             for (int l = 0; l < pl.L; l++) {
@@ -1329,13 +1398,18 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                             // two K halves, each split over the two column groups: the down-projection starts on the
                             // first half while the second is converted
                             const int qw = cw >> 2;
-                            acc_to_tmem_operand_half(th, cg * qw, qw, 1 + q);
+                            acc_to_tmem_operand_half(th, cg * qw, qw, 1 + q, pl.h_split == 2);
                             arrive_issuer(t, QB_BAR_AH_READY, false);
-                            acc_to_tmem_operand_half(th, (cw >> 1) + cg * qw, qw, 1 + q);
+                            acc_to_tmem_operand_half(th, (cw >> 1) + cg * qw, qw, 1 + q, pl.h_split == 2);
                             arrive_issuer(t, QB_BAR_AH2_READY, false);
+                        } else if (kColGroups == 4 && cw == 128) {     // one 32-column block per warp
+                            acc_to_tmem_operand_half(th, cg * 32, 32, 1 + q, pl.h_split == 2);
+                            arrive_issuer(t, QB_BAR_AH_READY, false);
+                            if (pl.h_split && cw == pl.hc) arrive_issuer(t, QB_BAR_AH2_READY, false);   // (a split plan waits for both)
                         } else {
                             acc_to_tmem_operand(th, c0, c1, 1 + q);
                             arrive_issuer(t, QB_BAR_AH_READY, false);
+                            if (kColGroups != 2 && pl.h_split && cw == pl.hc) arrive_issuer(t, QB_BAR_AH2_READY, false);   // (a split plan waits for both)
                         }
                         tr.ev(4 + 0x80 * t);
                     }

@@ -146,6 +146,7 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
     // H chunks of the full width hc (a multiple of 64) are handed over in two K halves: the down-projection starts on
     // the first half while the epilogue still converts the second (shortens the per-tile dependency chain)
     p->h_split = (opt.no_hsplit == 0 && L > 0 && hc % 64 == 0 && hc >= 64) ? 1 : 0;
+    if (p->h_split && hc == 128 && !p->pair && opt.blk32) p->h_split = 2;
     auto emit_gemm = [&](int n, int k_total, uint8_t a_src, int a_unit0, int d_col, bool acc_first,
                          uint8_t wait_a, uint8_t wait_d, uint8_t commit, bool split_k = false) {
         int ks = ((p->pair ? 2 : 1) * p->slot_bytes / (2 * n)) / 16 * 16;   // a pair CTA holds half the rows of a slab
@@ -166,6 +167,7 @@ int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const P
         op.n_slab = (uint8_t)n_slab; op.a_src = a_src; op.accumulate = acc_first ? 1 : 0;
         op.wait_a = wait_a; op.wait_d = wait_d; op.commit = commit;
         op.wait_a2_slab = (split_k && wait_a) ? (uint8_t)((k_total / 2) / ks) : 0;
+        op.a_blk32 = (split_k && a_src == QB_A_H && p->h_split == 2) ? 1 : 0;
         w_off += (uint32_t)(n * k_total * 2);
         ops->push_back(op);
     };

@@ -62,7 +62,9 @@ struct QbOp {
     uint8_t wait_d;      // QbBar to wait on before issuing (accumulator free), or NONE
     uint8_t commit;      // QbBar to tcgen05.commit to after the GEMM, or NONE
     uint8_t wait_a2_slab; // != 0: wait on QB_BAR_AH2_READY before this slab (the A operand arrives in two K halves)
-    uint8_t pad[3];
+    uint8_t a_blk32;     // QB_A_H only: the packed fp16 operand sits at the START of every 32-column fp32 block it was converted
+                         // from (k-step j at column 32 * (j / 2) + 8 * (j % 2)) instead of contiguously (h_split == 2)
+    uint8_t pad[2];
 };
 static_assert(sizeof(QbOp) == 32, "QbOp must stay 32 bytes");
 
@@ -89,8 +91,10 @@ struct QbStepPlan {
     int32_t slot_bytes;
     int32_t n_stage;
     int32_t smem_total;
-    int32_t h_split;         // 1: a full-width H chunk is converted and handed to the MMA issuer in two K halves (two
-                             // arrivals on AH_READY per chunk; the down-projection's slabs end on the half boundary)
+    int32_t h_split;         // != 0: a full-width H chunk is converted and handed to the MMA issuer in two K halves (two
+                             // arrivals on AH_READY per chunk; the down-projection's slabs end on the half boundary).
+                             // 2 (hc == 128): every epilogue warp writes its packed fp16 block over the start of the 32 fp32
+                             // columns it just read, so the warps of a lane quarter need no barrier between loads and stores
     int32_t pair;            // 1: CTA-pair kernel (cta_group::2, M = 256 over two CTAs): every slab is packed as two row
                              // halves, CTA r of a pair streams half r into a ring slot of slot_bytes
     // Decode loop (kLoop kernel: one tile walks every step, xhat stays with its rows): u = Wx . xhat runs on the tensor core
