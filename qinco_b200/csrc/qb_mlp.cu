@@ -470,6 +470,41 @@ __device__ __forceinline__ void acc_to_tmem_operand_half(uint32_t taddr, int c0,
     tmem_wait_st();
 }
 
+// Both K halves of a split H chunk: the two tcgen05.ld travel together (one TMEM round trip of ~130 cycles instead of two, one
+// quarter barrier instead of two), then half 0 is packed, stored and handed to the issuer (`ready(0)`) before half 1 is
+// packed.  Every packed target column lies in the fp32 columns [0, cw/2) of the chunk, all of which both warps of the lane
+// quarter have read before the barrier.
+#ifndef QB_HSPLIT_ONE_WAIT
+#define QB_HSPLIT_ONE_WAIT 0      // 1 (A-B): both halves stored before the one tcgen05.wait::st, both hand-offs after it
+#endif
+template <class Ready>
+__device__ __forceinline__ void acc_to_tmem_operand_split(uint32_t taddr, int cw, int cg, int quarter_bar, Ready&& ready) {
+    const int qw = cw >> 2;            // 16 or 32 columns per (half, column group)
+    uint32_t va[32], vb[32];
+    tmem_ld_cols(taddr + cg * qw, qw, va);
+    tmem_ld_cols(taddr + (cw >> 1) + cg * qw, qw, vb);
+    tmem_wait_ld();
+    named_bar_sync(quarter_bar, kColGroups * 32);
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) w[j] = pack_h2_relu(__uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
+    __syncwarp();
+    if (qw >= 32) tmem_st16(taddr + ((cg * qw) >> 1), w); else tmem_st8(taddr + ((cg * qw) >> 1), w);
+#if !QB_HSPLIT_ONE_WAIT
+    tmem_wait_st();
+    ready(0);
+#endif
+#pragma unroll
+    for (int j = 0; j < 16; j++) w[j] = pack_h2_relu(__uint_as_float(vb[2 * j]), __uint_as_float(vb[2 * j + 1]));
+    __syncwarp();
+    if (qw >= 32) tmem_st16(taddr + (((cw >> 1) + cg * qw) >> 1), w); else tmem_st8(taddr + (((cw >> 1) + cg * qw) >> 1), w);
+    tmem_wait_st();
+#if QB_HSPLIT_ONE_WAIT
+    ready(0);
+#endif
+    ready(1);
+}
+
 // Debug event log (MlpParams::trace, CTA 0 only): role 0 = epilogue thread 0, 1 = MMA issuer, 2 = producer.
 #ifdef QB_ENABLE_TRACE
 struct Tracer {
@@ -1118,11 +1153,15 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                                 wait_l(t, QB_BAR_HACC_FULL, 0x424);
                                 const uint32_t th = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
                                 if (kColGroups == 2 && pl.h_split && cw == pl.hc && (cw >> 2) <= 32) {
-                                    const int qw = cw >> 2;
-                                    acc_to_tmem_operand_half(th, cg * qw, qw, 1 + q, pl.h_split == 2);
-                                    arrive_issuer(t, QB_BAR_AH_READY, false);
-                                    acc_to_tmem_operand_half(th, (cw >> 1) + cg * qw, qw, 1 + q, pl.h_split == 2);
-                                    arrive_issuer(t, QB_BAR_AH2_READY, false);
+                                    if (pl.h_split == 2) {
+                                        const int qw = cw >> 2;
+                                        acc_to_tmem_operand_half(th, cg * qw, qw, 1 + q, true);
+                                        arrive_issuer(t, QB_BAR_AH_READY, false);
+                                        acc_to_tmem_operand_half(th, (cw >> 1) + cg * qw, qw, 1 + q, true);
+                                        arrive_issuer(t, QB_BAR_AH2_READY, false);
+                                    } else {
+                                        acc_to_tmem_operand_split(th, cw, cg, 1 + q, [&](int h) { arrive_issuer(t, h ? QB_BAR_AH2_READY : QB_BAR_AH_READY, false); });
+                                    }
                                 } else if (kColGroups == 4 && cw == 128) {     // one 32-column block per warp
                                     acc_to_tmem_operand_half(th, cg * 32, 32, 1 + q, pl.h_split == 2);
                                     arrive_issuer(t, QB_BAR_AH_READY, false);
@@ -1323,12 +1362,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 const uint32_t cs_a = smem_base + (uint32_t)pl.smem_tres + (uint32_t)(r & 63) * 16u;   // resident C_m quarter
                 const bool skip = pl.skip != 0;
                 f32x2 axy = 0ull, azw = 0ull;                       // four independent accumulation chains, in packed pairs
-#pragma unroll 1
-                for (int cb0 = c0; cb0 < c1; cb0 += 32) {
-                    const int n = c1 - cb0;                          // 16 or >= 32
-                    uint32_t v[32];
-                    tr.ev(12);
-                    tmem_ld_cols(taddr + cb0, n, v);
+                // one block of <= 32 accumulator columns already requested into v (`waited`: their tcgen05.ld has been waited for)
+                auto proc32 = [&](uint32_t (&v)[32], int cb0, int n, bool waited0) {
                     if (!kResident && cb0 > c0 && skip) load_row32(cb, p.cb_blk, code, d0 + cb0, n);
                     auto half16 = [&](int h, bool waited) {
                         float4 tv[4], cv[4];
@@ -1372,8 +1407,17 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                             }
                         }
                     };
-                    half16(0, false);
+                    half16(0, waited0);
                     if (n > 16) half16(1, true);
+                };
+                // (both tcgen05.ld of a 64-column thread in flight together would save a TMEM round trip, but with the 64 table
+                // registers of the resident variant the live set no longer fits 232 registers: ptxas spills the whole table row)
+#pragma unroll 1
+                for (int cb0 = c0; cb0 < c1; cb0 += 32) {
+                    uint32_t v[32];
+                    tr.ev(12);
+                    tmem_ld_cols(taddr + cb0, c1 - cb0, v);
+                    proc32(v, cb0, c1 - cb0, false);
                 }
                 if (kScore) {
                     float ax, ay, az, aw;
@@ -1397,11 +1441,15 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         if (kColGroups == 2 && pl.h_split && cw == pl.hc && (cw >> 2) <= 32) {
                             // two K halves, each split over the two column groups: the down-projection starts on the
                             // first half while the second is converted
-                            const int qw = cw >> 2;
-                            acc_to_tmem_operand_half(th, cg * qw, qw, 1 + q, pl.h_split == 2);
-                            arrive_issuer(t, QB_BAR_AH_READY, false);
-                            acc_to_tmem_operand_half(th, (cw >> 1) + cg * qw, qw, 1 + q, pl.h_split == 2);
-                            arrive_issuer(t, QB_BAR_AH2_READY, false);
+                            if (pl.h_split == 2) {
+                                const int qw = cw >> 2;
+                                acc_to_tmem_operand_half(th, cg * qw, qw, 1 + q, true);
+                                arrive_issuer(t, QB_BAR_AH_READY, false);
+                                acc_to_tmem_operand_half(th, (cw >> 1) + cg * qw, qw, 1 + q, true);
+                                arrive_issuer(t, QB_BAR_AH2_READY, false);
+                            } else {
+                                acc_to_tmem_operand_split(th, cw, cg, 1 + q, [&](int h) { arrive_issuer(t, h ? QB_BAR_AH2_READY : QB_BAR_AH_READY, false); });
+                            }
                         } else if (kColGroups == 4 && cw == 128) {     // one 32-column block per warp
                             acc_to_tmem_operand_half(th, cg * 32, 32, 1 + q, pl.h_split == 2);
                             arrive_issuer(t, QB_BAR_AH_READY, false);

@@ -1,8 +1,6 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "contract or fused or golden or chunk or determin or ragged or full" 2>&1 | tail -5
 B="python bench.py --steps 5 --warmup 3 --no-extras --no-cpu-baseline --no-e2e --no-decode"
-for w in c2 q1; do
-  $B --workload $w > gpurun_out/ab_${w}_ew16.json 2>gpurun_out/ab_${w}_ew16.err
-  QB_BLK32=1 $B --workload $w > gpurun_out/ab_${w}_ew16blk.json 2>/dev/null
-  QINCO_B200_LIB=$PWD/qinco_b200/variants/ew8.so $B --workload $w > gpurun_out/ab_${w}_ew8.json 2>/dev/null
-done
+QB_NO_FUSE=1 $B --workload c2 > gpurun_out/ab_c2_nofuse.json 2>/dev/null
+$B --workload c2 --plan-opts pair=2 > gpurun_out/ab_c2_pair.json 2>gpurun_out/ab_c2_pair.err
+$B --workload q1 --plan-opts pair=2 > gpurun_out/ab_q1_pair.json 2>/dev/null
+$B --workload c3 --plan-opts pair=2 > gpurun_out/ab_c3_pair.json 2>/dev/null
