@@ -500,7 +500,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS) + ["c5pw"])
-    ap.add_argument("--n", type=int, default=0, help="vectors per GPU per step (default: the workload's)")
+    ap.add_argument("--n", "--vectors", dest="n", type=int, default=0,
+                    help="vectors per GPU per step (default: the workload's); use --vectors under torchrun, whose own parser trips over --n")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-decode", action="store_true")

@@ -1,6 +1,4 @@
-set -x
-B="python bench.py --steps 5 --warmup 3 --no-extras --no-cpu-baseline --no-e2e --no-decode"
-QB_NO_FUSE=1 $B --workload c2 > gpurun_out/ab_c2_nofuse.json 2>/dev/null
-$B --workload c2 --plan-opts pair=2 > gpurun_out/ab_c2_pair.json 2>gpurun_out/ab_c2_pair.err
-$B --workload q1 --plan-opts pair=2 > gpurun_out/ab_q1_pair.json 2>/dev/null
-$B --workload c3 --plan-opts pair=2 > gpurun_out/ab_c3_pair.json 2>/dev/null
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus 2"
+timeout 200 $T --steps 5 --warmup 3 --no-extras --no-cpu-baseline --no-decode > gpurun_out/r02_bench_c2_n2.json 2> gpurun_out/r02_bench_c2_n2.err
+timeout 300 $T --workload c4 --vectors 300000 --steps 2 --warmup 3 --no-extras --no-cpu-baseline --no-e2e --no-decode > gpurun_out/r02_bench_c4_n2.json 2> gpurun_out/r02_bench_c4_n2.err
+tail -1 gpurun_out/r02_bench_c2_n2.json | cut -c1-300; tail -1 gpurun_out/r02_bench_c4_n2.json | cut -c1-300
