@@ -361,3 +361,17 @@ def test_hot_kernels_do_not_spill():
     assert len(hot) >= 10
     worst = max(hot, key=lambda t: t[1])
     assert worst[1] <= 128 and max(t[2] for t in hot) <= 256, worst
+
+
+def test_library_override_must_exist(monkeypatch):
+    """QINCO_B200_LIB (A-B builds of compile-time variants) never falls back silently to the default build."""
+    import importlib
+    from qinco_b200 import _lib
+    monkeypatch.setenv("QINCO_B200_LIB", "/nonexistent/libqinco_b200_variant.so")
+    saved = _lib._lib
+    _lib._lib = None
+    try:
+        with pytest.raises(RuntimeError, match="QINCO_B200_LIB"):
+            _lib.load()
+    finally:
+        _lib._lib = saved
