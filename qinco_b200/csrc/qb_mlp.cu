@@ -537,7 +537,78 @@ struct Tracer {
 // and multicasts it into the ring slot of both (cp.async.bulk ... .multicast::cluster), so a slab crosses L2 -> SM once per
 // two CTAs while every MMA stays local (cta_group::1, no cross-CTA accumulator traffic as in the pair kernel).  A ring
 // slot is recycled when the MMA warps of BOTH CTAs have committed it (multicast tcgen05.commit).
-template <bool kScore, bool kResident, bool kPair, bool kLoop = false, int kFuse = 0, bool kMcast = false>
+// Plan accessors.  The generic view reads the plan from the kernel-parameter bank.  The S128 view -- QINCo / QINCo2-S at
+// d = de = 128, dh = 256, K = 256 (BASELINE configs 1-2), exactly the plan make_step_plan() returns for it -- answers with
+// compile-time constants, so the epilogue's addresses become immediates and its shape branches disappear: between an
+// accumulator barrier and the first tcgen05.ld the generic code spends ~26 dependent uniform-datapath instructions
+// (8 % of the epilogue's time in the H phase alone, ncu).  L and the skip flag stay run-time (QINCo1 vs QINCo2, L = 2 / 16).
+#define QB_PLAN_FIELDS(X) X(D) X(De) X(Dh) X(K) X(has_proj) X(n_tiles) X(tmem_alloc_cols) X(n_ops_block) X(n_ops_out) X(hc) X(n_hchunk) \
+    X(oc) X(n_ochunk) X(tmem_e_col) X(tmem_h_col) X(tmem_tile_cols) X(smem_tres) X(smem_ring) X(slot_bytes) X(n_stage) X(h_split)   \
+    X(n_ops_pre) X(e_split) X(epart)
+template <int kShape>
+struct PlanView {
+    const QbStepPlan& q;
+#define X(f) __device__ __forceinline__ int f() const { return q.f; }
+    QB_PLAN_FIELDS(X)
+    X(L) X(skip)
+#undef X
+    __device__ __forceinline__ int smem_ae(int t) const { return q.smem_ae[t]; }
+    __device__ __forceinline__ int64_t block_w_bytes() const { return q.block_w_bytes; }
+};
+struct PlanS128 {       // == make_step_plan(128, 128, 256, L, 256, ...) with default options (launch_mlp compares field by field)
+    static constexpr int D = 128, De = 128, Dh = 256, K = 256, has_proj = 0, n_tiles = 2, tmem_alloc_cols = 512, n_ops_block = 4,
+                         n_ops_out = 0, hc = 128, n_hchunk = 2, oc = 0, n_ochunk = 0, tmem_e_col = 0, tmem_h_col = 128,
+                         tmem_tile_cols = 256, smem_tres = 65536, smem_ring = 98304, slot_bytes = 16384, n_stage = 7, h_split = 1,
+                         n_ops_pre = 0, e_split = 0, epart = 128, smem_ae1 = 32768, block_w_bytes = 131072;
+};
+template <>
+struct PlanView<1> {
+    const QbStepPlan& q;
+#define X(f) __device__ __forceinline__ constexpr int f() const { return PlanS128::f; }
+    QB_PLAN_FIELDS(X)
+#undef X
+    __device__ __forceinline__ int L() const { return q.L; }
+    __device__ __forceinline__ int skip() const { return q.skip; }
+    __device__ __forceinline__ constexpr int smem_ae(int t) const { return t * PlanS128::smem_ae1; }
+    __device__ __forceinline__ constexpr int64_t block_w_bytes() const { return PlanS128::block_w_bytes; }
+};
+bool plan_is_s128(const QbStepPlan& q) {
+#define X(f) if (q.f != PlanS128::f) return false;
+    QB_PLAN_FIELDS(X)
+#undef X
+    return q.smem_ae[0] == 0 && q.smem_ae[1] == PlanS128::smem_ae1 && q.block_w_bytes == PlanS128::block_w_bytes && q.pair == 0 && q.mcast == 0;
+}
+// The L384 view: the QINCo2-L family (de = dh = 384, K = 256: BASELINE configs 3-5, IVF-QINCo2-L) -- one tile per CTA, three H
+// chunks, E epilogue in two parts.  D and what follows from it (out_proj chunking) stay run-time: d = 128 / 96 / 768; so do the
+// pre-ops of the decode-loop plan, which is otherwise the same plan.
+#define QB_PLAN_FIELDS_L384(X) X(De) X(Dh) X(K) X(has_proj) X(n_tiles) X(tmem_alloc_cols) X(n_ops_block) X(hc) X(n_hchunk) X(tmem_e_col) \
+    X(tmem_h_col) X(tmem_tile_cols) X(smem_tres) X(smem_ring) X(slot_bytes) X(n_stage) X(h_split) X(e_split) X(epart)
+struct PlanL384 {
+    static constexpr int De = 384, Dh = 384, K = 256, has_proj = 1, n_tiles = 1, tmem_alloc_cols = 512, n_ops_block = 9, hc = 128,
+                         n_hchunk = 3, tmem_e_col = 0, tmem_h_col = 384, tmem_tile_cols = 512, smem_tres = -1, smem_ring = 98304,
+                         slot_bytes = 32768, n_stage = 3, h_split = 1, e_split = 1, epart = 192, smem_ae1 = 98304,
+                         block_w_bytes = 589824;
+};
+template <>
+struct PlanView<2> {
+    const QbStepPlan& q;
+#define X(f) __device__ __forceinline__ constexpr int f() const { return PlanL384::f; }
+    QB_PLAN_FIELDS_L384(X)
+#undef X
+#define X(f) __device__ __forceinline__ int f() const { return q.f; }
+    X(D) X(oc) X(n_ochunk) X(n_ops_out) X(n_ops_pre) X(L) X(skip)
+#undef X
+    __device__ __forceinline__ constexpr int smem_ae(int t) const { return t * PlanL384::smem_ae1; }
+    __device__ __forceinline__ constexpr int64_t block_w_bytes() const { return PlanL384::block_w_bytes; }
+};
+bool plan_is_l384(const QbStepPlan& q) {
+#define X(f) if (q.f != PlanL384::f) return false;
+    QB_PLAN_FIELDS_L384(X)
+#undef X
+    return q.smem_ae[0] == 0 && q.smem_ae[1] == PlanL384::smem_ae1 && q.block_w_bytes == PlanL384::block_w_bytes && q.pair == 0;
+}
+
+template <bool kScore, bool kResident, bool kPair, bool kLoop = false, int kFuse = 0, bool kMcast = false, int kShape = 0>
 __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_constant__ MlpParams p) {
     static_assert(!kMcast || (!kPair && !kResident && (kFuse == 0 || kFuse == 3)), "weight multicast: non-resident single-CTA-MMA variants");
     static_assert(!kLoop || (!kScore && !kResident && !kPair), "the decode loop is an apply-mode, single-CTA variant");
@@ -568,17 +639,19 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (uniform datapath)
-    const QbStepPlan& pl = p.plan;
-    const int n_ops = pl.n_ops_block + pl.n_ops_out;
-    const int NT = pl.n_tiles;
+    static_assert(kShape == 0 || (kShape == 1 && kResident && !kPair && !kLoop && !kMcast) || (kShape == 2 && !kResident && !kPair),
+                  "fixed-shape views: S128 for the resident score kernels, L384 for the one-tile-per-CTA kernels");
+    const PlanView<kShape> pl{p.plan};
+    const int n_ops = pl.n_ops_block() + pl.n_ops_out();
+    const int NT = pl.n_tiles();
     // One tile set walks `n_ls` steps (1 outside the decode loop); a step is the phases  -1: pre-ops (decode loop only:
     // u = Wx . xhat), 0 .. L-1: residual blocks (one shared op list), L: out_proj ops.
     const int n_ls = kLoop ? p.n_loop_steps : 1;
     constexpr int kFirstPhase = kLoop ? -1 : 0;
     auto phase_ops = [&](int ph, int& i0, int& i1, size_t& w_rel) {
-        if (ph < 0) { i0 = n_ops; i1 = n_ops + pl.n_ops_pre; w_rel = 0; }
-        else if (ph < pl.L) { i0 = 0; i1 = pl.n_ops_block; w_rel = (size_t)ph * (size_t)pl.block_w_bytes; }
-        else { i0 = pl.n_ops_block; i1 = n_ops; w_rel = 0; }
+        if (ph < 0) { i0 = n_ops; i1 = n_ops + pl.n_ops_pre(); w_rel = 0; }
+        else if (ph < pl.L()) { i0 = 0; i1 = pl.n_ops_block(); w_rel = (size_t)ph * (size_t)pl.block_w_bytes(); }
+        else { i0 = pl.n_ops_block(); i1 = n_ops; w_rel = 0; }
     };
     const int64_t n_tiles = (p.n_rows + QB_TILE_M - 1) / QB_TILE_M;
     // Work units ("sets" of NT tiles).  Default: NT consecutive tiles, sets strided over the CTAs.  Resident mode (score,
@@ -626,19 +699,19 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         for (int b = 0; b < 3; b++) { mbar_init(smem_u32(&rows_full[b]), 1); mbar_init(smem_u32(&rows_empty[b]), kEpiThreads); }
         for (int s = 0; s < QB_MAX_STAGE; s++) {
             mbar_init(smem_u32(&w_full[s]), (kPair && leader) ? 2 : 1);   // leader: own half landed + the peer's relay
-            mbar_init(smem_u32(&w_empty[s]), (uint32_t)pl.n_tiles * (kMcast ? 2u : 1u));   // released by every tile slot's MMA warp (of both CTAs with multicast)
+            mbar_init(smem_u32(&w_empty[s]), (uint32_t)pl.n_tiles() * (kMcast ? 2u : 1u));   // released by every tile slot's MMA warp (of both CTAs with multicast)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
         if (kPair) {
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                         "r"((uint32_t)pl.tmem_alloc_cols)
+                         "r"((uint32_t)pl.tmem_alloc_cols())
                          : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         } else {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                         "r"((uint32_t)pl.tmem_alloc_cols)
+                         "r"((uint32_t)pl.tmem_alloc_cols())
                          : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
@@ -660,7 +733,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     const uint32_t a_sfull = opaque(smem_u32(&sel_full[0])), a_sempty = opaque(smem_u32(&sel_empty[0]));
     const uint32_t a_stash = opaque(smem_u32(&sel_stash[0])), a_skey = opaque(smem_u32(&sel_key[0]));
     auto bar_addr = [&](int t, int b) { return a_bars + (uint32_t)(t * QB_BAR_COUNT + b) * 8u; };
-    const uint32_t tile_cols = (uint32_t)pl.tmem_tile_cols;
+    const uint32_t tile_cols = (uint32_t)pl.tmem_tile_cols();
 
     // (unconditional on purpose: ptxas only budgets registers per region when every path executes the setmaxnreg)
     if (warp >= kEpiWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSvcRegs));
@@ -670,9 +743,9 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         uint32_t stage = 0, phase = 0;
         if (kResident) {    // this CTA's quarter of T_m and C_m: per 4-column block 64 codes x 16 B = 1 KB, contiguous in the tables
             if (elect_one()) {
-                mbar_expect_tx(a_tres, (uint32_t)pl.D * 256u);
-                for (int c4 = 0; c4 < (pl.D >> 2); c4++)
-                    bulk_g2s(smem_base + pl.smem_tres + c4 * 1024, p.cb_blk + ((size_t)c4 * pl.K + hq * 64) * 4, 1024, a_tres);
+                mbar_expect_tx(a_tres, (uint32_t)pl.D() * 256u);
+                for (int c4 = 0; c4 < (pl.D() >> 2); c4++)
+                    bulk_g2s(smem_base + pl.smem_tres() + c4 * 1024, p.cb_blk + ((size_t)c4 * pl.K() + hq * 64) * 4, 1024, a_tres);
             }
             __syncwarp();
         }
@@ -683,13 +756,13 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             const int b = (int)(k % 3);
             mbar_wait((a_rempty + (uint32_t)(b) * 8u), (uint32_t)(((k / 3) & 1) ^ 1), p.err_flag, 0x600 + b);
             if (elect_one()) {
-                const uint32_t de_b = (uint32_t)pl.De * 4u, d_b = (uint32_t)pl.D * 4u;
+                const uint32_t de_b = (uint32_t)pl.De() * 4u, d_b = (uint32_t)pl.D() * 4u;
                 mbar_expect_tx((a_rfull + (uint32_t)(b) * 8u), 4u * (de_b + d_b));
                 for (int t = 0; t < 4; t++) {       // tile slot t / 2, beam t % 2 of the tile
                     int64_t beam = 4 * set + t;
                     if (beam >= n_beams) beam = 0;
-                    bulk_g2s((a_beam + (uint32_t)(((b * 2 + (t >> 1)) * 2 + (t & 1)) * 256) * 4u), p.u + beam * pl.De, de_b, (a_rfull + (uint32_t)(b) * 8u));
-                    bulk_g2s((a_beam + (uint32_t)(((b * 2 + (t >> 1)) * 2 + (t & 1)) * 256 + pl.De) * 4u), p.r + beam * pl.D, d_b, (a_rfull + (uint32_t)(b) * 8u));
+                    bulk_g2s((a_beam + (uint32_t)(((b * 2 + (t >> 1)) * 2 + (t & 1)) * 256) * 4u), p.u + beam * pl.De(), de_b, (a_rfull + (uint32_t)(b) * 8u));
+                    bulk_g2s((a_beam + (uint32_t)(((b * 2 + (t >> 1)) * 2 + (t & 1)) * 256 + pl.De()) * 4u), p.r + beam * pl.D(), d_b, (a_rfull + (uint32_t)(b) * 8u));
                 }
             }
             __syncwarp();
@@ -699,7 +772,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
         QB_FOR_SETS(it_p, set) {
             if (kResident) push_rows(set + set_stride, kset + 1);
             for (int ls = 0; ls < n_ls; ls++)
-            for (int l = kFirstPhase; l <= pl.L; l++) {
+            for (int l = kFirstPhase; l <= pl.L(); l++) {
                 int i0, i1;
                 size_t w_rel;
                 phase_ops(l, i0, i1, w_rel);
@@ -716,16 +789,16 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         if (elect_one()) {
                             if (kMcast) {       // the whole slab lands here: this CTA's half and the peer's, both multicast
                                 mbar_expect_tx((a_wfull + stage * 8u), full);
-                                bulk_g2s_mcast(smem_base + pl.smem_ring + stage * pl.slot_bytes + cta_rank * bytes,
+                                bulk_g2s_mcast(smem_base + pl.smem_ring() + stage * pl.slot_bytes() + cta_rank * bytes,
                                                src + (size_t)s * slab_bytes + cta_rank * bytes, bytes, (a_wfull + stage * 8u), (uint16_t)3);
                             } else {
                             mbar_expect_tx((a_wfull + stage * 8u), bytes);
-                            bulk_g2s(smem_base + pl.smem_ring + stage * pl.slot_bytes,
+                            bulk_g2s(smem_base + pl.smem_ring() + stage * pl.slot_bytes(),
                                      src + (size_t)s * slab_bytes + (kPair ? cta_rank * bytes : 0u), bytes, (a_wfull + stage * 8u));
                             }
                         }
                         __syncwarp();
-                        if (++stage == (uint32_t)pl.n_stage) { stage = 0; phase ^= 1; }
+                        if (++stage == (uint32_t)pl.n_stage()) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -744,16 +817,16 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             if (t == 0) {
                 uint32_t stage = 0, phase = 0;
                 for (int64_t set = set_first; more_sets(set); set += set_stride) {
-                    for (int l = 0; l <= pl.L; l++) {
-                        const int i0 = (l < pl.L) ? 0 : pl.n_ops_block;
-                        const int i1 = (l < pl.L) ? pl.n_ops_block : n_ops;
+                    for (int l = 0; l <= pl.L(); l++) {
+                        const int i0 = (l < pl.L()) ? 0 : pl.n_ops_block();
+                        const int i1 = (l < pl.L()) ? pl.n_ops_block() : n_ops;
                         for (int i = i0; i < i1; i++) {
                             const uint32_t n_slab = p.ops[i].n_slab;
                             for (uint32_t s = 0; s < n_slab; s++) {
                                 mbar_wait((a_wfull + stage * 8u), phase, p.err_flag, 0x700 + stage);
                                 if (elect_one()) mbar_arrive_cluster(mapa_rank((a_wfull + stage * 8u), 0));
                                 __syncwarp();
-                                if (++stage == (uint32_t)pl.n_stage) { stage = 0; phase ^= 1; }
+                                if (++stage == (uint32_t)pl.n_stage()) { stage = 0; phase ^= 1; }
                             }
                         }
                     }
@@ -765,7 +838,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             // settle the PREVIOUS set: by then the other three code quarters have normally reported too, so the wait is a
             // formality; whoever holds the global winner adds xhat_b to its stashed o and writes xhat' and the history.
             const int lane = tid & 31;
-            const int D = pl.D;
+            const int D = pl.D();
             auto ld_acquire_u32 = [](const uint32_t* ptr) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory"); return v; };
             auto ld_relaxed_u64 = [](const unsigned long long* ptr) { unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory"); return v; };
             auto settle = [&](int64_t set, int t, int buf) {
@@ -859,13 +932,13 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             uint32_t par = 0;
             Tracer tr;
             tr.init(p, 1 + t, (tid & 31) == 0);      // trace roles 1 / 2: MMA warps of tile slots 0 / 1
-            const uint32_t ring_lo = ((smem_base + pl.smem_ring) >> 4) & 0x3FFFu;    // descriptor address fields (14 bits, 16-B units)
-            const uint32_t slot_lo = (uint32_t)pl.slot_bytes >> 4;
+            const uint32_t ring_lo = ((smem_base + pl.smem_ring()) >> 4) & 0x3FFFu;    // descriptor address fields (14 bits, 16-B units)
+            const uint32_t slot_lo = (uint32_t)pl.slot_bytes() >> 4;
             const uint32_t tcol = tmem_base + (uint32_t)t * tile_cols;
-            const uint32_t ae_lo = ((smem_base + pl.smem_ae[t]) >> 4) & 0x3FFFu;
+            const uint32_t ae_lo = ((smem_base + pl.smem_ae(t)) >> 4) & 0x3FFFu;
             QB_FOR_SETS(it_m, set) {
                 for (int ls = 0; ls < n_ls; ls++)
-                for (int l = kFirstPhase; l <= pl.L; l++) {
+                for (int l = kFirstPhase; l <= pl.L(); l++) {
                     int i0, i1;
                     size_t w_rel_unused;
                     phase_ops(l, i0, i1, w_rel_unused);
@@ -935,7 +1008,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                             a_cur += (uint32_t)nk * (from_smem ? ((2 * kAkcBytes) >> 4) : 8u);
                             j0 += (uint32_t)nk;
                             acc = 1;
-                            if (++stage == (uint32_t)pl.n_stage) { stage = 0; phase ^= 1; }
+                            if (++stage == (uint32_t)pl.n_stage()) { stage = 0; phase ^= 1; }
                         }
                         tr.ev(0x400 + i);
                     }
@@ -966,7 +1039,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 else mbar_arrive(bar_addr(t, bar));
             }
         };
-        const int De = pl.De, K = pl.K, D = pl.D;
+        const int De = pl.De(), K = pl.K(), D = pl.D();
         int e0c, e1c, o0c, o1c;             // this thread's columns of e / of the output (no out_proj)
         group_range(De, cg, e0c, e1c);
         group_range(D, cg, o0c, o1c);
@@ -998,7 +1071,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             const uint32_t x_lo_chunk = (uint32_t)(D >> 3);        // k-chunk of the first xhat_lo column
             // n (16 or 32) columns of xhat starting at column c: fp16 hi / lo parts -> A operand k-chunks of tile slot t
             auto put_operand = [&](int t, int c, int n, const float (&x)[32]) {
-                const uint32_t dst = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
+                const uint32_t dst = smem_base + pl.smem_ae(t) + (uint32_t)r * 16u;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     if (8 * j < n) {
@@ -1053,7 +1126,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             };
             // init of a step: Eacc <- T_m[code] (fp32); the operand [xhat_hi | xhat_lo] is already in shared memory
             auto init_loop = [&](int t, int code, const float* t_blk) {
-                const uint32_t tl = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col;
+                const uint32_t tl = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col();
 #pragma unroll 1
                 for (int c = e0c; c < e1c; c += 32) {
                     const int n = (e1c - c) >= 32 ? 32 : 16;
@@ -1075,9 +1148,9 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             // the single out_proj chunk in Hacc.  Last step: scale / shift and write the result; otherwise write the running
             // xhat and the next step's operand.
             auto final_loop = [&](int t, int64_t row, bool valid, int code, const float* cb_blk, bool last) {
-                const uint32_t taddr = lane_base + (uint32_t)t * tile_cols + (pl.has_proj ? pl.tmem_h_col : pl.tmem_e_col);
+                const uint32_t taddr = lane_base + (uint32_t)t * tile_cols + (pl.has_proj() ? pl.tmem_h_col() : pl.tmem_e_col());
                 float* xrow = p.xhat_out + row * D;
-                const bool skip = pl.skip != 0;
+                const bool skip = pl.skip() != 0;
 #pragma unroll 1
                 for (int c = o0c; c < o1c; c += 32) {
                     const int n = (o1c - c) >= 32 ? 32 : 16;
@@ -1135,25 +1208,25 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
 #pragma unroll 1
                     for (int t = 0; t < NT; t++) {
                         wait_l(t, QB_BAR_EACC_FULL, 0x425);
-                        if (pl.L > 0 || pl.has_proj) {      // (no GEMM follows in a block-less model without out_proj)
-                            acc_to_smem_operand(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, e0c, e1c,
-                                                smem_base + pl.smem_ae[t] + (uint32_t)r * 16u);
+                        if (pl.L() > 0 || pl.has_proj()) {      // (no GEMM follows in a block-less model without out_proj)
+                            acc_to_smem_operand(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col(), e0c, e1c,
+                                                smem_base + pl.smem_ae(t) + (uint32_t)r * 16u);
                             arrive_issuer(t, QB_BAR_AE_READY, true);
                         }
                     }
 #pragma unroll 1
-                    for (int l = 0; l < pl.L; l++) {
+                    for (int l = 0; l < pl.L(); l++) {
 #pragma unroll 1
-                        for (int j = 0; j < pl.n_hchunk; j++) {
-                            const int cw = min(pl.hc, pl.Dh - j * pl.hc);
+                        for (int j = 0; j < pl.n_hchunk(); j++) {
+                            const int cw = min(pl.hc(), pl.Dh() - j * pl.hc());
                             int c0, c1;
                             group_range(cw, cg, c0, c1);
 #pragma unroll 1
                             for (int t = 0; t < NT; t++) {
                                 wait_l(t, QB_BAR_HACC_FULL, 0x424);
-                                const uint32_t th = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
-                                if (kColGroups == 2 && pl.h_split && cw == pl.hc && (cw >> 2) <= 32) {
-                                    if (pl.h_split == 2) {
+                                const uint32_t th = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col();
+                                if (kColGroups == 2 && pl.h_split() && cw == pl.hc() && (cw >> 2) <= 32) {
+                                    if (pl.h_split() == 2) {
                                         const int qw = cw >> 2;
                                         acc_to_tmem_operand_half(th, cg * qw, qw, 1 + q, true);
                                         arrive_issuer(t, QB_BAR_AH_READY, false);
@@ -1163,30 +1236,30 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                                         acc_to_tmem_operand_split(th, cw, cg, 1 + q, [&](int h) { arrive_issuer(t, h ? QB_BAR_AH2_READY : QB_BAR_AH_READY, false); });
                                     }
                                 } else if (kColGroups == 4 && cw == 128) {     // one 32-column block per warp
-                                    acc_to_tmem_operand_half(th, cg * 32, 32, 1 + q, pl.h_split == 2);
+                                    acc_to_tmem_operand_half(th, cg * 32, 32, 1 + q, pl.h_split() == 2);
                                     arrive_issuer(t, QB_BAR_AH_READY, false);
-                                    if (pl.h_split && cw == pl.hc) arrive_issuer(t, QB_BAR_AH2_READY, false);
+                                    if (pl.h_split() && cw == pl.hc()) arrive_issuer(t, QB_BAR_AH2_READY, false);
                                 } else {
                                     acc_to_tmem_operand(th, c0, c1, 1 + q);
                                     arrive_issuer(t, QB_BAR_AH_READY, false);
-                                    if (kColGroups != 2 && pl.h_split && cw == pl.hc) arrive_issuer(t, QB_BAR_AH2_READY, false);
+                                    if (kColGroups != 2 && pl.h_split() && cw == pl.hc()) arrive_issuer(t, QB_BAR_AH2_READY, false);
                                 }
                             }
                         }
-                        if (l + 1 < pl.L || pl.has_proj) {
+                        if (l + 1 < pl.L() || pl.has_proj()) {
 #pragma unroll 1
                             for (int t = 0; t < NT; t++) {
-                                const uint32_t te = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col;
-                                const uint32_t sd = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
-                                const int n_ep = pl.e_split ? 2 : 1;
+                                const uint32_t te = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col();
+                                const uint32_t sd = smem_base + pl.smem_ae(t) + (uint32_t)r * 16u;
+                                const int n_ep = pl.e_split() ? 2 : 1;
 #pragma unroll 1
                                 for (int ep = 0; ep < n_ep; ep++) {
                                     int h0 = e0c, h1 = e1c;
-                                    if (pl.e_split) {
-                                        group_range(ep == 0 ? pl.epart : De - pl.epart, cg, h0, h1);
-                                        if (ep) { h0 += pl.epart; h1 += pl.epart; }
+                                    if (pl.e_split()) {
+                                        group_range(ep == 0 ? pl.epart() : De - pl.epart(), cg, h0, h1);
+                                        if (ep) { h0 += pl.epart(); h1 += pl.epart(); }
                                     }
-                                    wait_l(t, (pl.e_split && ep == 0) ? QB_BAR_EACC_HALF : QB_BAR_EACC_FULL, 0x425);
+                                    wait_l(t, (pl.e_split() && ep == 0) ? QB_BAR_EACC_HALF : QB_BAR_EACC_FULL, 0x425);
                                     acc_to_smem_operand(te, h0, h1, sd);
                                 }
                                 arrive_issuer(t, QB_BAR_AE_READY, true);
@@ -1195,9 +1268,9 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     }
 #pragma unroll 1
                     for (int t = 0; t < NT; t++) {
-                        if (pl.has_proj) wait_l(t, QB_BAR_HACC_FULL, 0x434);
-                        else if (pl.L > 0) {
-                            if (pl.e_split) wait_l(t, QB_BAR_EACC_HALF, 0x437);
+                        if (pl.has_proj()) wait_l(t, QB_BAR_HACC_FULL, 0x434);
+                        else if (pl.L() > 0) {
+                            if (pl.e_split()) wait_l(t, QB_BAR_EACC_HALF, 0x437);
                             wait_l(t, QB_BAR_EACC_FULL, 0x435);
                         }
                         const int64_t row = t ? row1 : row0;
@@ -1275,7 +1348,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             // ---- init: e0 = T_m[code] + u_b over this thread's columns ------------------------------------------------
             auto init_tile = [&](int t, int code, int64_t beam, int rb) {
                 const uint32_t tl = lane_base + (uint32_t)t * tile_cols;
-                const uint32_t ae_dst = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
+                const uint32_t ae_dst = smem_base + pl.smem_ae(t) + (uint32_t)r * 16u;
                 const float* up = p.u + beam * De;
                 if (!kResident && cg == 0 && r * 32 < De) prefetch_l1(up + r * 32);   // the per-beam row is shared by many rows: pull it into L1
                 // 32 columns per batch: operand loads first, one wide TMEM store, four shared-memory k-chunk rows
@@ -1305,11 +1378,11 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     if (n > 16) {
                         half16(1);
                         __syncwarp();
-                        tmem_st32(tl + pl.tmem_e_col + c, e);
+                        tmem_st32(tl + pl.tmem_e_col() + c, e);
                         to_smem(0); to_smem(1); to_smem(2); to_smem(3);
                     } else {
                         __syncwarp();
-                        tmem_st16p(tl + pl.tmem_e_col + c, e);
+                        tmem_st16p(tl + pl.tmem_e_col() + c, e);
                         to_smem(0); to_smem(1);
                     }
                 };
@@ -1359,8 +1432,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                                   float4 (&cb)[8], float& acc, uint32_t rows_a) {
                 const float* src = (kScore ? p.r : p.xhat_in) + beam * D + d0;         // not used in resident mode
                 const uint32_t rs_a = rows_a + (uint32_t)d0 * 4u;                        // resident: r_b row in shared memory
-                const uint32_t cs_a = smem_base + (uint32_t)pl.smem_tres + (uint32_t)(r & 63) * 16u;   // resident C_m quarter
-                const bool skip = pl.skip != 0;
+                const uint32_t cs_a = smem_base + (uint32_t)pl.smem_tres() + (uint32_t)(r & 63) * 16u;   // resident C_m quarter
+                const bool skip = pl.skip() != 0;
                 f32x2 axy = 0ull, azw = 0ull;                       // four independent accumulation chains, in packed pairs
                 // one block of <= 32 accumulator columns already requested into v (`waited`: their tcgen05.ld has been waited for)
                 auto proc32 = [&](uint32_t (&v)[32], int cb0, int n, bool waited0) {
@@ -1427,21 +1500,21 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 }
             };
 #pragma unroll 1
-            for (int l = 0; l < pl.L; l++) {
+            for (int l = 0; l < pl.L(); l++) {
 #pragma unroll 1
-                for (int j = 0; j < pl.n_hchunk; j++) {
-                    const int cw = min(pl.hc, pl.Dh - j * pl.hc);
+                for (int j = 0; j < pl.n_hchunk(); j++) {
+                    const int cw = min(pl.hc(), pl.Dh() - j * pl.hc());
                     int c0, c1;
                     group_range(cw, cg, c0, c1);
 #pragma unroll 1
                     for (int t = 0; t < NT; t++) {
                         wait_bar(t, QB_BAR_HACC_FULL, 0x404);
                         tr.ev(3 + 0x80 * t);
-                        const uint32_t th = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
-                        if (kColGroups == 2 && pl.h_split && cw == pl.hc && (cw >> 2) <= 32) {
+                        const uint32_t th = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col();
+                        if (kColGroups == 2 && pl.h_split() && cw == pl.hc() && (cw >> 2) <= 32) {
                             // two K halves, each split over the two column groups: the down-projection starts on the
                             // first half while the second is converted
-                            if (pl.h_split == 2) {
+                            if (pl.h_split() == 2) {
                                 const int qw = cw >> 2;
                                 acc_to_tmem_operand_half(th, cg * qw, qw, 1 + q, true);
                                 arrive_issuer(t, QB_BAR_AH_READY, false);
@@ -1451,33 +1524,33 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                                 acc_to_tmem_operand_split(th, cw, cg, 1 + q, [&](int h) { arrive_issuer(t, h ? QB_BAR_AH2_READY : QB_BAR_AH_READY, false); });
                             }
                         } else if (kColGroups == 4 && cw == 128) {     // one 32-column block per warp
-                            acc_to_tmem_operand_half(th, cg * 32, 32, 1 + q, pl.h_split == 2);
+                            acc_to_tmem_operand_half(th, cg * 32, 32, 1 + q, pl.h_split() == 2);
                             arrive_issuer(t, QB_BAR_AH_READY, false);
-                            if (pl.h_split && cw == pl.hc) arrive_issuer(t, QB_BAR_AH2_READY, false);   // (a split plan waits for both)
+                            if (pl.h_split() && cw == pl.hc()) arrive_issuer(t, QB_BAR_AH2_READY, false);   // (a split plan waits for both)
                         } else {
                             acc_to_tmem_operand(th, c0, c1, 1 + q);
                             arrive_issuer(t, QB_BAR_AH_READY, false);
-                            if (kColGroups != 2 && pl.h_split && cw == pl.hc) arrive_issuer(t, QB_BAR_AH2_READY, false);   // (a split plan waits for both)
+                            if (kColGroups != 2 && pl.h_split() && cw == pl.hc()) arrive_issuer(t, QB_BAR_AH2_READY, false);   // (a split plan waits for both)
                         }
                         tr.ev(4 + 0x80 * t);
                     }
                 }
-                if (l + 1 < pl.L || pl.has_proj) {
+                if (l + 1 < pl.L() || pl.has_proj()) {
 #pragma unroll 1
                     for (int t = 0; t < NT; t++) {
-                        const uint32_t te = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col;
-                        const uint32_t sd = smem_base + pl.smem_ae[t] + (uint32_t)r * 16u;
+                        const uint32_t te = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col();
+                        const uint32_t sd = smem_base + pl.smem_ae(t) + (uint32_t)r * 16u;
                         // with e_split the first column part is final while the second part's MMAs still run (ONE call site
                         // of the conversion on purpose: a second inlined copy made ptxas spill ~900 B per thread)
-                        const int n_ep = pl.e_split ? 2 : 1;
+                        const int n_ep = pl.e_split() ? 2 : 1;
 #pragma unroll 1
                         for (int ep = 0; ep < n_ep; ep++) {
                             int h0 = e0c, h1 = e1c;
-                            if (pl.e_split) {
-                                group_range(ep == 0 ? pl.epart : De - pl.epart, cg, h0, h1);
-                                if (ep) { h0 += pl.epart; h1 += pl.epart; }
+                            if (pl.e_split()) {
+                                group_range(ep == 0 ? pl.epart() : De - pl.epart(), cg, h0, h1);
+                                if (ep) { h0 += pl.epart(); h1 += pl.epart(); }
                             }
-                            wait_bar(t, (pl.e_split && ep == 0) ? QB_BAR_EACC_HALF : QB_BAR_EACC_FULL, 0x405);
+                            wait_bar(t, (pl.e_split() && ep == 0) ? QB_BAR_EACC_HALF : QB_BAR_EACC_FULL, 0x405);
                             tr.ev(5 + 0x80 * t);
                             acc_to_smem_operand(te, h0, h1, sd);
                         }
@@ -1540,10 +1613,10 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     const unsigned long long key = k0 < k1 ? k0 : k1;
                     const int wrow = 64 * h + ((int)(key & 0xffffffffull) & 63);        // tile row of the local winner
                     if (key != ~0ull && (wrow >> 5) == q) {                              // warp-uniform: this warp owns that row
-                        const uint32_t taddr = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col;
-                        const uint32_t cs_a = smem_base + (uint32_t)pl.smem_tres + (uint32_t)(wrow & 63) * 16u;
+                        const uint32_t taddr = lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col();
+                        const uint32_t cs_a = smem_base + (uint32_t)pl.smem_tres() + (uint32_t)(wrow & 63) * 16u;
                         const uint32_t st = a_stash + (uint32_t)(((buf * 2 + t) * 2 + h) * 128) * 4u;
-                        const bool skip = pl.skip != 0;
+                        const bool skip = pl.skip() != 0;
 #pragma unroll 1
                         for (int c = o0c; c < o1c; c += 32) {
                             const int n = o1c - c;
@@ -1572,7 +1645,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
             };
             const int64_t set_next = set + set_stride;
             const bool has_next = more_sets(set_next);
-            if (!pl.has_proj) {
+            if (!pl.has_proj()) {
                 const int rbn = (int)((kset + 1) % 3);
 #pragma unroll 1
                 for (int t = 0; t < NT; t++) {
@@ -1581,9 +1654,9 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     for (int i = 0; i < 8; i++) cb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     // inputs of the final epilogue travel while the last down-projection runs
                     if (!kResident && cg == 0 && r * 32 < D) prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
-                    if (!kResident && pl.skip && o0c < o1c) load_row32(cb, p.cb_blk, t ? code1 : code0, o0c, o1c - o0c);
-                    if (pl.L > 0 && pl.e_split) wait_bar(t, QB_BAR_EACC_HALF, 0x407);
-                    if (pl.L > 0) wait_bar(t, QB_BAR_EACC_FULL, 0x405);
+                    if (!kResident && pl.skip() && o0c < o1c) load_row32(cb, p.cb_blk, t ? code1 : code0, o0c, o1c - o0c);
+                    if (pl.L() > 0 && pl.e_split()) wait_bar(t, QB_BAR_EACC_HALF, 0x407);
+                    if (pl.L() > 0) wait_bar(t, QB_BAR_EACC_FULL, 0x405);
                     tr.ev(5 + 0x80 * t);
                     float a = 0.f;
                     // resident launches: code / beam / row follow from (set, tile slot, thread); nothing is carried in registers
@@ -1591,7 +1664,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     const int code_t = kResident ? hq * 64 + (r & 63) : (t ? code1 : code0);
                     const int64_t row_t = kResident ? beam_t * 256 + code_t : (t ? row1 : row0);
                     const bool valid_t = kResident ? beam_t < n_beams : (t ? valid1 : valid0);
-                    final_cols(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col, o0c, o1c, 0, code_t, beam_t,
+                    final_cols(lane_base + (uint32_t)t * tile_cols + pl.tmem_e_col(), o0c, o1c, 0, code_t, beam_t,
                                row_t, valid_t, cb, a,
                                a_beam + (uint32_t)(((rb * 2 + t) * 2 + (r >> 6)) * 256 + De) * 4u);
                     tc_fence_before();
@@ -1612,9 +1685,9 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                 primed = has_next;
             }
             // ---- out_proj chunks ---------------------------------------------------------------------------------------
-            if (pl.has_proj) {
-                for (int qq = 0; qq < pl.n_ochunk; qq++) {
-                    const int cw = min(pl.oc, D - qq * pl.oc);
+            if (pl.has_proj()) {
+                for (int qq = 0; qq < pl.n_ochunk(); qq++) {
+                    const int cw = min(pl.oc(), D - qq * pl.oc());
                     int c0, c1;
                     group_range(cw, cg, c0, c1);
 #pragma unroll 1
@@ -1622,14 +1695,14 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                         float4 cb[8];
 #pragma unroll
                         for (int i = 0; i < 8; i++) cb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (pl.skip && c0 < c1) load_row32(cb, p.cb_blk, t ? code1 : code0, qq * pl.oc + c0, c1 - c0);
+                        if (pl.skip() && c0 < c1) load_row32(cb, p.cb_blk, t ? code1 : code0, qq * pl.oc() + c0, c1 - c0);
                         if (qq == 0 && cg == 0 && r * 32 < D) prefetch_l1((kScore ? p.r : p.xhat_in) + (t ? beam1 : beam0) * D + r * 32);
                         wait_bar(t, QB_BAR_HACC_FULL, 0x414);
-                        const uint32_t ta = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col;
+                        const uint32_t ta = lane_base + (uint32_t)t * tile_cols + pl.tmem_h_col();
                         float a = t ? acc1 : acc0;
-                        final_cols(ta, c0, c1, qq * pl.oc, t ? code1 : code0, t ? beam1 : beam0, t ? row1 : row0, t ? valid1 : valid0, cb, a, 0u);
+                        final_cols(ta, c0, c1, qq * pl.oc(), t ? code1 : code0, t ? beam1 : beam0, t ? row1 : row0, t ? valid1 : valid0, cb, a, 0u);
                         if (t) acc1 = a; else acc0 = a;
-                        if (qq + 1 < pl.n_ochunk) arrive_issuer(t, QB_BAR_HACC_FREE, false);
+                        if (qq + 1 < pl.n_ochunk()) arrive_issuer(t, QB_BAR_HACC_FREE, false);
                         else tc_fence_before();
                     }
                 }
@@ -1734,7 +1807,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     if (!(p.dbg & 1) && __any_sync(0xffffffffu, slot != 0xff)) {
                         int c0, c1;
                         group_range(D, cg, c0, c1);
-                        const uint32_t ta = lane_base + (pl.has_proj ? pl.tmem_h_col : pl.tmem_e_col);
+                        const uint32_t ta = lane_base + (pl.has_proj() ? pl.tmem_h_col() : pl.tmem_e_col());
                         const uint32_t st = opaque(smem_u32(&selb_stash[0])) + (uint32_t)((s_idx * F_out + (slot & 0x3f)) * D) * 4u;
 #pragma unroll 1
                         for (int c = c0; c < c1; c += 32) {
@@ -1769,7 +1842,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                             const float4 o = lds4(opaque(smem_u32(&selb_stash[0])) + (uint32_t)(((sgm * F_out + slot) * D) + 4 * d4) * 4u);
                             const float4 xi = ldg4(p.xhat_in + (vs * p.F_in + parent) * D + 4 * d4);
                             float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (pl.skip) {
+                            if (pl.skip()) {
                                 const int code = p.A > 0 ? (int)__ldg(p.idx + (vs * p.F_in + parent) * p.A + slot_a) : slot_a;
                                 cv = ldg4(p.cb_blk + ((size_t)d4 * K + code) * 4);
                             }
@@ -1792,7 +1865,7 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
                     }
                     (void)a_rd; (void)a_rf;
                 }
-            } else if (pl.has_proj && kScore) {
+            } else if (pl.has_proj() && kScore) {
                 publish_dist(0, acc0, row0, valid0);
                 if (NT > 1) publish_dist(1, acc1, row1, valid1);
             }
@@ -1811,11 +1884,11 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     if (warp == kMmaWarp) {
         if (kPair)
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                         "r"((uint32_t)pl.tmem_alloc_cols)
+                         "r"((uint32_t)pl.tmem_alloc_cols())
                          : "memory");
         else
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                         "r"((uint32_t)pl.tmem_alloc_cols)
+                         "r"((uint32_t)pl.tmem_alloc_cols())
                          : "memory");
     }
 }
@@ -1832,6 +1905,9 @@ cudaError_t mlp_set_smem_attr(int smem_bytes) {
                          (const void*)qb_mlp_kernel<false, false, false>, (const void*)qb_mlp_kernel<true, false, true>,
                          (const void*)qb_mlp_kernel<true, true, true>, (const void*)qb_mlp_kernel<false, false, true>,
                          (const void*)qb_mlp_kernel<false, false, false, true>, (const void*)qb_mlp_kernel<true, true, false, false, 1>, (const void*)qb_mlp_kernel<true, true, false, false, 2>,
+                         (const void*)qb_mlp_kernel<true, true, false, false, 1, false, 1>,
+                         (const void*)qb_mlp_kernel<true, false, false, false, 3, true, 2>, (const void*)qb_mlp_kernel<true, false, false, false, 0, true, 2>,
+                         (const void*)qb_mlp_kernel<false, false, false, false, 0, true, 2>, (const void*)qb_mlp_kernel<false, false, false, true, 0, true, 2>,
                          (const void*)qb_mlp_kernel<true, false, false, false, 0, true>, (const void*)qb_mlp_kernel<false, false, false, false, 0, true>,
                          (const void*)qb_mlp_kernel<false, false, false, true, 0, true>,
                          (const void*)qb_mlp_kernel<true, false, false, false, 3, false>, (const void*)qb_mlp_kernel<true, false, false, false, 3, true>};
@@ -1905,11 +1981,19 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        static const bool fixed_ok = getenv("QB_NO_FIXED_SHAPE") == nullptr;
+        const bool l384 = fixed_ok && mcast && plan_is_l384(q.plan);
+        if (loop && l384) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, false, true, 0, true, 2>, q);
         if (loop && mcast) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, false, true, 0, true>, q);
         if (loop) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, false, true>, q);
         if (q.fuse == 3) {
+            if (l384) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, false, false, 3, true, 2>, q);
             if (mcast) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, false, false, 3, true>, q);
             return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, false, false, 3, false>, q);
+        }
+        if (l384) {
+            if (q.mode == QB_MODE_SCORE) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, false, false, 0, true, 2>, q);
+            return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, false, false, 0, true, 2>, q);
         }
         if (mcast) {
             if (q.mode == QB_MODE_SCORE) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, false, false, 0, true>, q);
@@ -1920,6 +2004,7 @@ cudaError_t launch_mlp(const MlpParams& p, int n_sm, cudaStream_t stream) {
             if (q.mode == QB_MODE_SCORE) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, false, true>, q);
             return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<false, false, true>, q);
         }
+        if (resident && q.fuse == 1 && fixed_ok && plan_is_s128(q.plan)) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, true, false, false, 1, false, 1>, q);
         if (resident && q.fuse == 1) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, true, false, false, 1>, q);
         if (resident && q.fuse == 2) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, true, false, false, 2>, q);
         if (resident) return cudaLaunchKernelEx(&cfg, qb_mlp_kernel<true, true, false>, q);
