@@ -1,5 +1,5 @@
-B="python bench.py --steps 4 --warmup 3 --no-extras --no-cpu-baseline --no-e2e --no-decode"
-$B --workload c3 > gpurun_out/ab_c3_fixed.json 2>gpurun_out/ab_c3_fixed.err
-QB_NO_FIXED_SHAPE=1 $B --workload c3 > gpurun_out/ab_c3_generic.json 2>/dev/null
-$B --workload c5 > gpurun_out/ab_c5_fixed.json 2>gpurun_out/ab_c5_fixed.err
-$B --workload c4 > gpurun_out/ab_c4_fixed.json 2>gpurun_out/ab_c4_fixed.err
+OUT=gpurun_out
+for w in c3 q1 c4 c5; do
+  timeout 110 python bench.py --workload $w --steps 3 --warmup 3 --no-extras > $OUT/r02_bench_$w.json 2> $OUT/r02_bench_$w.err
+done
+for w in c3 q1 c4 c5; do tail -1 $OUT/r02_bench_$w.json | cut -c1-120; done
