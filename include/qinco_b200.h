@@ -143,7 +143,8 @@ int qb_debug_step(qb_model* m, int step, const float* xhat_dev, const uint8_t* c
 
 /* Host-only test hooks (no CUDA call): export the tcgen05 op list of one step (32-byte QbOp records, csrc/qb_plan.h),
  * pack weights into the slab blob and build the hoisted tables, so the CPU test-suite can replay the kernel's dataflow
- * in numpy.  opts5 = {hc, n_tiles, slot_bytes, max_stage, max_slab_k} or NULL. */
+ * in numpy.  opts5 = {hc, n_tiles, slot_bytes, max_stage, max_slab_k} or NULL.  plan_out[29..31] = e_split, mcast and the
+ * compile-time plan view the kernels use for this plan (0 generic, 1 S128, 2 L384). */
 int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const int32_t* opts5, int32_t* plan_out,
                    int n_plan_out, void* ops_out, int max_ops);
 int qb_plan_pack(int D, int De, int Dh, int L, int K, int qinco1_mode, const int32_t* opts5, const float* const* up,

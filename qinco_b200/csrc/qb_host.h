@@ -33,6 +33,9 @@ float f16_to_f32(uint16_t h);
 int make_step_plan(int D, int De, int Dh, int L, int K, int qinco1_mode, const PlanOptions& opt, QbStepPlan* plan,
                    std::vector<QbOp>* ops, std::string* err);
 
+// which compile-time plan view (qb_mlp.cu: PlanView<kShape>) the kernels may use for this plan: 0 generic, 1 S128, 2 L384
+int mlp_plan_view(const QbStepPlan& plan);
+
 int pack_step_weights(const QbStepPlan& plan, const std::vector<QbOp>& ops, const float* const* up,
                       const float* const* down, const float* out_proj, uint16_t* blob, std::string* err);
 

@@ -1893,6 +1893,8 @@ __global__ void __launch_bounds__(kThreads, 1) qb_mlp_kernel(const __grid_consta
     }
 }
 
+int mlp_plan_view(const QbStepPlan& plan) { return plan_is_s128(plan) ? 1 : (plan_is_l384(plan) ? 2 : 0); }
+
 cudaError_t mlp_set_smem_attr(int smem_bytes) {
     // the attribute belongs to the function, not to a model: only ever raise it (several models share the process)
     static int current[64] = {0};

@@ -409,7 +409,8 @@ int qb_plan_export(int D, int De, int Dh, int L, int K, int qinco1_mode, const i
     const int32_t v[] = {p.D, p.De, p.Dh, p.L, p.K, p.has_proj, p.skip, p.n_tiles, p.tmem_alloc_cols,
                          p.n_ops_block, p.n_ops_out, p.hc, p.n_hchunk, p.oc, p.n_ochunk, p.tmem_e_col, p.tmem_h_col,
                          p.tmem_tile_cols, p.smem_tres, p.smem_ring, p.slot_bytes, p.n_stage, p.smem_total,
-                         (int32_t)p.block_w_bytes, (int32_t)p.w_blob_bytes, p.pair, p.h_split, p.n_ops_pre, p.ae_chunks};
+                         (int32_t)p.block_w_bytes, (int32_t)p.w_blob_bytes, p.pair, p.h_split, p.n_ops_pre, p.ae_chunks,
+                         p.e_split, p.mcast, qb::mlp_plan_view(p)};
     const int nv = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < nv && i < n_plan_out; i++) plan_out[i] = v[i];
     if ((int)ops.size() > max_ops) return -2;

@@ -20,7 +20,8 @@ OP_DTYPE = np.dtype([("w_off", "<u4"), ("slab_bytes", "<u4"), ("last_bytes", "<u
                      ("pad", "u1", 3)])
 PLAN_FIELDS = ["D", "De", "Dh", "L", "K", "has_proj", "skip", "n_tiles", "tmem_alloc_cols", "n_ops_block", "n_ops_out",
                "hc", "n_hchunk", "oc", "n_ochunk", "tmem_e_col", "tmem_h_col", "tmem_tile_cols", "smem_tres", "smem_ring",
-               "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes", "pair", "h_split", "n_ops_pre", "ae_chunks"]
+               "slot_bytes", "n_stage", "smem_total", "block_w_bytes", "w_blob_bytes", "pair", "h_split", "n_ops_pre", "ae_chunks",
+               "e_split", "mcast", "plan_view"]
 A_E, A_H = 0, 1
 BAR_AE_READY, BAR_AH_READY, BAR_HACC_FREE, BAR_HACC_FULL, BAR_EACC_FULL = 1, 2, 3, 4, 5
 
@@ -375,3 +376,23 @@ def test_library_override_must_exist(monkeypatch):
             _lib.load()
     finally:
         _lib._lib = saved
+
+
+@pytest.mark.parametrize("shape,view", [
+    (dict(D=128, de=128, dh=256, L=2), 1),                          # BASELINE config 2 (QINCo2-S)
+    (dict(D=128, de=128, dh=256, L=16, qinco1_mode=True), 1),       # config 1 (QINCo1)
+    (dict(D=128, de=384, dh=384, L=16), 2),                         # config 3 (QINCo2-L)
+    (dict(D=96, de=384, dh=384, L=16), 2),                          # config 4 (Deep1B shape)
+    (dict(D=768, de=384, dh=384, L=16), 2),                         # config 5 (Contriever shape)
+    (dict(D=64, de=64, dh=128, L=2), 0),                            # anything else: the generic kernels
+])
+def test_baseline_shapes_get_their_compile_time_plan_view(lib, shape, view):
+    """The fixed-shape kernels are only chosen when the planner's output matches their constants field by field; if the
+    planner changes, this test (not a silent 6-9 % slowdown) says so."""
+    cfg = synth.make_cfg(None, M=8, K=256, A=16, B=16, **shape)
+    plan, _ = export_plan(lib, cfg)
+    assert plan["plan_view"] == view, plan
+    if view == 2 and shape["D"] <= 128:       # the decode-loop plan of the L family uses the same view (its pre-ops are run-time
+        # fields); d = 768 has no decode-loop plan (out_proj in six chunks)
+        loop, _ = export_plan(lib, cfg, [plan["hc"], (1 << 8) | (2 << 16), plan["slot_bytes"], 1 << 10, 0])
+        assert loop["plan_view"] == 2 and loop["n_ops_pre"] > 0
